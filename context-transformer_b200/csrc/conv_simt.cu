@@ -1,0 +1,271 @@
+// conv_simt.cu — CUDA-core (fp32-accumulate) implicit-GEMM convolution, NHWC max-pool, layout
+// conversion and row softmax for sm_100a.
+//
+// Role: (1) the fp32 "parity" precision mode of the conv stack — every conv of
+// models/RFB_Net_vgg.py (BasicConv :7-22, vgg() :323-343, heads :387-416) evaluated in fp32 so the
+// 1e-4 parity bar against the fp32 reference is meaningful; (2) in the 16-bit throughput mode, the
+// geometries the tcgen05 kernel does not take (Cin = 3 stem, strided convs).
+//
+// GEMM view: M = N*Ho*Wo output pixels (flattened over the whole batch, so small late-pyramid maps
+// still fill tiles), N = Cout, K = KH*KW*Cin with k = tap*Cin + ci.  64x64x16 tiles, 256 threads,
+// 4x4 outputs per thread, operands staged in shared memory; activations NHWC so the K-run of one
+// tap is contiguous.  Epilogue: + bias (BatchNorm folded) [+ residual] [ReLU] -> up to three output
+// segments (lets loc/conf/obj heads land directly in their concatenated [B,P,*] buffers, the
+// permute(0,2,3,1).contiguous()+cat of RFB_Net_vgg.py:239-248 for free).
+#include "common.cuh"
+
+namespace ctx {
+
+constexpr int BM = 64, BN = 64, BK = 16, PADM = 68;
+
+struct ConvGeom {
+  int N, H, W, Cin, in_cstride, in_coffset, Cout, CoutP, KH, KW, stride, pad_h, pad_w, dil, Ho, Wo, relu;
+  int K, M;
+  int res_dtype, res_cstride, res_coffset;
+};
+
+template <typename TIn> struct Vec4Load;
+template <> struct Vec4Load<float> {
+  static __device__ __forceinline__ void load(const float* p, float* o) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+};
+template <> struct Vec4Load<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* o) {
+    uint2 v = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&v.x), b = *reinterpret_cast<__nv_bfloat162*>(&v.y);
+    o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
+  }
+};
+template <> struct Vec4Load<__half> {
+  static __device__ __forceinline__ void load(const __half* p, float* o) {
+    uint2 v = *reinterpret_cast<const uint2*>(p);
+    __half2 a = *reinterpret_cast<__half2*>(&v.x), b = *reinterpret_cast<__half2*>(&v.y);
+    o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
+  }
+};
+
+template <typename TIn, bool ALIGNED>
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const TIn* __restrict__ in, const float* __restrict__ wgt, const float* __restrict__ bias,
+                 const void* __restrict__ residual, ConvGeom g, SegTable segs) {
+  __shared__ __align__(16) float As[BK][PADM];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int tx = tid & 15, ty = tid >> 4;
+
+  // A-load role: pixel lm, k-sub [lk, lk+4)
+  const int lm = tid >> 2, lk = (tid & 3) * 4;
+  const int gm = m0 + lm;
+  const bool m_ok = gm < g.M;
+  int pn = 0, poy = 0, pox = 0;
+  if (m_ok) { pn = gm / (g.Ho * g.Wo); int r = gm - pn * g.Ho * g.Wo; poy = r / g.Wo; pox = r - poy * g.Wo; }
+  const int iy0 = poy * g.stride - g.pad_h, ix0 = pox * g.stride - g.pad_w;
+  // B-load role: k row bk, 4 consecutive couts
+  const int bk = tid >> 4, bn = (tid & 15) * 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    float av[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ALIGNED) {
+      // Cin % 16 == 0: the whole BK chunk lies inside one tap
+      const int tap = k0 / g.Cin, ci = k0 - tap * g.Cin + lk;
+      const int ky = tap / g.KW, kx = tap - ky * g.KW;
+      const int iy = iy0 + ky * g.dil, ix = ix0 + kx * g.dil;
+      if (m_ok && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+        Vec4Load<TIn>::load(in + ((size_t)(pn * g.H + iy) * g.W + ix) * g.in_cstride + g.in_coffset + ci, av);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k0 + lk + e;
+        if (m_ok && k < g.K) {
+          const int tap = k / g.Cin, ci = k - tap * g.Cin;
+          const int ky = tap / g.KW, kx = tap - ky * g.KW;
+          const int iy = iy0 + ky * g.dil, ix = ix0 + kx * g.dil;
+          if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+            av[e] = to_f32<TIn>(in[((size_t)(pn * g.H + iy) * g.W + ix) * g.in_cstride + g.in_coffset + ci]);
+        }
+      }
+    }
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k0 + bk < g.K && n0 + bn < g.CoutP)
+      bv = *reinterpret_cast<const float4*>(wgt + (size_t)(k0 + bk) * g.CoutP + n0 + bn);
+    __syncthreads();                 // previous tile fully consumed
+#pragma unroll
+    for (int e = 0; e < 4; ++e) As[lk + e][lm] = av[e];
+    *reinterpret_cast<float4*>(&Bs[bk][bn]) = bv;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+    const int n = m / (g.Ho * g.Wo);
+    const int pix = m - n * g.Ho * g.Wo;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= g.Cout) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[c];
+      if (residual) v += load_as(residual, (long long)m * g.res_cstride + g.res_coffset + c, g.res_dtype);
+      if (g.relu) v = fmaxf(v, 0.f);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        if (s < segs.nseg && c >= segs.seg[s].c_begin && c < segs.seg[s].c_end) {
+          const CtxOutSeg& sg = segs.seg[s];
+          store_as(sg.ptr, (long long)n * sg.img_stride + (long long)pix * sg.pix_stride + sg.ch_offset + (c - sg.c_begin),
+                   sg.dtype, v);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// nn.MaxPool2d on an NHWC view.  One thread per output element, channel fastest (coalesced).
+// Window clipped to the input (padding never wins; ceil_mode is resolved by the host in Ho/Wo).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_kernel(CtxPoolParams p) {
+  const long long total = (long long)p.N * p.Ho * p.Wo * p.C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % p.C);
+    long long r = i / p.C;
+    const int ox = (int)(r % p.Wo); r /= p.Wo;
+    const int oy = (int)(r % p.Ho);
+    const int n = (int)(r / p.Ho);
+    const int y0 = max(oy * p.stride - p.pad, 0), y1 = min(oy * p.stride - p.pad + p.k, p.H);
+    const int x0 = max(ox * p.stride - p.pad, 0), x1 = min(ox * p.stride - p.pad + p.k, p.W);
+    float m = -INFINITY;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x)
+        m = fmaxf(m, load_as(p.in, (long long)n * p.in_img_stride + (long long)(y * p.W + x) * p.in_pix_stride + c, p.dtype));
+    store_as(p.out, (long long)n * p.out_img_stride + (long long)(oy * p.Wo + ox) * p.out_pix_stride + c, p.dtype, m);
+  }
+}
+
+// x[N,C,H,W] fp32 -> NHWC (RFBNet.forward takes NCHW, RFB_Net_vgg.py:210)
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ in, void* __restrict__ out, int N, int C, int H, int W, int dtype) {
+  const long long hw = (long long)H * W, total = (long long)N * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / hw, r = i - n * hw;
+    for (int c = 0; c < C; ++c) store_as(out, i * C + c, dtype, in[(n * C + c) * hw + r]);
+  }
+}
+
+// softmax over the last dimension (output activation, RFB_Net_vgg.py:279-285); one thread per row
+__global__ void __launch_bounds__(256)
+softmax_lastdim_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int cols) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const float* x = in + r * cols;
+    float m = -INFINITY;
+    for (int c = 0; c < cols; ++c) m = fmaxf(m, x[c]);
+    float s = 0.f;
+    for (int c = 0; c < cols; ++c) s += expf(x[c] - m);
+    const float inv = 1.0f / s;
+    float* y = out + r * cols;
+    for (int c = 0; c < cols; ++c) y[c] = expf(x[c] - m) * inv;
+  }
+}
+
+static int validate_conv(const CtxConvParams* p) {
+  CTX_REQUIRE(p, "conv: null params");
+  CTX_REQUIRE(p->in && p->weight, "conv: null tensor pointer");
+  CTX_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0 && p->Cin > 0 && p->Cout > 0, "conv: bad dims");
+  CTX_REQUIRE(p->KH > 0 && p->KW > 0 && p->stride > 0 && p->dil > 0 && p->pad_h >= 0 && p->pad_w >= 0, "conv: bad geometry");
+  CTX_REQUIRE(p->in_cstride >= p->in_coffset + p->Cin, "conv: input channel slice out of range");
+  const int ho = (p->H + 2 * p->pad_h - p->dil * (p->KH - 1) - 1) / p->stride + 1;
+  const int wo = (p->W + 2 * p->pad_w - p->dil * (p->KW - 1) - 1) / p->stride + 1;
+  CTX_REQUIRE(ho == p->Ho && wo == p->Wo, "conv: Ho/Wo (%d,%d) inconsistent with geometry (%d,%d)", p->Ho, p->Wo, ho, wo);
+  CTX_REQUIRE(p->nseg >= 1 && p->nseg <= 3, "conv: nseg must be 1..3");
+  for (int s = 0; s < p->nseg; ++s)
+    CTX_REQUIRE(p->seg[s].ptr && p->seg[s].c_begin >= 0 && p->seg[s].c_end <= p->Cout && p->seg[s].c_begin < p->seg[s].c_end,
+                "conv: bad output segment %d", s);
+  return CTX_OK;
+}
+
+int conv_simt_launch(const CtxConvParams* p, cudaStream_t st) {
+  int rc = validate_conv(p);
+  if (rc) return rc;
+  ConvGeom g;
+  g.N = p->N; g.H = p->H; g.W = p->W; g.Cin = p->Cin; g.in_cstride = p->in_cstride; g.in_coffset = p->in_coffset;
+  g.Cout = p->Cout; g.CoutP = (p->Cout + 3) & ~3; g.KH = p->KH; g.KW = p->KW; g.stride = p->stride;
+  g.pad_h = p->pad_h; g.pad_w = p->pad_w; g.dil = p->dil; g.Ho = p->Ho; g.Wo = p->Wo; g.relu = p->relu;
+  g.K = p->KH * p->KW * p->Cin; g.M = p->N * p->Ho * p->Wo;
+  g.res_dtype = p->res_dtype; g.res_cstride = p->res_cstride; g.res_coffset = p->res_coffset;
+  SegTable segs; segs.nseg = p->nseg;
+  for (int s = 0; s < 3; ++s) segs.seg[s] = p->seg[s < p->nseg ? s : 0];
+  dim3 grid(cdiv(g.M, BM), cdiv(g.Cout, BN));
+  const bool aligned = (p->Cin % 16 == 0) && (p->in_cstride % 4 == 0) && (p->in_coffset % 4 == 0);
+  const float* w = (const float*)p->weight;
+#define LAUNCH(T, A) conv_simt_kernel<T, A><<<grid, 256, 0, st>>>((const T*)p->in, w, p->bias, p->residual, g, segs)
+  if (p->in_dtype == CTX_F32) { if (aligned) LAUNCH(float, true); else LAUNCH(float, false); }
+  else if (p->in_dtype == CTX_BF16) { if (aligned) LAUNCH(__nv_bfloat16, true); else LAUNCH(__nv_bfloat16, false); }
+  else if (p->in_dtype == CTX_F16) { if (aligned) LAUNCH(__half, true); else LAUNCH(__half, false); }
+  else { set_error("conv: bad in_dtype %d", p->in_dtype); return CTX_ERR_INVALID; }
+#undef LAUNCH
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
+int maxpool_launch(const CtxPoolParams* p, cudaStream_t st) {
+  CTX_REQUIRE(p && p->in && p->out, "maxpool: null pointer");
+  CTX_REQUIRE(p->N > 0 && p->C > 0 && p->k > 0 && p->stride > 0 && p->Ho > 0 && p->Wo > 0, "maxpool: bad dims");
+  CTX_REQUIRE((p->Ho - 1) * p->stride - p->pad < p->H && (p->Wo - 1) * p->stride - p->pad < p->W,
+              "maxpool: last window starts outside the input");
+  long long total = (long long)p->N * p->Ho * p->Wo * p->C;
+  int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+  maxpool_nhwc_kernel<<<blocks, 256, 0, st>>>(*p);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
+int nchw_to_nhwc_launch(const float* in, void* out, int N, int C, int H, int W, int dtype, cudaStream_t st) {
+  CTX_REQUIRE(in && out && N > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad arguments");
+  long long total = (long long)N * H * W;
+  int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+  nchw_to_nhwc_kernel<<<blocks, 256, 0, st>>>(in, out, N, C, H, W, dtype);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
+int softmax_launch(const float* in, float* out, long long rows, int cols, cudaStream_t st) {
+  CTX_REQUIRE(in && out && rows >= 0 && cols > 0, "softmax: bad arguments");
+  if (rows == 0) return CTX_OK;
+  int blocks = (int)std::min<long long>((rows + 255) / 256, 148LL * 32);
+  softmax_lastdim_kernel<<<blocks, 256, 0, st>>>(in, out, rows, cols);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
+}  // namespace ctx
+
+extern "C" int ctx_conv2d_simt(const CtxConvParams* p, void* stream) { return ctx::conv_simt_launch(p, (cudaStream_t)stream); }
+extern "C" int ctx_maxpool2d_nhwc(const CtxPoolParams* p, void* stream) { return ctx::maxpool_launch(p, (cudaStream_t)stream); }
+extern "C" int ctx_nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, int out_dtype, void* stream) {
+  return ctx::nchw_to_nhwc_launch(in, out, N, C, H, W, out_dtype, (cudaStream_t)stream);
+}
+extern "C" int ctx_softmax_lastdim(const float* in, float* out, long long rows, int cols, void* stream) {
+  return ctx::softmax_launch(in, out, rows, cols, (cudaStream_t)stream);
+}

@@ -1,0 +1,174 @@
+// train.cu — target assignment and hard-negative ranking of the few-shot fine-tune loop for sm_100a.
+//
+// Replaces, batched and on device:
+//   utils/box_utils.py:83-132 (match), :5-14 (point_form), :29-68 (intersect / jaccard),
+//   :135-156 (encode)  — the per-image python loop of multibox_loss_combined.py:70-74;
+//   layers/modules/multibox_loss_combined.py:91-93 (the two full sorts that turn the mining loss
+//   into a rank).
+//
+// Integer results (matched truth index, labels, obj flags, ranks) are bit-exact against the CPU
+// oracle: every IoU is evaluated in fp32 with explicit round-to-nearest intrinsics in the
+// reference's operation order, arg-max ties resolve to the first index (torch.max on CPU), and the
+// forced matches are applied in ground-truth order so the last ground truth wins a collision
+// (box_utils.py:122-123).
+#include "common.cuh"
+#include "sort.cuh"
+
+namespace ctx {
+
+constexpr int kMatchThreads = 1024;
+constexpr int kMaxObj = 128;
+
+// jaccard of a ground-truth box (corner form) and a prior (corner form) — box_utils.py:29-68
+__device__ __forceinline__ float jaccard_one(float4 t, float area_t, float4 p) {
+  float w = fmaxf(__fsub_rn(fminf(t.z, p.z), fmaxf(t.x, p.x)), 0.0f);
+  float h = fmaxf(__fsub_rn(fminf(t.w, p.w), fmaxf(t.y, p.y)), 0.0f);
+  float inter = __fmul_rn(w, h);
+  float area_p = __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y));
+  float uni = __fsub_rn(__fadd_rn(area_t, area_p), inter);
+  return __fdiv_rn(inter, uni);
+}
+
+// point_form — box_utils.py:5-14
+__device__ __forceinline__ float4 point_form(float4 p) {
+  float hw = __fmul_rn(p.z, 0.5f), hh = __fmul_rn(p.w, 0.5f);
+  return make_float4(__fsub_rn(p.x, hw), __fsub_rn(p.y, hh), __fadd_rn(p.x, hw), __fadd_rn(p.y, hh));
+}
+
+// One CTA per image.
+__global__ void __launch_bounds__(kMatchThreads)
+match_encode_kernel(const float* __restrict__ truths, const int* __restrict__ num_obj, int max_obj,
+                    const float* __restrict__ priors, int P, float threshold, float v0, float v1,
+                    float* __restrict__ loc_t, float* __restrict__ conf_t, unsigned char* __restrict__ obj_t,
+                    int* __restrict__ best_truth_idx_out, float* __restrict__ best_truth_overlap_out) {
+  __shared__ float s_t[kMaxObj][6];
+  __shared__ float s_area[kMaxObj];
+  __shared__ int s_best_prior[kMaxObj];
+  __shared__ unsigned long long s_red[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int n = num_obj ? num_obj[b] : max_obj;
+  n = min(max(n, 0), min(max_obj, kMaxObj));
+  for (int i = tid; i < n * 6; i += blockDim.x) s_t[i / 6][i % 6] = truths[((size_t)b * max_obj) * 6 + i];
+  __syncthreads();
+  if (tid < n) s_area[tid] = __fmul_rn(__fsub_rn(s_t[tid][2], s_t[tid][0]), __fsub_rn(s_t[tid][3], s_t[tid][1]));
+  __syncthreads();
+
+  // best prior per ground truth: arg-max over priors, first index on ties (box_utils.py:108)
+  for (int j = 0; j < n; ++j) {
+    const float4 t = make_float4(s_t[j][0], s_t[j][1], s_t[j][2], s_t[j][3]);
+    const float at = s_area[j];
+    unsigned long long best = 0ull;                 // (iou bits << 32) | (~p): max == larger iou, then smaller p
+    for (int p = tid; p < P; p += blockDim.x) {
+      float4 pr = point_form(reinterpret_cast<const float4*>(priors)[p]);
+      float ov = jaccard_one(t, at, pr);
+      unsigned long long key = ((unsigned long long)float_order_bits(ov) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)p);
+      best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (lane == 0) s_red[warp] = best;
+    __syncthreads();
+    if (warp == 0) {
+      best = lane < (int)(blockDim.x >> 5) ? s_red[lane] : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+      }
+      if (lane == 0) s_best_prior[j] = (int)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull));
+    }
+    __syncthreads();
+  }
+
+  // best truth per prior (first index on ties, :110), forced matches (:119-123), labels, encode
+  for (int p = tid; p < P; p += blockDim.x) {
+    const float4 pc = reinterpret_cast<const float4*>(priors)[p];
+    const float4 pr = point_form(pc);
+    float best_ov = -INFINITY;
+    int best_j = 0;
+    for (int j = 0; j < n; ++j) {
+      float ov = jaccard_one(make_float4(s_t[j][0], s_t[j][1], s_t[j][2], s_t[j][3]), s_area[j], pr);
+      if (ov > best_ov) { best_ov = ov; best_j = j; }
+    }
+    const size_t at = (size_t)b * P + p;
+    if (best_truth_overlap_out) best_truth_overlap_out[at] = n > 0 ? best_ov : 0.f;   // `overlap[idx]`, :115-116
+    for (int j = 0; j < n; ++j)
+      if (s_best_prior[j] == p) { best_ov = 2.0f; best_j = j; }
+    float label = 0.f, weight = 1.f;
+    float4 enc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n > 0) {
+      label = s_t[best_j][4]; weight = s_t[best_j][5];
+      if (best_ov < threshold) { label = 0.f; weight = 1.f; }
+      // encode — box_utils.py:135-156
+      const float mx1 = s_t[best_j][0], my1 = s_t[best_j][1], mx2 = s_t[best_j][2], my2 = s_t[best_j][3];
+      float gx = __fsub_rn(__fmul_rn(__fadd_rn(mx1, mx2), 0.5f), pc.x);
+      float gy = __fsub_rn(__fmul_rn(__fadd_rn(my1, my2), 0.5f), pc.y);
+      gx = __fdiv_rn(gx, __fmul_rn(v0, pc.z));
+      gy = __fdiv_rn(gy, __fmul_rn(v0, pc.w));
+      float gw = __fdiv_rn(logf(__fdiv_rn(__fsub_rn(mx2, mx1), pc.z)), v1);
+      float gh = __fdiv_rn(logf(__fdiv_rn(__fsub_rn(my2, my1), pc.w)), v1);
+      enc = make_float4(gx, gy, gw, gh);
+    }
+    reinterpret_cast<float4*>(loc_t)[at] = enc;
+    reinterpret_cast<float2*>(conf_t)[at] = make_float2(label, weight);
+    obj_t[at] = label != 0.f ? 1 : 0;
+    if (best_truth_idx_out) best_truth_idx_out[at] = best_j;
+  }
+}
+
+// One CTA per image: rank[p] = position of p in the stable descending sort of loss[b, :].
+__global__ void __launch_bounds__(1024)
+hard_negative_rank_kernel(const float* __restrict__ loss, int P, int key_stride, uint64_t* __restrict__ keys_ws,
+                          int* __restrict__ rank) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw);
+  const int b = blockIdx.x;
+  uint64_t* gkeys = keys_ws + (size_t)b * key_stride;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) gkeys[p] = make_key(loss[(size_t)b * P + p], (uint32_t)p);
+  __syncthreads();
+  const uint64_t* sorted = block_sort_desc(gkeys, P, skeys);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) rank[(size_t)b * P + key_index(sorted[i])] = i;
+}
+
+}  // namespace ctx
+
+using namespace ctx;
+
+extern "C" int ctx_match_encode(const float* truths, const int* num_obj, int max_obj, const float* priors, int batch,
+                                int num_priors, float threshold, float var0, float var1, float* loc_t, float* conf_t,
+                                unsigned char* obj_t, int* best_truth_idx, float* best_truth_overlap, void* stream) {
+  CTX_REQUIRE(batch >= 0 && num_priors >= 1 && max_obj >= 0, "ctx_match_encode: bad sizes");
+  CTX_REQUIRE(max_obj <= kMaxObj, "ctx_match_encode: max_obj %d exceeds the supported %d", max_obj, kMaxObj);
+  CTX_REQUIRE(priors && loc_t && conf_t && obj_t && (truths || max_obj == 0), "ctx_match_encode: null pointer");
+  if (batch == 0) return CTX_OK;
+  match_encode_kernel<<<batch, kMatchThreads, 0, (cudaStream_t)stream>>>(truths, num_obj, max_obj, priors, num_priors,
+                                                                        threshold, var0, var1, loc_t, conf_t, obj_t,
+                                                                        best_truth_idx, best_truth_overlap);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
+extern "C" size_t ctx_rank_workspace_bytes(int batch, int num_priors) {
+  if (batch <= 0 || num_priors <= 0) return 256;
+  return align_up(sizeof(uint64_t) * (size_t)batch * next_pow2(num_priors), 256);
+}
+
+extern "C" int ctx_hard_negative_rank(const float* loss, int batch, int num_priors, int* rank, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  CTX_REQUIRE(batch >= 0 && num_priors >= 1, "ctx_hard_negative_rank: bad sizes");
+  CTX_REQUIRE(loss && rank, "ctx_hard_negative_rank: null pointer");
+  if (batch == 0) return CTX_OK;
+  const size_t need = ctx_rank_workspace_bytes(batch, num_priors);
+  if (!workspace || workspace_bytes < need) {
+    set_error("ctx_hard_negative_rank: workspace %zu < required %zu", workspace_bytes, need);
+    return CTX_ERR_WORKSPACE;
+  }
+  const int smem = kSortSmem * (int)sizeof(uint64_t);
+  hard_negative_rank_kernel<<<batch, 1024, smem, (cudaStream_t)stream>>>(loss, num_priors, next_pow2(num_priors),
+                                                                         (uint64_t*)workspace, rank);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}

@@ -1,0 +1,137 @@
+"""``Detect`` and the fused post-processing of the inference path.
+
+``Detect`` mirrors reference ``layers/functions/detection.py:6-55``: same constructor
+``Detect(num_classes, bkg_label, cfg)``, same plain-method call ``detector.forward(predictions,
+prior)`` returning ``(boxes[B,P,4], scores[B,P,num_classes])`` on the device of ``loc``, fresh
+tensors each call, also kept on ``self.boxes`` / ``self.scores``.  Like the reference it does NOT
+threshold or suppress.  The arithmetic (``decode`` of utils/box_utils.py:184-202, score combine
+``cat(obj0, obj1*conf)``) runs in one CUDA kernel for the whole batch (``ctx_detect_forward``)
+instead of a Python loop over images.
+
+``DetectPost`` is the device-resident replacement of the numpy loop that follows ``Detect`` in
+reference ``test.py:133-161`` (pixel scale, per-class ``score > thresh``, ``nms``, per-image
+``max_per_image`` cut): one call, fixed-shape records out, no host round trips.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+NMS_HARD, NMS_SOFT_LINEAR, NMS_SOFT_GAUSSIAN, NMS_SOFT_HARD = 0, 1, 2, 3
+
+
+def _f32c(t, name):
+    _lib.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class Detect(object):
+    def __init__(self, num_classes, bkg_label, cfg):
+        self.num_classes = num_classes
+        self.background_label = bkg_label
+        self.variance = cfg['variance']
+
+    def forward(self, predictions, prior):
+        loc, conf, obj = predictions
+        loc_data = _f32c(loc.detach(), 'loc')
+        conf_data = _f32c(conf.detach(), 'conf')
+        obj_data = _f32c(obj.detach(), 'obj')
+        prior_data = _f32c(prior.detach().to(loc_data.device), 'prior')
+        num = loc_data.size(0)
+        self.num_priors = prior_data.size(0)
+        if conf_data.size(-1) != self.num_classes - 1:
+            raise ValueError('Detect: conf has %d classes, expected num_classes-1 = %d'
+                             % (conf_data.size(-1), self.num_classes - 1))
+        self.boxes = torch.empty(num, self.num_priors, 4, device=loc_data.device)
+        self.scores = torch.empty(num, self.num_priors, self.num_classes, device=loc_data.device)
+        with torch.cuda.device(loc_data.device):
+            _lib.check(_lib.lib().ctx_detect_forward(
+                loc_data.data_ptr(), conf_data.data_ptr(), obj_data.data_ptr(), prior_data.data_ptr(),
+                num, self.num_priors, self.num_classes - 1, float(self.variance[0]), float(self.variance[1]),
+                self.boxes.data_ptr(), self.scores.data_ptr(), _lib.current_stream_ptr()), 'ctx_detect_forward')
+        return self.boxes, self.scores
+
+    __call__ = forward
+
+
+class DetectPost(object):
+    """Fused decode + score + per-class (soft-)NMS + top-k (reference test.py:133-161).
+
+    forward(predictions, prior, scale) -> (records[B,max_out,6], counts[B], prior_idx[B,max_out])
+      records rows are (x1, y1, x2, y2, score, class) in pixel units, ordered class ascending then
+      score descending — exactly the rows ``all_boxes[j][i]`` of test.py would hold, flattened.
+      ``counts[b]`` is the number of detections the reference keeps (ties at the top-k threshold
+      can exceed ``max_per_image``; rows beyond ``max_out`` are dropped).
+    ``scale`` is ``[w, h, w, h]`` (one for the batch) or ``[B,4]`` (test.py:123-124).
+    ``suppress_on_equal`` selects the reference's CPU NMS convention (``ovr >= thresh``,
+    cpu_nms.pyx:65) instead of the GPU/python one (``>``, nms_kernel.cu:71).
+    """
+
+    def __init__(self, num_classes, bkg_label, cfg, score_thresh=0.01, nms_thresh=0.45, max_per_image=200,
+                 max_out=None, suppress_on_equal=False, nms_method=NMS_HARD, soft_sigma=0.5, soft_threshold=0.001):
+        self.num_classes = num_classes
+        self.background_label = bkg_label
+        self.variance = cfg['variance']
+        self.score_thresh = score_thresh
+        self.nms_thresh = nms_thresh
+        self.max_per_image = max_per_image
+        self.max_out = max_out if max_out is not None else (max_per_image + 56 if max_per_image > 0 else 1024)
+        self.suppress_on_equal = suppress_on_equal
+        self.nms_method = nms_method
+        self.soft_sigma = soft_sigma
+        self.soft_threshold = soft_threshold
+        self._ws = None
+
+    def forward(self, predictions, prior, scale):
+        loc, conf, obj = predictions
+        loc = _f32c(loc.detach(), 'loc')
+        conf = _f32c(conf.detach(), 'conf')
+        obj = _f32c(obj.detach(), 'obj')
+        dev = loc.device
+        prior = _f32c(prior.detach().to(dev), 'prior')
+        B, P = loc.size(0), prior.size(0)
+        Cfg = self.num_classes - 1
+        if conf.size(-1) != Cfg:
+            raise ValueError('DetectPost: conf has %d classes, expected %d' % (conf.size(-1), Cfg))
+        scale = torch.as_tensor(scale, dtype=torch.float32).to(dev).contiguous()
+        per_image = int(scale.dim() == 2)
+        if per_image and scale.size(0) != B:
+            raise ValueError('DetectPost: scale must be [4] or [B,4]')
+        p = _lib.CtxPostParams(B, P, Cfg, float(self.variance[0]), float(self.variance[1]), per_image,
+                               float(self.score_thresh), float(self.nms_thresh), int(self.suppress_on_equal),
+                               int(self.nms_method), float(self.soft_sigma), float(self.soft_threshold),
+                               int(self.max_per_image), int(self.max_out))
+        L = _lib.lib()
+        need = L.ctx_postprocess_workspace_bytes(B, P, Cfg)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        records = torch.zeros(B, self.max_out, 6, device=dev)
+        counts = torch.zeros(B, dtype=torch.int32, device=dev)
+        prior_idx = torch.full((B, self.max_out), -1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.ctx_detect_postprocess(
+                loc.data_ptr(), conf.data_ptr(), obj.data_ptr(), prior.data_ptr(), scale.data_ptr(), C.byref(p),
+                records.data_ptr(), counts.data_ptr(), prior_idx.data_ptr(),
+                self._ws.data_ptr(), self._ws.numel(), _lib.current_stream_ptr()), 'ctx_detect_postprocess')
+        return records, counts, prior_idx
+
+    __call__ = forward
+
+
+def records_to_all_boxes(records, counts, num_classes):
+    """Host-side view of the records in the reference's result structure (test.py:107-108,154):
+    ``all_boxes[j][i]`` = float32 ndarray [k,5] for class j, image i."""
+    import numpy as np
+    rec = records.cpu().numpy()
+    cnt = counts.cpu().numpy()
+    B = rec.shape[0]
+    all_boxes = [[np.empty((0, 5), dtype=np.float32) for _ in range(B)] for _ in range(num_classes)]
+    for i in range(B):
+        r = rec[i, :min(int(cnt[i]), rec.shape[1])]
+        cls = r[:, 5].astype(np.int64)
+        for j in np.unique(cls):
+            all_boxes[j][i] = r[cls == j, :5].copy()
+    return all_boxes

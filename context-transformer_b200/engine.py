@@ -1,0 +1,387 @@
+"""``Engine`` — compiles an ``RFBNet`` (eval mode) into a flat program of sm_100a kernels.
+
+One engine = one (batch, precision, device).  Building it
+  * folds every BatchNorm (running stats, eps 1e-5) and bias into a per-channel fp32 epilogue
+    vector and packs the conv weights in the kernels' layouts (device-side tensor ops, once);
+  * allocates every activation once, NHWC (channels-last), in the engine's precision, so that the
+    reference's ``permute(0,2,3,1).contiguous()`` + ``cat`` of the head outputs
+    (models/RFB_Net_vgg.py:239-248) is just where the head conv's epilogue writes;
+  * turns each RFB block (:26-112) into branch convs whose last conv writes its slice of the
+    concat buffer, a shortcut conv, and a ConvLinear conv whose epilogue adds the shortcut and
+    applies the ReLU (``out*scale + short`` with ``scale`` folded into the weights);
+  * evaluates loc / conf / obj of a level as ONE 3x3 conv with three output segments (the
+    reference runs the conf conv twice in phase-2 'ours', :240,243);
+  * adds the conf max-pool (ceil_mode, :242-244), the fused Context-Transformer kernel (:253-271)
+    and the output softmaxes (:279-285);
+and records all of it in a ``ctx_prog`` (csrc/prog.cu), optionally captured into a CUDA graph.
+``run(x)`` copies the input into the program's static input buffer and replays the program.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .rfb_net import CONF_POOL, SOURCE_SPLIT, BasicConv, _RFBBlock
+
+_DT = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'fp16': torch.float16}
+
+
+class View(object):
+    """A [N,H,W,C] channels-last activation living at channel offset ``coff`` of a buffer whose
+    pixels are ``cstride`` channels wide."""
+    __slots__ = ('buf', 'N', 'H', 'W', 'C', 'cstride', 'coff')
+
+    def __init__(self, buf, N, H, W, C, cstride=None, coff=0):
+        self.buf, self.N, self.H, self.W, self.C = buf, N, H, W, C
+        self.cstride = C if cstride is None else cstride
+        self.coff = coff
+
+    def slice(self, off, c):
+        return View(self.buf, self.N, self.H, self.W, c, self.cstride, self.coff + off)
+
+    def tensor(self):
+        return self.buf.view(self.N, self.H, self.W, self.cstride)[..., self.coff:self.coff + self.C]
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def _pool_out(h, k, s, pad, ceil_mode):
+    if ceil_mode:
+        o = int(math.ceil((h + 2 * pad - k) / float(s))) + 1
+        if (o - 1) * s >= h + pad:
+            o -= 1
+    else:
+        o = (h + 2 * pad - k) // s + 1
+    return o
+
+
+class Engine(object):
+    def __init__(self, net, batch, precision, device, use_graph=True):
+        if precision not in _DT:
+            raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
+        if not torch.cuda.is_available():
+            raise _lib.CtxError('no CUDA device: the detection hot path has no CPU fallback')
+        self.L = _lib.lib()
+        self.dev = torch.device(device)
+        if self.dev.type != 'cuda':
+            raise _lib.CtxError('Engine needs a CUDA device, got %s' % device)
+        if self.dev.index is None:
+            self.dev = torch.device('cuda', torch.cuda.current_device())
+        self.net_version = self._version_of(net)
+        self.batch = batch
+        self.precision = precision
+        self.act_dtype = _DT[precision]
+        self.act_code = _lib.dtype_code(self.act_dtype)
+        self.keep = []                       # tensors whose raw pointers the program holds
+        self.layers = []                     # (name, kind, flops) per op, for the benchmark / ncu tables
+        self.prog = C.c_void_p()
+        _lib.check(self.L.ctx_prog_create(C.byref(self.prog)), 'ctx_prog_create')
+        self.graph_ready = False
+        self.use_graph = use_graph
+        self.stream = torch.cuda.Stream(device=self.dev)
+        with torch.cuda.device(self.dev), torch.no_grad():
+            self._compile(net)
+
+    def __del__(self):
+        try:
+            if self.prog:
+                self.L.ctx_prog_destroy(self.prog)
+                self.prog = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _version_of(net):
+        return tuple((t.data_ptr(), t._version) for t in list(net.parameters()) + list(net.buffers()))
+
+    def stale(self, net):
+        return self._version_of(net) != self.net_version
+
+    def _alloc(self, *shape, dtype=None):
+        t = torch.empty(*shape, dtype=dtype or self.act_dtype, device=self.dev)
+        self.keep.append(t)
+        return t
+
+    def _new_view(self, N, H, W, C):
+        return View(self._alloc(N * H * W * C), N, H, W, C)
+
+    # ------------------------------------------------------------------------------------------
+    def _fold(self, conv, bn, scale=1.0):
+        w = conv.weight.detach().to(self.dev, torch.float32)
+        if bn is not None:
+            s = bn.weight.detach().to(self.dev, torch.float32) / torch.sqrt(
+                bn.running_var.detach().to(self.dev, torch.float32) + bn.eps)
+            b = bn.bias.detach().to(self.dev, torch.float32) - bn.running_mean.detach().to(self.dev, torch.float32) * s
+            w = w * s.view(-1, 1, 1, 1)
+        elif conv.bias is not None:
+            b = conv.bias.detach().to(self.dev, torch.float32)
+        else:
+            b = torch.zeros(w.size(0), device=self.dev)
+        if scale != 1.0:
+            w, b = w * scale, b * scale
+        return w, b
+
+    def _emit_conv(self, name, src, w, b, stride, pad, dil, relu, segs=None, out=None, residual=None):
+        """w: folded fp32 [Cout,Cin,KH,KW]; b: fp32 [Cout].  segs: list of (tensor, c_begin, c_end, img_stride,
+        pix_stride, ch_offset) for multi-destination epilogues; otherwise writes ``out`` (a View) or a new one."""
+        Cout, Cin, KH, KW = w.shape
+        assert Cin == src.C, (name, Cin, src.C)
+        ph, pw = pad
+        Ho = (src.H + 2 * ph - dil * (KH - 1) - 1) // stride + 1
+        Wo = (src.W + 2 * pw - dil * (KW - 1) - 1) // stride + 1
+        p = _lib.CtxConvParams()
+        p.N, p.H, p.W, p.Cin = src.N, src.H, src.W, Cin
+        p.in_cstride, p.in_coffset = src.cstride, src.coff
+        p.Cout, p.KH, p.KW, p.stride, p.pad_h, p.pad_w, p.dil = Cout, KH, KW, stride, ph, pw, dil
+        p.Ho, p.Wo, p.relu = Ho, Wo, int(relu)
+        p.in_dtype = _lib.dtype_code(src.buf.dtype)
+        setattr(p, 'in', src.buf.data_ptr())
+        bias = b.contiguous()
+        self.keep.append(bias)
+        p.bias = bias.data_ptr()
+        if residual is not None:
+            assert (residual.N, residual.H, residual.W, residual.C) == (src.N, Ho, Wo, Cout)
+            p.residual = residual.buf.data_ptr()
+            p.res_dtype = _lib.dtype_code(residual.buf.dtype)
+            p.res_cstride, p.res_coffset = residual.cstride, residual.coff
+        result = None
+        if segs is None:
+            if out is None:
+                out = self._new_view(src.N, Ho, Wo, Cout)
+            assert (out.N, out.H, out.W, out.C) == (src.N, Ho, Wo, Cout), name
+            segs = [(out.buf, 0, Cout, Ho * Wo * out.cstride, out.cstride, out.coff)]
+            result = out
+        p.nseg = len(segs)
+        for i, (t, c0, c1, img_stride, pix_stride, ch_off) in enumerate(segs):
+            p.seg[i].ptr = t.data_ptr()
+            p.seg[i].c_begin, p.seg[i].c_end = c0, c1
+            p.seg[i].img_stride, p.seg[i].pix_stride, p.seg[i].ch_offset = img_stride, pix_stride, ch_off
+            p.seg[i].dtype = _lib.dtype_code(t.dtype)
+        flops = 2.0 * src.N * Ho * Wo * Cout * Cin * KH * KW
+        use_tc = self.precision != 'fp32' and self.L.ctx_conv2d_tc_supported(C.byref(p)) == 1
+        if use_tc:
+            cin_p = (Cin + 63) // 64 * 64 if Cin > 32 else ((Cin + 15) // 16 * 16)
+            cout_p = (Cout + 15) // 16 * 16
+            wt = torch.zeros(cout_p, KH * KW, cin_p, dtype=self.act_dtype, device=self.dev)
+            wt[:Cout, :, :Cin] = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin).to(self.act_dtype)
+            self.keep.append(wt)
+            p.weight = wt.data_ptr()
+            _lib.check(self.L.ctx_prog_add_conv_tc(self.prog, C.byref(p)), 'ctx_prog_add_conv_tc(%s)' % name)
+            kind = 'conv_tc'
+        else:
+            cout_p = (Cout + 3) // 4 * 4
+            wt = torch.zeros(KH * KW * Cin, cout_p, dtype=torch.float32, device=self.dev)
+            wt[:, :Cout] = w.permute(2, 3, 1, 0).reshape(KH * KW * Cin, Cout)
+            self.keep.append(wt)
+            p.weight = wt.data_ptr()
+            _lib.check(self.L.ctx_prog_add_conv_simt(self.prog, C.byref(p)), 'ctx_prog_add_conv_simt(%s)' % name)
+            kind = 'conv_simt'
+        self.layers.append((name, kind, flops, (src.N, src.H, src.W, Cin, Cout, KH, KW, stride, dil)))
+        return result
+
+    def _emit_pool(self, name, src, k, s, pad, ceil_mode, out=None, in_img_stride=None, out_img_stride=None):
+        Ho, Wo = _pool_out(src.H, k, s, pad, ceil_mode), _pool_out(src.W, k, s, pad, ceil_mode)
+        if out is None:
+            out = self._new_view(src.N, Ho, Wo, src.C)
+        p = _lib.CtxPoolParams()
+        p.N, p.H, p.W, p.C, p.Ho, p.Wo, p.k, p.stride, p.pad = src.N, src.H, src.W, src.C, Ho, Wo, k, s, pad
+        p.dtype = _lib.dtype_code(src.buf.dtype)
+        esz = src.buf.element_size()
+        setattr(p, 'in', src.buf.data_ptr() + src.coff * esz)
+        p.in_img_stride = in_img_stride if in_img_stride is not None else src.H * src.W * src.cstride
+        p.in_pix_stride = src.cstride
+        p.out = out.buf.data_ptr() + out.coff * out.buf.element_size()
+        p.out_img_stride = out_img_stride if out_img_stride is not None else Ho * Wo * out.cstride
+        p.out_pix_stride = out.cstride
+        _lib.check(self.L.ctx_prog_add_pool(self.prog, C.byref(p)), 'ctx_prog_add_pool(%s)' % name)
+        self.layers.append((name, 'pool', 0.0, (src.N, src.H, src.W, src.C, k, s)))
+        return out
+
+    def _basic_conv(self, name, m, src, out=None, residual=None, relu=None, scale=1.0):
+        w, b = self._fold(m.conv, m.bn, scale)
+        c = m.conv
+        return self._emit_conv(name, src, w, b, c.stride[0], _pair(c.padding), c.dilation[0],
+                               (m.relu is not None) if relu is None else relu, out=out, residual=residual)
+
+    def _rfb(self, name, m, src):
+        branches = m.branches()
+        stride = m.shortcut.conv.stride[0]
+        Ho = (src.H - 1) // stride + 1
+        Wo = (src.W - 1) // stride + 1
+        cat_c = sum(br[-1].out_channels for br in branches)
+        cat = self._new_view(src.N, Ho, Wo, cat_c)
+        off = 0
+        for bi, br in enumerate(branches):
+            t = src
+            for li, layer in enumerate(br):
+                last = li == len(br) - 1
+                t = self._basic_conv('%s.branch%d.%d' % (name, bi, li), layer, t,
+                                     out=cat.slice(off, layer.out_channels) if last else None)
+            off += br[-1].out_channels
+        short = self._basic_conv(name + '.shortcut', m.shortcut, src)
+        # relu(ConvLinear(cat) * scale + short): scale folds into the weights, the add + ReLU into the epilogue
+        return self._basic_conv(name + '.ConvLinear', m.ConvLinear, cat, residual=short, relu=True, scale=float(m.scale))
+
+    # ------------------------------------------------------------------------------------------
+    def _compile(self, net):
+        B, S = self.batch, net.size
+        self.x_in = self._alloc(B, 3, S, S, dtype=torch.float32)
+        x = self._new_view(B, S, S, 3)
+        _lib.check(self.L.ctx_prog_add_nchw_to_nhwc(self.prog, self.x_in.data_ptr(), x.buf.data_ptr(), B, 3, S, S,
+                                                    self.act_code), 'ctx_prog_add_nchw_to_nhwc')
+        self.layers.append(('input.nhwc', 'layout', 0.0, (B, 3, S, S)))
+        sources = []
+
+        def run_base(lo, hi, x):
+            k = lo
+            while k < hi:
+                m = net.base[k]
+                if isinstance(m, nn.Conv2d):
+                    relu = k + 1 < len(net.base) and isinstance(net.base[k + 1], nn.ReLU)
+                    w, b = self._fold(m, None)
+                    x = self._emit_conv('base.%d' % k, x, w, b, m.stride[0], _pair(m.padding), m.dilation[0], relu)
+                    k += 2 if relu else 1
+                elif isinstance(m, nn.MaxPool2d):
+                    x = self._emit_pool('base.%d' % k, x, m.kernel_size, m.stride, m.padding, m.ceil_mode)
+                    k += 1
+                elif isinstance(m, nn.ReLU):
+                    raise _lib.CtxError('base.%d: ReLU without a preceding conv' % k)
+                else:
+                    raise _lib.CtxError('base.%d: unsupported module %s' % (k, type(m).__name__))
+            return x
+
+        x = run_base(0, SOURCE_SPLIT, x)
+        sources.append(self._rfb('Norm', net.Norm, x))
+        x = run_base(SOURCE_SPLIT, len(net.base), x)
+        for k, m in enumerate(net.extras):
+            if isinstance(m, _RFBBlock):
+                x = self._rfb('extras.%d' % k, m, x)
+            elif isinstance(m, BasicConv):
+                x = self._basic_conv('extras.%d' % k, m, x)
+            else:
+                raise _lib.CtxError('extras.%d: unsupported module %s' % (k, type(m).__name__))
+            if k < net.indicator or k % 2 == 0:
+                sources.append(x)
+
+        # ---- heads: one conv per level, three output segments -----------------------------------
+        Csrc = net.num_classes
+        anchors = [l.out_channels // 4 for l in net.loc]
+        level_p = [s.H * s.W * a for s, a in zip(sources, anchors)]
+        P = sum(level_p)
+        self.num_priors = P
+        ours = net.ours
+        if ours and len(sources) > len(CONF_POOL):
+            raise IndexError('Context-Transformer pooling is defined for 6 pyramid levels only (size 300); size %d '
+                             'has %d (undefined upstream as well, RFB_Net_vgg.py:235-243)' % (S, len(sources)))
+        self.loc = self._alloc(B, P, 4, dtype=torch.float32)
+        self.conf_raw = self._alloc(B, P, Csrc, dtype=torch.float32)
+        self.obj_raw = self._alloc(B, P, 2, dtype=torch.float32)
+        poff = 0
+        pooled_shapes = []
+        for i, (s, a) in enumerate(zip(sources, anchors)):
+            wl, bl = self._fold(net.loc[i], None)
+            wc, bc = self._fold(net.conf[i], None)
+            wo, bo = self._fold(net.obj[i], None)
+            w = torch.cat([wl, wc, wo], 0)
+            b = torch.cat([bl, bc, bo], 0)
+            c1, c2, c3 = a * 4, a * 4 + a * Csrc, a * 4 + a * Csrc + a * 2
+            segs = [(self.loc.view(-1)[poff * 4:], 0, c1, P * 4, a * 4, 0),
+                    (self.conf_raw.view(-1)[poff * Csrc:], c1, c2, P * Csrc, a * Csrc, 0),
+                    (self.obj_raw.view(-1)[poff * 2:], c2, c3, P * 2, a * 2, 0)]
+            self._emit_conv('head.%d' % i, s, w, b, 1, (1, 1), 1, False, segs=segs)
+            if ours:
+                k = CONF_POOL[i]
+                pooled_shapes.append((_pool_out(s.H, k, k, 0, True), _pool_out(s.W, k, k, 0, True), a))
+            poff += level_p[i]
+        self.head_end_op = self.L.ctx_prog_num_ops(self.prog)
+
+        # ---- Context-Transformer (phase 2, method 'ours') ----------------------------------------
+        if ours:
+            Pk = sum(h * w * a for h, w, a in pooled_shapes)
+            self.num_pooled = Pk
+            self.pooled = self._alloc(B, Pk, Csrc, dtype=torch.float32)
+            poff, koff = 0, 0
+            for i, (s, a) in enumerate(zip(sources, anchors)):
+                hp, wp, _ = pooled_shapes[i]
+                src = View(self.conf_raw.view(-1), B, s.H, s.W, a * Csrc, a * Csrc, poff * Csrc)
+                dst = View(self.pooled.view(-1), B, hp, wp, a * Csrc, a * Csrc, koff * Csrc)
+                self._emit_pool('conf_pool.%d' % i, src, CONF_POOL[i], CONF_POOL[i], 0, True, out=dst,
+                                in_img_stride=P * Csrc, out_img_stride=Pk * Csrc)
+                poff += level_p[i]
+                koff += hp * wp * a
+            incre = net.setting == 'incre'
+            n_novel = net.OBJ_Target.out_features
+            n_out = n_novel + (Csrc if incre else 0)
+            self.conf = self._alloc(B, P, n_out, dtype=torch.float32)
+            self.kv = self._alloc(B, Pk, 2 * Csrc, dtype=torch.float32)
+            f32 = lambda t: self._hold(t.detach().to(self.dev, torch.float32).contiguous())
+            ap = _lib.CtxAttnParams()
+            ap.batch, ap.num_priors, ap.num_pooled, ap.dim = B, P, Pk, Csrc
+            ap.num_novel, ap.incre, ap.apply_softmax = n_novel, int(incre), 1
+            ap.conf, ap.pooled = self.conf_raw.data_ptr(), self.pooled.data_ptr()
+            ap.theta_w, ap.theta_b = f32(net.theta.weight), f32(net.theta.bias)
+            ap.phi_w, ap.phi_b = f32(net.phi.weight), f32(net.phi.bias)
+            ap.g_w, ap.g_b = f32(net.g.weight), f32(net.g.bias)
+            if incre:
+                ap.fc_base_w, ap.fc_base_b = f32(net.fc_base.weight), f32(net.fc_base.bias)
+            ap.Wz = f32(net.Wz)
+            ap.obj_target_w = f32(net.OBJ_Target.weight)
+            ap.scale = float(net.scale.detach().float().cpu().item())
+            ap.kv_scratch, ap.out = self.kv.data_ptr(), self.conf.data_ptr()
+            _lib.check(self.L.ctx_prog_add_attention(self.prog, C.byref(ap)), 'ctx_prog_add_attention')
+            self.layers.append(('context_transformer', 'attention', 4.0 * B * P * Pk * Csrc, (B, P, Pk, Csrc)))
+        else:
+            self.conf = self._alloc(B, P, Csrc, dtype=torch.float32)
+            _lib.check(self.L.ctx_prog_add_softmax(self.prog, self.conf_raw.data_ptr(), self.conf.data_ptr(), B * P, Csrc),
+                       'ctx_prog_add_softmax')
+            self.layers.append(('conf.softmax', 'softmax', 0.0, (B * P, Csrc)))
+        self.obj = self._alloc(B, P, 2, dtype=torch.float32)
+        _lib.check(self.L.ctx_prog_add_softmax(self.prog, self.obj_raw.data_ptr(), self.obj.data_ptr(), B * P, 2),
+                   'ctx_prog_add_softmax')
+        self.layers.append(('obj.softmax', 'softmax', 0.0, (B * P, 2)))
+        self.num_ops = self.L.ctx_prog_num_ops(self.prog)
+        self.conv_flops = sum(l[2] for l in self.layers if l[1].startswith('conv'))
+
+    def _hold(self, t):
+        self.keep.append(t)
+        return t.data_ptr()
+
+    # ------------------------------------------------------------------------------------------
+    def load_input(self, x):
+        """Stage ``x`` ([B,3,S,S], any device, fp32) into the program's input buffer (async on the
+        current stream; a pinned host tensor becomes one H2D copy)."""
+        if tuple(x.shape) != tuple(self.x_in.shape):
+            raise ValueError('engine compiled for input %s, got %s' % (tuple(self.x_in.shape), tuple(x.shape)))
+        self.x_in.copy_(x, non_blocking=True)
+
+    def launch(self):
+        """Replay the program on the current stream (input already staged)."""
+        st = torch.cuda.current_stream(self.dev)
+        if self.use_graph and not self.graph_ready:
+            # capture on the engine's private stream, then replay on the caller's stream
+            self.stream.wait_stream(st)
+            with torch.cuda.stream(self.stream):
+                _lib.check(self.L.ctx_prog_run_range(self.prog, 0, self.num_ops, C.c_void_p(self.stream.cuda_stream)),
+                           'ctx_prog_run (warm-up)')
+                self.stream.synchronize()
+                _lib.check(self.L.ctx_prog_instantiate_graph(self.prog, C.c_void_p(self.stream.cuda_stream)),
+                           'ctx_prog_instantiate_graph')
+            st.wait_stream(self.stream)
+            self.graph_ready = True
+        _lib.check(self.L.ctx_prog_run(self.prog, C.c_void_p(st.cuda_stream)), 'ctx_prog_run')
+
+    def run(self, x):
+        with torch.cuda.device(self.dev):
+            self.load_input(x)
+            self.launch()
+        return self.loc, self.conf, self.obj
+
+    def run_range(self, first, last):
+        with torch.cuda.device(self.dev):
+            st = torch.cuda.current_stream(self.dev)
+            _lib.check(self.L.ctx_prog_run_range(self.prog, first, last, C.c_void_p(st.cuda_stream)), 'ctx_prog_run_range')

@@ -1,0 +1,178 @@
+/* ctx_b200.h — C ABI of the B200-native detection hot path (libctx_b200.so).
+ *
+ * Drop-in boundary for Ze-Yang/Context-Transformer's inference path.  Every entry point is
+ * `extern "C"`, takes plain pointers / sizes / a `cudaStream_t` passed as `void*`, returns an
+ * `int` status (0 = OK) and never prints or aborts; `ctx_last_error()` returns a thread-local
+ * message for the last non-zero status.  Unless a name ends in `_host`, pointers are DEVICE
+ * pointers owned by the caller (the Python host passes `tensor.data_ptr()`), the call is
+ * asynchronous on `stream`, and the callee allocates nothing (scratch comes in as `workspace`).
+ *
+ * Each declaration cites the reference interface (file:line under the reference repo) it
+ * replaces.  INTEGRATION.md shows the reference-side binding for each.
+ */
+#ifndef CTX_B200_H_
+#define CTX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTX_OK 0
+#define CTX_ERR_INVALID 1     /* bad argument (null pointer, negative size, unsupported geometry) */
+#define CTX_ERR_CUDA 2        /* a CUDA runtime / driver call failed */
+#define CTX_ERR_WORKSPACE 3   /* workspace too small */
+#define CTX_ERR_UNSUPPORTED 4 /* valid request that this build does not implement */
+
+#define CTX_F32 0
+#define CTX_BF16 1
+#define CTX_F16 2
+
+/* ---- library ------------------------------------------------------------------------------ */
+int ctx_version(void);
+const char* ctx_last_error(void);
+/* Number of kernel launches issued by this library since process start (bench.py gpu_launches). */
+unsigned long long ctx_launch_count(void);
+
+/* ---- Detect.forward : layers/functions/detection.py:18-55 + utils/box_utils.py:184-202 ----- */
+/* boxes_out[B,P,4] = decode(loc, priors, var);  scores_out[B,P,1+C] = cat(obj0, obj1*conf).   */
+int ctx_detect_forward(const float* loc, const float* conf, const float* obj, const float* priors,
+                       int batch, int num_priors, int num_fg_classes, float var0, float var1,
+                       float* boxes_out, float* scores_out, void* stream);
+
+/* ---- fused post-processing : test.py:133-161 (scale, per-class threshold + NMS, top-k) ------ */
+typedef struct CtxPostParams {
+  int batch, num_priors, num_fg_classes;
+  float var0, var1;
+  int scale_per_image;      /* 0: scale[4] shared, 1: scale[batch,4]                (test.py:123-124,136) */
+  float score_thresh;       /* candidates are score >  score_thresh                 (test.py:143) */
+  float nms_thresh;         /* IoU threshold, +1 pixel convention                   (test.py:152) */
+  int suppress_on_equal;    /* 1: cpu_nms ">=" (cpu_nms.pyx:65), 0: gpu_nms ">" (nms_kernel.cu:71) */
+  int nms_method;           /* 0 hard NMS; 1/2/3: cpu_soft_nms method 1 (linear) / 2 (gaussian) / 0 (hard) */
+  float soft_sigma, soft_threshold; /* cpu_soft_nms sigma, threshold (Nt = nms_thresh)   (cpu_nms.pyx:70) */
+  int max_per_image;        /* 200 upstream; <=0 disables the cut                   (test.py:96,155-161) */
+  int max_out;              /* record capacity per image (>= max_per_image; ties may exceed it upstream) */
+} CtxPostParams;
+size_t ctx_postprocess_workspace_bytes(int batch, int num_priors, int num_fg_classes);
+/* records[B,max_out,6] = x1,y1,x2,y2,score,class (class asc, score desc); counts[B] = number of
+ * detections the reference would keep (may exceed max_out -> truncated); prior_idx[B,max_out]
+ * (optional) = index of the prior each record came from. */
+int ctx_detect_postprocess(const float* loc, const float* conf, const float* obj, const float* priors,
+                           const float* scale, const CtxPostParams* p,
+                           float* records, int* counts, int* prior_idx,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- NMS : utils/nms_wrapper.py:23-31, utils/nms/gpu_nms.pyx:16-31, cpu_nms.pyx:17-68 -------- */
+size_t ctx_nms_workspace_bytes(int n);
+/* dets[n,5] device (x1,y1,x2,y2,score).  keep_out[n] device: indices into dets, best score first. */
+int ctx_nms_device(const float* dets, int n, float thresh, int suppress_on_equal,
+                   int* keep_out, int* num_out, void* workspace, size_t workspace_bytes, void* stream);
+/* Host-pointer convenience with nms_wrapper.nms semantics (blocking). */
+int ctx_nms_host(const float* dets_host, int n, float thresh, int suppress_on_equal,
+                 int* keep_host, int* num_out_host, int device_id);
+/* Legacy signature, literal drop-in for utils/nms/gpu_nms.hpp:1-2 (rows pre-sorted by the caller,
+ * host pointers, blocking; errors are recorded in ctx_last_error() instead of printed). */
+void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
+          float nms_overlap_thresh, int device_id);
+/* cpu_soft_nms : utils/nms/cpu_nms.pyx:70-163.  In-place on boxes_host[n,5]; *n_out = N_final. */
+int ctx_soft_nms_host(float* boxes_host, int n, float sigma, float Nt, float threshold,
+                      unsigned method, int* n_out, int device_id);
+
+/* ---- conv / pool program : models/RFB_Net_vgg.py BasicConv :7-22, vgg :323-343, heads :387-416 */
+typedef struct CtxOutSeg {   /* where output channels [c_begin, c_end) of a conv go */
+  void* ptr;
+  int c_begin, c_end;
+  long long img_stride;      /* elements between images */
+  int pix_stride;            /* elements between output pixels (row-major oy*Wo+ox) */
+  int ch_offset;             /* element offset of channel c_begin inside a pixel */
+  int dtype;                 /* CTX_F32 / CTX_BF16 / CTX_F16 */
+} CtxOutSeg;
+
+typedef struct CtxConvParams {
+  int N, H, W, Cin;          /* NHWC input; Cin channels are consumed ...                       */
+  int in_cstride, in_coffset;/* ... starting at channel in_coffset of a pixel of in_cstride channels */
+  int Cout, KH, KW, stride, pad_h, pad_w, dil;
+  int Ho, Wo;
+  int relu;
+  int in_dtype;
+  const void* in;
+  const void* weight;        /* SIMT path: fp32 [KH*KW*Cin][Cout]; TC path: 16-bit [Cout_pad][KH*KW][Cin_pad] */
+  const float* bias;         /* [Cout] (BatchNorm folded in) or NULL */
+  const void* residual;      /* optional NHWC tensor added before ReLU (RFB shortcut, :59-61) */
+  int res_dtype, res_cstride, res_coffset;
+  int nseg;
+  CtxOutSeg seg[3];
+} CtxConvParams;
+
+typedef struct CtxPoolParams { /* nn.MaxPool2d on NHWC views (vgg 'M'/'C'/pool5, conf pool :242-244) */
+  int N, H, W, C, Ho, Wo, k, stride, pad;
+  int dtype;
+  const void* in; long long in_img_stride; int in_pix_stride;
+  void* out; long long out_img_stride; int out_pix_stride;
+} CtxPoolParams;
+
+int ctx_conv2d_simt(const CtxConvParams* p, void* stream);          /* fp32-accumulate CUDA-core path */
+int ctx_conv2d_tc_supported(const CtxConvParams* p);                /* 1 if the tcgen05 path takes it  */
+/* tcgen05/TMA implicit-GEMM path.  The plan owns the TMA descriptors (pointers are baked in).   */
+int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out);
+int ctx_conv2d_tc_plan_run(void* plan, void* stream);
+void ctx_conv2d_tc_plan_destroy(void* plan);
+int ctx_maxpool2d_nhwc(const CtxPoolParams* p, void* stream);
+/* x[N,3,H,W] fp32 NCHW (RFBNet.forward input, :210) -> NHWC of dtype */
+int ctx_nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, int out_dtype, void* stream);
+
+/* ---- Context-Transformer : models/RFB_Net_vgg.py:253-271 (+ :273-285 output activation) ------ */
+typedef struct CtxAttnParams {
+  int batch, num_priors, num_pooled, dim;      /* P, Pk, C_src (60 transfer / 15 incre) */
+  int num_novel;                               /* rows of OBJ_Target (20 / 5) */
+  int incre;                                   /* 1: conf = cat(fc_base(conf)+conf, novel) */
+  int apply_softmax;                           /* eval mode (:279-285) */
+  const float* conf;                           /* [B,P,dim] raw conf head output */
+  const float* pooled;                         /* [B,Pk,dim] spatially max-pooled conf */
+  const float *theta_w, *theta_b, *phi_w, *phi_b, *g_w, *g_b;   /* [dim,dim], [dim] */
+  const float *fc_base_w, *fc_base_b;          /* incre only */
+  const float* Wz;                             /* [dim] */
+  const float* obj_target_w;                   /* [num_novel, dim] */
+  float scale;
+  float* kv_scratch;                           /* [B,Pk,2*dim] fp32 */
+  float* out;                                  /* [B,P, incre ? dim+num_novel : num_novel] */
+} CtxAttnParams;
+int ctx_attention_forward(const CtxAttnParams* p, void* stream);
+/* row softmax over the last dim (C <= 128) — output activation :279-285 for obj / non-'ours' conf */
+int ctx_softmax_lastdim(const float* in, float* out, long long rows, int cols, void* stream);
+
+/* ---- op program: a recorded list of the ops above, replayed with one call ------------------- */
+int ctx_prog_create(void** prog_out);
+int ctx_prog_add_conv_simt(void* prog, const CtxConvParams* p);
+int ctx_prog_add_conv_tc(void* prog, const CtxConvParams* p);
+int ctx_prog_add_pool(void* prog, const CtxPoolParams* p);
+int ctx_prog_add_nchw_to_nhwc(void* prog, const float* in, void* out, int N, int C, int H, int W, int out_dtype);
+int ctx_prog_add_attention(void* prog, const CtxAttnParams* p);
+int ctx_prog_add_softmax(void* prog, const float* in, float* out, long long rows, int cols);
+int ctx_prog_num_ops(void* prog);
+int ctx_prog_run(void* prog, void* stream);
+/* capture the op list into a CUDA graph on `stream` (non-default); later ctx_prog_run calls replay it */
+int ctx_prog_instantiate_graph(void* prog, void* stream);
+/* run ops [first, last) — used by bench.py/ncu to time one layer class */
+int ctx_prog_run_range(void* prog, int first, int last, void* stream);
+void ctx_prog_destroy(void* prog);
+
+/* ---- training targets : utils/box_utils.py:83-156, multibox_loss_combined.py:88-96 ----------- */
+/* Batched match(): truths[B,max_obj,6] (x1,y1,x2,y2,label,weight; rows >= num_obj[b] ignored).
+ * Outputs loc_t[B,P,4], conf_t[B,P,2], obj_t[B,P] (uint8); optional best_truth_idx[B,P] and
+ * best_truth_overlap[B,P] (the `overlap` argument of match(), box_utils.py:115-116).          */
+int ctx_match_encode(const float* truths, const int* num_obj, int max_obj, const float* priors,
+                     int batch, int num_priors, float threshold, float var0, float var1,
+                     float* loc_t, float* conf_t, unsigned char* obj_t, int* best_truth_idx,
+                     float* best_truth_overlap, void* stream);
+/* rank[b,p] = position of p in the descending stable sort of loss[b,:] (the reference's two sorts). */
+size_t ctx_rank_workspace_bytes(int batch, int num_priors);
+int ctx_hard_negative_rank(const float* loss, int batch, int num_priors, int* rank,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTX_B200_H_ */

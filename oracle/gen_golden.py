@@ -1,0 +1,166 @@
+"""TEST INFRASTRUCTURE ONLY — generate tests/golden/*.npz by running the REAL reference
+(/root/reference, imported by oracle/ref_import.py) on the seeded synthetic inputs of
+oracle/synth.py.  Run in the build container only:  python -m oracle.gen_golden
+
+The reference ships no tests or golden vectors, so these files are what pins the
+oracle (and through it the CUDA path) to the reference's behaviour.  Large tensors are stored
+sub-sampled (every ``ROW_STRIDE``-th prior) together with float64 checksums of the full tensor.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+from . import ref_import, synth
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+ROW_STRIDE = 5
+
+NET_CASES = [  # tag, method, phase, setting, size, num_classes, batch
+    ('ours_transfer_300', 'ours', 2, 'transfer', 300, 60, 2),
+    ('ours_incre_300', 'ours', 2, 'incre', 300, 15, 1),
+    ('ft_300', 'ft', 2, 'transfer', 300, 20, 1),
+    ('ft_512', 'ft', 2, 'transfer', 512, 20, 1),
+]
+
+
+def checksum(a):
+    a = np.asarray(a, dtype=np.float64)
+    return np.array([a.sum(), np.abs(a).sum(), (a * a).sum()])
+
+
+def gen_priors(r):
+    out = {}
+    for name in ('VOC_300', 'VOC_512', 'COCO_300', 'COCO_512'):
+        p = r.PriorBox(getattr(r.cfg, name)).forward().numpy()
+        out[name] = p
+    np.savez_compressed(os.path.join(GOLD, 'priors.npz'), **out)
+
+
+def gen_net(r):
+    torch.set_num_threads(os.cpu_count() or 1)
+    for tag, method, phase, setting, size, ncls, batch in NET_CASES:
+        args = types.SimpleNamespace(method=method, phase=phase, setting=setting)
+        torch.manual_seed(0)
+        net = r.build_net(args, size, ncls)
+        net.load_state_dict(synth.seeded_state(net.state_dict(), seed=0))
+        net.eval()
+        net.device = 'cpu'
+        x = synth.seeded_input(batch, size, seed=0)
+        with torch.no_grad():
+            loc, conf, obj = net(x)
+            conf_init = net(x, init=True)
+            net.train()
+            loc_tr, conf_tr, obj_tr = net(x) if batch > 1 else (None, None, None)   # BN needs batch > 1 on 1x1 maps
+        d = dict(keys=np.array(list(net.state_dict().keys())),
+                 shapes=np.array([str(tuple(v.shape)) for v in net.state_dict().values()]),
+                 loc=loc.numpy()[:, ::ROW_STRIDE], conf=conf.numpy()[:, ::ROW_STRIDE], obj=obj.numpy()[:, ::ROW_STRIDE],
+                 conf_init=conf_init.numpy()[:, ::ROW_STRIDE],
+                 loc_sum=checksum(loc), conf_sum=checksum(conf), obj_sum=checksum(obj),
+                 conf_argmax=conf.argmax(-1).numpy().astype(np.int16))
+        np.savez_compressed(os.path.join(GOLD, 'net_%s.npz' % tag), **d)
+        print(tag, loc.shape, conf.shape, float(conf.max()), flush=True)
+
+
+def gen_post(r):
+    """Detect.forward + the numpy loop of test.py:133-161 with the reference's own NMS routines."""
+    priors = r.PriorBox(r.cfg.VOC_300).forward()
+    B, P, C = 2, priors.size(0), 20
+    loc, conf, obj = synth.calibrated_heads(B, P, C, seed=0)
+    det = r.Detect(21, 0, r.cfg.VOC_300)
+    boxes, scores = det.forward((loc, conf, obj), priors)
+    scale = np.array([500., 375., 500., 375.], dtype=np.float32)
+    out = dict(boxes=boxes.numpy()[:, ::ROW_STRIDE], scores=scores.numpy()[:, ::ROW_STRIDE],
+               boxes_sum=checksum(boxes), scores_sum=checksum(scores), scale=scale)
+    for conv, fn in (('gt', r.py_cpu_nms), ('ge', r.cpu_nms)):
+        if fn is None:
+            continue
+        for b in range(B):
+            bx = (boxes[b] * torch.from_numpy(scale)).numpy()
+            sc = scores[b].numpy()
+            all_dets = [np.empty((0, 5), np.float32)] * 21
+            all_idx = [np.empty((0,), np.int64)] * 21
+            for j in range(1, 21):
+                inds = np.where(sc[:, j] > 0.01)[0]
+                if len(inds) == 0:
+                    continue
+                c_dets = np.hstack((bx[inds], sc[inds, j][:, None])).astype(np.float32, copy=False)
+                keep = np.asarray(fn(c_dets, 0.45), dtype=np.int64)
+                all_dets[j] = c_dets[keep]
+                all_idx[j] = inds[keep]
+            image_scores = np.hstack([all_dets[j][:, -1] for j in range(1, 21)])
+            if len(image_scores) > 200:
+                th = np.sort(image_scores)[-200]
+                for j in range(1, 21):
+                    k = np.where(all_dets[j][:, -1] >= th)[0]
+                    all_dets[j] = all_dets[j][k]
+                    all_idx[j] = all_idx[j][k]
+            rec = np.vstack([np.hstack([all_dets[j], np.full((len(all_dets[j]), 1), j, np.float32)]) for j in range(1, 21)])
+            out['records_%s_%d' % (conv, b)] = rec.astype(np.float32)
+            out['prior_idx_%s_%d' % (conv, b)] = np.concatenate([all_idx[j] for j in range(1, 21)]).astype(np.int32)
+    np.savez_compressed(os.path.join(GOLD, 'post_voc300.npz'), **out)
+
+
+def gen_nms(r):
+    out = {}
+    for n, seed in ((0, 0), (1, 1), (63, 2), (64, 3), (65, 4), (300, 5), (2000, 6)):
+        d = synth.random_dets(n, seed=seed)
+        out['keep_gt_%d' % n] = np.asarray(r.py_cpu_nms(d, 0.45) if n else [], dtype=np.int32)
+        if r.cpu_nms is not None:
+            out['keep_ge_%d' % n] = np.asarray(r.cpu_nms(d, 0.45) if n else [], dtype=np.int32)
+    if r.cpu_soft_nms is not None:
+        for method in (0, 1, 2):
+            for n, seed in ((1, 1), (65, 4), (300, 5)):
+                d = synth.random_dets(n, seed=seed).copy()
+                keep = r.cpu_soft_nms(d, sigma=0.5, Nt=0.3, threshold=0.001, method=method)
+                out['soft_m%d_%d' % (method, n)] = d[:len(keep)].copy()
+    np.savez_compressed(os.path.join(GOLD, 'nms.npz'), **out)
+
+
+def gen_match_loss(r):
+    priors = r.PriorBox(r.cfg.VOC_300).forward()
+    P = priors.size(0)
+    B = 4
+    targets = synth.synthetic_targets(B, seed=0)
+    targets[1][0, 4] = -1.0           # an "ignore" label (counts as object, box_utils.py:130)
+    targets[2][:, 5] = 0.7            # mixup weights
+    loc_t = torch.zeros(B, P, 4)
+    conf_t = torch.zeros(B, P, 2)
+    obj_t = torch.zeros(B, P, dtype=torch.bool)
+    overlap = torch.zeros(B, P)
+    for i in range(B):
+        r.box_utils.match(0.5, targets[i][:, :4], priors, [0.1, 0.2], targets[i][:, 4:6], loc_t, conf_t, obj_t, i, overlap)
+    g = synth._gen(0, 'losspred')
+    loc_p = torch.randn(B, P, 4, generator=g)
+    conf_p = torch.randn(B, P, 20, generator=g)
+    obj_p = torch.randn(B, P, 2, generator=g)
+    crit = r.MultiBoxLoss_combined(21, 0.5, True, 0, True, 3, 0.5, False)
+    losses = crit((loc_p, conf_p, obj_p), priors, targets)
+    pos = conf_t[:, :, 0] != 0
+    out = dict(loc_t_pos=loc_t[pos].numpy(), pos_index=pos.nonzero().numpy().astype(np.int32),
+               conf_t=conf_t.numpy(), obj_t=obj_t.numpy(), overlap=overlap.numpy()[:, ::ROW_STRIDE],
+               loc_t_sum=checksum(loc_t), targets=np.array([t.numpy() for t in targets], dtype=object),
+               loss=np.array([float(losses['loss_box_reg']), float(losses['loss_cls']), float(losses['loss_obj'])]))
+    np.savez_compressed(os.path.join(GOLD, 'match_loss.npz'), **out)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    r = ref_import.load()
+    which = sys.argv[1:] or ['priors', 'nms', 'post', 'match', 'net']
+    if 'priors' in which:
+        gen_priors(r)
+    if 'nms' in which:
+        gen_nms(r)
+    if 'post' in which:
+        gen_post(r)
+    if 'match' in which:
+        gen_match_loss(r)
+    if 'net' in which:
+        gen_net(r)
+
+
+if __name__ == '__main__':
+    main()
