@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the detection hot path (BASELINE.json metric: images/sec at 300x300).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp16|fp32] [--impl reference]
+
+Workload (BASELINE.json configs[1]): RFB_Net_vgg 300x300, phase-2 'ours' transfer head (60-d conf
+-> Context-Transformer -> 20 classes), batch 32 per GPU, synthetic input, seeded random weights.
+A step is one pass of the compiled forward (layout change, conv stack, heads, conf pool,
+Context-Transformer, softmaxes) over one batch.
+
+  value      images/s, inputs already resident in HBM, device time (CUDA events, max over ranks)
+  e2e        images/s through the user-facing call chain with HOST buffers: pinned input -> H2D ->
+             net(x) -> DetectPost (decode + score + per-class NMS + top-200) -> [all-gather at N>1]
+             -> D2H of the detection records                      (reference test.py:121-161)
+  roofline   the conv implicit-GEMM kernels (dominant): algorithmic conv FLOPs of one step / the
+             summed per-launch durations of those kernels, measured live with CUDA events
+  cpu_baseline  the oracle port of the reference forward (+ Detect + cpu_nms) on the host cores,
+             bounded sample, rank 0 at N = 1 only
+  --impl reference   times only that CPU path, same metric/config, prints the same JSON shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SIZE, NUM_SRC_CLASSES, BATCH_PER_GPU = 300, 60, 32
+CONV_GFLOP_PER_IMG = 77.29 - 7.57      # SURVEY §8d (each conv once; the reference runs the conf heads twice)
+SCALE = [500.0, 375.0, 500.0, 375.0]
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def bench_state(net):
+    """Seeded random weights (oracle/synth.py recipe) with the objectness head biased towards
+    background so that ~1-2 % of priors are objects: the NMS then sees a trained-detector-like
+    O(10^2) candidates per class instead of the degenerate all-or-nothing of raw random weights
+    (SURVEY.md §8d 'score distribution caveat')."""
+    from oracle import synth
+    sd = synth.seeded_state(net.state_dict(), seed=0)
+    for k in list(sd):
+        if k.startswith('obj.') and k.endswith('.bias'):
+            b = sd[k].clone().view(-1, 2)
+            b[:, 0] += 2.5
+            b[:, 1] -= 2.5
+            sd[k] = b.view(-1)
+    return sd
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for l in self.lines:
+            f = [x.strip() for x in l.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, imgs_per_step, threads):
+    """The reference's CPU path restated (oracle/): forward + Detect + per-class cpu_nms + top-200.
+    Returns (images/s, seconds, description)."""
+    import numpy as np
+    import torch
+
+    import context_transformer_b200 as ctx
+    from oracle import c_oracle, np_oracle, synth, torch_net
+    torch.set_num_threads(threads)
+    args = types.SimpleNamespace(method='ours', phase=2, setting='transfer')
+    net = ctx.build_net(args, SIZE, NUM_SRC_CLASSES)           # parameter container only (shapes / names)
+    sd = bench_state(net)
+    priors = np_oracle.prior_box(ctx.VOC_300)
+    x = synth.seeded_input(imgs_per_step, SIZE, seed=0)
+    scale = np.asarray(SCALE, np.float32)
+    nms_fn = lambda d, t: c_oracle.cpu_nms(d, t, False)
+
+    def step():
+        with torch.no_grad():
+            loc, conf, obj = torch_net.forward(sd, x, SIZE, NUM_SRC_CLASSES, 'ours', 2, 'transfer')
+        boxes, scores = np_oracle.detect(loc.numpy(), conf.numpy(), obj.numpy(), priors)
+        n = 0
+        for b in range(imgs_per_step):
+            dets, _ = np_oracle.postprocess_image(boxes[b], scores[b], scale, 0.01, 0.45, 200, nms_fn=nms_fn)
+            n += sum(len(d) for d in dets if d is not None)
+        return n
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return imgs_per_step * steps / dt, dt, ('%d steps x %d images: torch fp32 forward (oracle/torch_net.py) + Detect + '
+                                            'per-class cpu_nms + top-200 (oracle/np_oracle.py, oracle/c/nms_oracle.c)'
+                                            % (steps, imgs_per_step))
+
+
+def workload_config(precision, n_gpus, extra=None):
+    cfg = {'workload': 'RFB_Net_vgg 300x300 + Context-Transformer (phase 2, ours, transfer 60->20), forward only, '
+                       'batch %d per GPU' % BATCH_PER_GPU,
+           'global_batch': BATCH_PER_GPU * n_gpus, 'image_size': SIZE, 'precision': precision,
+           'parallelism': 'dp%d (batch shards, one all-gather of detection records in e2e)' % n_gpus,
+           'cache': 'L2 flushed (512 MiB write) before every timed step; per-step activations (>2 GB) exceed L2'}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def run_reference(args):
+    rank = env_int('RANK', 0)
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    ips, dt, sample = cpu_reference_run(args.steps, min(args.warmup, 2), 2, threads)
+    line = {'impl': 'reference', 'metric': 'images/sec', 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': min(args.warmup, 2), 'ms_per_step': 1000.0 * dt / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config('fp32 (CPU)', args.gpus, {'note': 'host CPU path; each step is a 2-image sample'}),
+            'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp16', 'fp32'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='plain launches instead of one CUDA-graph replay')
+    ap.add_argument('--quick', action='store_true', help='device-resident forward only (for ncu): no e2e, per-op or CPU legs')
+    ap.add_argument('--layers', default=None, help='write the per-kernel timing table (JSON) to this path')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import context_transformer_b200 as ctx
+    from context_transformer_b200 import _lib, shard
+    from oracle import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the hot path has no CPU fallback; use --impl reference for the CPU arm)')
+    world, rank, local = env_int('WORLD_SIZE', 1), env_int('RANK', 0), env_int('LOCAL_RANK', 0)
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    n_gpus = world
+
+    margs = types.SimpleNamespace(method='ours', phase=2, setting='transfer', precision=args.precision)
+    net = ctx.build_net(margs, SIZE, NUM_SRC_CLASSES)
+    net.load_state_dict(bench_state(net))
+    net.eval()
+    net.device = str(dev)
+    net.use_cuda_graph = not args.no_graph
+    net.to(dev)
+    priors = ctx.PriorBox(ctx.VOC_300).forward().to(dev)
+    post = ctx.DetectPost(21, 0, ctx.VOC_300)
+    B = BATCH_PER_GPU
+    x_host = synth.seeded_input(B, SIZE, seed=rank).pin_memory()
+    x_dev = x_host.to(dev)
+    eng = net.engine(B)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    scale = torch.tensor(SCALE, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """device ms summed over `steps` calls of fn, L2 flushed before each (untimed)."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    # ---- device-resident forward ------------------------------------------------------------
+    def step_device():
+        eng.load_input(x_dev)
+        eng.launch()
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count()
+    ms_total = timed(step_device, args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop()
+    ms_per_step = ms_total / args.steps
+    value = n_gpus * B * args.steps / (ms_total / 1000.0)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'ms_per_step': ms_per_step,
+                              'gpu_launches': int(launches), 'quick': True}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- end to end through the public API, host buffers --------------------------------------
+    out_host = torch.empty(B * n_gpus, post.max_out + 1, 6).pin_memory()
+    n_det = [0]
+
+    def step_e2e():
+        pred = net(x_host)                                    # H2D of the pinned input inside forward
+        rec, cnt, _ = post.forward(pred, priors, scale)
+        if world > 1:
+            rec, cnt = shard.gather_records(rec, cnt)
+        out_host.copy_(shard.pack_records(rec, cnt), non_blocking=True)
+        torch.cuda.current_stream().synchronize()             # the caller reads the records
+        n_det[0] = int(out_host[:, -1, 0].sum())
+
+    for _ in range(args.warmup):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = n_gpus * B * args.steps / (ms_e2e / 1000.0)
+    h2d = x_host.numel() * 4
+    d2h = out_host.numel() * 4
+
+    # ---- per-kernel pass: CUDA events around every op of the program ---------------------------
+    reps = 3
+    per_op = []
+    eng.load_input(x_dev)
+    for i, (name, kind, flops, shape) in enumerate(eng.layers):
+        ts = []
+        for _ in range(reps):
+            flush.zero_() if flops > 5e9 else None
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.run_range(i, i + 1)
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        per_op.append({'op': name, 'kind': kind, 'gflop': flops / 1e9, 'ms': min(ts), 'shape': list(shape)})
+    conv_ops = [o for o in per_op if o['kind'].startswith('conv')]
+    conv_ms = sum(o['ms'] for o in conv_ops)
+    conv_flops = sum(o['gflop'] for o in conv_ops) * 1e9
+    tc_ops = [o for o in conv_ops if o['kind'] == 'conv_tc']
+    all_ms = sum(o['ms'] for o in per_op)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
+    achieved_tf = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {'bound': 'tensor', 'kernel': 'conv implicit-GEMM family (%d launches/step, %d on tcgen05)' % (len(conv_ops), len(tc_ops)),
+                'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
+                'traffic': None, 'peak_source': peak_src,
+                'conv_ms_per_step': conv_ms, 'conv_share_of_step': conv_ms / all_ms if all_ms else None,
+                'algorithmic_gflop_per_step': conv_flops / 1e9}
+    if args.layers and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.layers)), exist_ok=True)
+        json.dump({'precision': args.precision, 'batch': B, 'ops': per_op}, open(args.layers, 'w'), indent=1)
+
+    line = {'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': n_gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'fp16': 'f16', 'fp32': 'f32'}[args.precision], 'data': 'synthetic',
+            'config': workload_config(args.precision, n_gpus, {'detections_per_batch_e2e': n_det[0],
+                                                                'cuda_graph': bool(eng.graph_ready)}),
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / args.steps,
+                    'includes': 'H2D input, forward, DetectPost (decode+score+NMS+top-200), %sD2H records'
+                                % ('all-gather, ' if world > 1 else '')},
+            'gpu_launches': int(launches), 'roofline': roofline}
+
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        ips, dt, sample = cpu_reference_run(6, 1, 2, threads)
+        line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

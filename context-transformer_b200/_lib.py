@@ -57,7 +57,8 @@ class CtxAttnParams(C.Structure):
                 ('theta_w', C.c_void_p), ('theta_b', C.c_void_p), ('phi_w', C.c_void_p), ('phi_b', C.c_void_p),
                 ('g_w', C.c_void_p), ('g_b', C.c_void_p), ('fc_base_w', C.c_void_p), ('fc_base_b', C.c_void_p),
                 ('Wz', C.c_void_p), ('obj_target_w', C.c_void_p), ('scale', C.c_float),
-                ('kv_scratch', C.c_void_p), ('out', C.c_void_p)]
+                ('use_tensor_cores', C.c_int), ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+                ('out', C.c_void_p)]
 
 
 _P, _I, _F, _SZ, _LL = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
@@ -81,6 +82,9 @@ SIGNATURES = {
     'ctx_conv2d_tc_plan_destroy': (None, [_P]),
     'ctx_maxpool2d_nhwc': (_I, [C.POINTER(CtxPoolParams), _P]),
     'ctx_nchw_to_nhwc': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    'ctx_nchw_to_patch27': (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    'ctx_prog_add_nchw_to_patch27': (_I, [_P, _P, _P, _I, _I, _I, _I]),
+    'ctx_attention_workspace_bytes': (_SZ, [C.POINTER(CtxAttnParams)]),
     'ctx_attention_forward': (_I, [C.POINTER(CtxAttnParams), _P]),
     'ctx_softmax_lastdim': (_I, [_P, _P, _LL, _I, _P]),
     'ctx_prog_create': (_I, [C.POINTER(_P)]),

@@ -83,8 +83,9 @@ attention_kernel(CtxAttnParams p) {
 #pragma unroll
   for (int d = 0; d < DP; ++d) acc[d] = 0.f;
   float m = -INFINITY, l = 0.f;
-  const float* kb = p.kv_scratch + (size_t)b * p.num_pooled * D;
-  const float* vb = p.kv_scratch + (size_t)p.batch * p.num_pooled * D + (size_t)b * p.num_pooled * D;
+  const float* kv_scratch = reinterpret_cast<const float*>(p.workspace);
+  const float* kb = kv_scratch + (size_t)b * p.num_pooled * D;
+  const float* vb = kv_scratch + (size_t)p.batch * p.num_pooled * D + (size_t)b * p.num_pooled * D;
   for (int t0 = 0; t0 < p.num_pooled; t0 += kKeyTile) {
     const int nt = min(kKeyTile, p.num_pooled - t0);
     for (int i = threadIdx.x; i < kKeyTile * DP; i += blockDim.x) {
@@ -184,11 +185,14 @@ attention_kernel(CtxAttnParams p) {
   for (int c = 0; c < n_out; ++c) orow[c] = o[c];
 }
 
+int attention_tc_launch(const CtxAttnParams* a, cudaStream_t st);
+size_t attention_tc_workspace_bytes(int B, int P, int Pk);
+
 template <int D>
 static int attention_launch_t(const CtxAttnParams* p, cudaStream_t st) {
   const long long rows = (long long)p->batch * p->num_pooled;
-  float* k_out = p->kv_scratch;
-  float* v_out = p->kv_scratch + rows * D;
+  float* k_out = reinterpret_cast<float*>(p->workspace);
+  float* v_out = k_out + rows * D;
   kv_project_kernel<D><<<cdiv(rows, 128), 128, 0, st>>>(p->pooled, p->phi_w, p->phi_b, p->g_w, p->g_b, rows, k_out, v_out);
   CTX_LAUNCH_CHECK();
   dim3 grid(cdiv(p->num_priors, kAttnThreads), p->batch);
@@ -200,11 +204,16 @@ static int attention_launch_t(const CtxAttnParams* p, cudaStream_t st) {
 int attention_simt_launch(const CtxAttnParams* p, cudaStream_t st) {
   CTX_REQUIRE(p, "attention: null params");
   CTX_REQUIRE(p->conf && p->pooled && p->theta_w && p->theta_b && p->phi_w && p->phi_b && p->g_w && p->g_b && p->Wz &&
-              p->obj_target_w && p->kv_scratch && p->out, "attention: null pointer");
+              p->obj_target_w && p->workspace && p->out, "attention: null pointer");
   CTX_REQUIRE(!p->incre || (p->fc_base_w && p->fc_base_b), "attention: incre needs fc_base");
   CTX_REQUIRE(p->batch > 0 && p->num_priors > 0 && p->num_pooled > 0, "attention: bad sizes");
   CTX_REQUIRE(p->num_novel > 0 && p->num_novel + (p->incre ? p->dim : 0) <= 64, "attention: too many output classes");
-  if (p->dim == 60) { CTX_REQUIRE(p->num_novel <= 64, "attention: num_novel"); return attention_launch_t<60>(p, st); }
+  if (p->use_tensor_cores) {
+    CTX_REQUIRE(p->num_novel <= 32, "attention (tensor-core path): num_novel must be <= 32");
+    return attention_tc_launch(p, st);
+  }
+  CTX_REQUIRE(p->workspace_bytes >= sizeof(float) * 2 * (size_t)p->batch * p->num_pooled * p->dim, "attention: workspace too small");
+  if (p->dim == 60) return attention_launch_t<60>(p, st);
   if (p->dim == 15) return attention_launch_t<15>(p, st);
   if (p->dim == 20) return attention_launch_t<20>(p, st);
   set_error("attention: dim %d not instantiated (60 transfer / 15 incre / 20)", p->dim);
@@ -212,6 +221,12 @@ int attention_simt_launch(const CtxAttnParams* p, cudaStream_t st) {
 }
 
 }  // namespace ctx
+
+extern "C" size_t ctx_attention_workspace_bytes(const CtxAttnParams* p) {
+  if (!p || p->batch <= 0 || p->num_priors <= 0 || p->num_pooled <= 0 || p->dim <= 0) return 1024;
+  if (p->use_tensor_cores) return ctx::attention_tc_workspace_bytes(p->batch, p->num_priors, p->num_pooled);
+  return ctx::align_up(sizeof(float) * 2 * (size_t)p->batch * p->num_pooled * p->dim, 1024);
+}
 
 extern "C" int ctx_attention_forward(const CtxAttnParams* p, void* stream) {
   return ctx::attention_simt_launch(p, (cudaStream_t)stream);

@@ -13,6 +13,7 @@
 // segments (lets loc/conf/obj heads land directly in their concatenated [B,P,*] buffers, the
 // permute(0,2,3,1).contiguous()+cat of RFB_Net_vgg.py:239-248 for free).
 #include "common.cuh"
+#include <algorithm>
 
 namespace ctx {
 
@@ -164,6 +165,82 @@ maxpool_nhwc_kernel(CtxPoolParams p) {
   }
 }
 
+// 16-bit fast path: 8 channels (16 bytes) per thread, fully coalesced 128-bit loads/stores.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_vec8_kernel(CtxPoolParams p) {
+  const int C8 = p.C >> 3;
+  const long long total = (long long)p.N * p.Ho * p.Wo * C8;
+  const uint16_t* in = reinterpret_cast<const uint16_t*>(p.in);
+  uint16_t* out = reinterpret_cast<uint16_t*>(p.out);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    long long r = i / C8;
+    const int ox = (int)(r % p.Wo); r /= p.Wo;
+    const int oy = (int)(r % p.Ho);
+    const int n = (int)(r / p.Ho);
+    const int y0 = max(oy * p.stride - p.pad, 0), y1 = min(oy * p.stride - p.pad + p.k, p.H);
+    const int x0 = max(ox * p.stride - p.pad, 0), x1 = min(ox * p.stride - p.pad + p.k, p.W);
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        const uint4 v = *reinterpret_cast<const uint4*>(in + (long long)n * p.in_img_stride + (long long)(y * p.W + x) * p.in_pix_stride + c);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f;
+          if (BF16) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+          else f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+          m[2 * e] = fmaxf(m[2 * e], f.x); m[2 * e + 1] = fmaxf(m[2 * e + 1], f.y);
+        }
+      }
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(m[2 * e], m[2 * e + 1]); o[e] = *reinterpret_cast<uint32_t*>(&h); }
+      else { __half2 h = __floats2half2_rn(m[2 * e], m[2 * e + 1]); o[e] = *reinterpret_cast<uint32_t*>(&h); }
+    }
+    *reinterpret_cast<uint4*>(out + (long long)n * p.out_img_stride + (long long)(oy * p.Wo + ox) * p.out_pix_stride + c) =
+        make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// First-layer patch extraction for the tensor-core path: x[N,3,H,W] fp32 NCHW -> patches[N,H,W,32] 16-bit with
+// channel = (ky*3 + kx)*3 + ci for the 3x3 / pad 1 neighbourhood (27 values) and 5 zero channels, so that
+// conv1_1 (Cin = 3, reference base.0) becomes a K = 32 GEMM row per pixel instead of a CUDA-core convolution.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+patch27_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int N, int H, int W) {
+  const long long hw = (long long)H * W, total = (long long)N * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / hw;
+    const int r = (int)(i - n * hw), y = r / W, x = r - y * W;
+    float v[32];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = y + ky - 1, ix = x + kx - 1;
+        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = ok ? in[(n * 3 + c) * hw + (long long)iy * W + ix] : 0.f;
+      }
+#pragma unroll
+    for (int e = 27; e < 32; ++e) v[e] = 0.f;
+    uint32_t o[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]); o[e] = *reinterpret_cast<uint32_t*>(&h); }
+      else { __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]); o[e] = *reinterpret_cast<uint32_t*>(&h); }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + i * 32);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dst[e] = make_uint4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+  }
+}
+
 // x[N,C,H,W] fp32 -> NHWC (RFBNet.forward takes NCHW, RFB_Net_vgg.py:210)
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ in, void* __restrict__ out, int N, int C, int H, int W, int dtype) {
@@ -235,6 +312,15 @@ int maxpool_launch(const CtxPoolParams* p, cudaStream_t st) {
   CTX_REQUIRE((p->Ho - 1) * p->stride - p->pad < p->H && (p->Wo - 1) * p->stride - p->pad < p->W,
               "maxpool: last window starts outside the input");
   long long total = (long long)p->N * p->Ho * p->Wo * p->C;
+  const bool vec = p->dtype != CTX_F32 && p->C % 8 == 0 && p->in_pix_stride % 8 == 0 && p->out_pix_stride % 8 == 0 &&
+                   p->in_img_stride % 8 == 0 && p->out_img_stride % 8 == 0 && ((uintptr_t)p->in) % 16 == 0 && ((uintptr_t)p->out) % 16 == 0;
+  if (vec) {
+    int blocks = (int)std::min<long long>((total / 8 + 255) / 256, 148LL * 32);
+    if (p->dtype == CTX_BF16) maxpool_nhwc_vec8_kernel<true><<<blocks, 256, 0, st>>>(*p);
+    else maxpool_nhwc_vec8_kernel<false><<<blocks, 256, 0, st>>>(*p);
+    CTX_LAUNCH_CHECK();
+    return CTX_OK;
+  }
   int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
   maxpool_nhwc_kernel<<<blocks, 256, 0, st>>>(*p);
   CTX_LAUNCH_CHECK();
@@ -246,6 +332,17 @@ int nchw_to_nhwc_launch(const float* in, void* out, int N, int C, int H, int W, 
   long long total = (long long)N * H * W;
   int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
   nchw_to_nhwc_kernel<<<blocks, 256, 0, st>>>(in, out, N, C, H, W, dtype);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
+int patch27_launch(const float* in, void* out, int N, int H, int W, int dtype, cudaStream_t st) {
+  CTX_REQUIRE(in && out && N > 0 && H > 0 && W > 0, "patch27: bad arguments");
+  CTX_REQUIRE(dtype == CTX_BF16 || dtype == CTX_F16, "patch27: 16-bit output only");
+  long long total = (long long)N * H * W;
+  int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+  if (dtype == CTX_BF16) patch27_kernel<true><<<blocks, 256, 0, st>>>(in, (uint16_t*)out, N, H, W);
+  else patch27_kernel<false><<<blocks, 256, 0, st>>>(in, (uint16_t*)out, N, H, W);
   CTX_LAUNCH_CHECK();
   return CTX_OK;
 }
@@ -265,6 +362,9 @@ extern "C" int ctx_conv2d_simt(const CtxConvParams* p, void* stream) { return ct
 extern "C" int ctx_maxpool2d_nhwc(const CtxPoolParams* p, void* stream) { return ctx::maxpool_launch(p, (cudaStream_t)stream); }
 extern "C" int ctx_nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, int out_dtype, void* stream) {
   return ctx::nchw_to_nhwc_launch(in, out, N, C, H, W, out_dtype, (cudaStream_t)stream);
+}
+extern "C" int ctx_nchw_to_patch27(const float* in, void* out, int N, int H, int W, int out_dtype, void* stream) {
+  return ctx::patch27_launch(in, out, N, H, W, out_dtype, (cudaStream_t)stream);
 }
 extern "C" int ctx_softmax_lastdim(const float* in, float* out, long long rows, int cols, void* stream) {
   return ctx::softmax_launch(in, out, rows, cols, (cudaStream_t)stream);

@@ -14,9 +14,10 @@ int conv_simt_launch(const CtxConvParams* p, cudaStream_t st);
 int maxpool_launch(const CtxPoolParams* p, cudaStream_t st);
 int nchw_to_nhwc_launch(const float* in, void* out, int N, int C, int H, int W, int dtype, cudaStream_t st);
 int softmax_launch(const float* in, float* out, long long rows, int cols, cudaStream_t st);
+int patch27_launch(const float* in, void* out, int N, int H, int W, int dtype, cudaStream_t st);
 int attention_simt_launch(const CtxAttnParams* p, cudaStream_t st);
 
-enum OpKind { OP_CONV_SIMT, OP_CONV_TC, OP_POOL, OP_NCHW2NHWC, OP_ATTN, OP_SOFTMAX };
+enum OpKind { OP_CONV_SIMT, OP_CONV_TC, OP_POOL, OP_NCHW2NHWC, OP_PATCH27, OP_ATTN, OP_SOFTMAX };
 
 struct Op {
   OpKind kind;
@@ -41,6 +42,7 @@ static int run_op(Op& op, cudaStream_t st) {
     case OP_CONV_TC: return ctx_conv2d_tc_plan_run(op.tc_plan, st);
     case OP_POOL: return maxpool_launch(&op.pool, st);
     case OP_NCHW2NHWC: return nchw_to_nhwc_launch(op.cvt.in, op.cvt.out, op.cvt.N, op.cvt.C, op.cvt.H, op.cvt.W, op.cvt.dtype, st);
+    case OP_PATCH27: return patch27_launch(op.cvt.in, op.cvt.out, op.cvt.N, op.cvt.H, op.cvt.W, op.cvt.dtype, st);
     case OP_ATTN: return attention_simt_launch(&op.attn, st);
     case OP_SOFTMAX: return softmax_launch(op.sm.in, op.sm.out, op.sm.rows, op.sm.cols, st);
   }
@@ -106,6 +108,14 @@ extern "C" int ctx_prog_add_nchw_to_nhwc(void* prog, const float* in, void* out,
   PROG_OR_FAIL(prog);
   Op op{}; op.kind = OP_NCHW2NHWC;
   op.cvt.in = in; op.cvt.out = out; op.cvt.N = N; op.cvt.C = C; op.cvt.H = H; op.cvt.W = W; op.cvt.dtype = out_dtype;
+  pr->ops.push_back(op);
+  return CTX_OK;
+}
+
+extern "C" int ctx_prog_add_nchw_to_patch27(void* prog, const float* in, void* out, int N, int H, int W, int out_dtype) {
+  PROG_OR_FAIL(prog);
+  Op op{}; op.kind = OP_PATCH27;
+  op.cvt.in = in; op.cvt.out = out; op.cvt.N = N; op.cvt.C = 3; op.cvt.H = H; op.cvt.W = W; op.cvt.dtype = out_dtype;
   pr->ops.push_back(op);
   return CTX_OK;
 }

@@ -165,7 +165,7 @@ class Engine(object):
         flops = 2.0 * src.N * Ho * Wo * Cout * Cin * KH * KW
         use_tc = self.precision != 'fp32' and self.L.ctx_conv2d_tc_supported(C.byref(p)) == 1
         if use_tc:
-            cin_p = (Cin + 63) // 64 * 64 if Cin > 32 else ((Cin + 15) // 16 * 16)
+            cin_p = (Cin + 63) // 64 * 64
             cout_p = (Cout + 15) // 16 * 16
             wt = torch.zeros(cout_p, KH * KW, cin_p, dtype=self.act_dtype, device=self.dev)
             wt[:Cout, :, :Cin] = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin).to(self.act_dtype)
@@ -231,10 +231,22 @@ class Engine(object):
     def _compile(self, net):
         B, S = self.batch, net.size
         self.x_in = self._alloc(B, 3, S, S, dtype=torch.float32)
-        x = self._new_view(B, S, S, 3)
-        _lib.check(self.L.ctx_prog_add_nchw_to_nhwc(self.prog, self.x_in.data_ptr(), x.buf.data_ptr(), B, 3, S, S,
-                                                    self.act_code), 'ctx_prog_add_nchw_to_nhwc')
-        self.layers.append(('input.nhwc', 'layout', 0.0, (B, 3, S, S)))
+        stem = net.base[0]
+        stem_as_gemm = (self.precision != 'fp32' and isinstance(stem, nn.Conv2d) and stem.in_channels == 3
+                        and stem.kernel_size == (3, 3) and stem.stride == (1, 1) and stem.padding == (1, 1)
+                        and stem.dilation == (1, 1))
+        if stem_as_gemm:
+            # Cin = 3 cannot feed the tensor cores: lay the input out as 3x3 patches (K = 27 -> 32) and run
+            # the stem conv as a 1x1 conv over them
+            x = self._new_view(B, S, S, 32)
+            _lib.check(self.L.ctx_prog_add_nchw_to_patch27(self.prog, self.x_in.data_ptr(), x.buf.data_ptr(), B, S, S,
+                                                           self.act_code), 'ctx_prog_add_nchw_to_patch27')
+            self.layers.append(('input.patch27', 'layout', 0.0, (B, 3, S, S)))
+        else:
+            x = self._new_view(B, S, S, 3)
+            _lib.check(self.L.ctx_prog_add_nchw_to_nhwc(self.prog, self.x_in.data_ptr(), x.buf.data_ptr(), B, 3, S, S,
+                                                        self.act_code), 'ctx_prog_add_nchw_to_nhwc')
+            self.layers.append(('input.nhwc', 'layout', 0.0, (B, 3, S, S)))
         sources = []
 
         def run_base(lo, hi, x):
@@ -244,6 +256,12 @@ class Engine(object):
                 if isinstance(m, nn.Conv2d):
                     relu = k + 1 < len(net.base) and isinstance(net.base[k + 1], nn.ReLU)
                     w, b = self._fold(m, None)
+                    if k == 0 and stem_as_gemm:
+                        wp = torch.zeros(w.size(0), 32, 1, 1, device=self.dev)
+                        wp[:, :27, 0, 0] = w.permute(0, 2, 3, 1).reshape(w.size(0), 27)    # (ky, kx, ci) order of patch27
+                        x = self._emit_conv('base.0', x, wp, b, 1, (0, 0), 1, relu)
+                        k += 2 if relu else 1
+                        continue
                     x = self._emit_conv('base.%d' % k, x, w, b, m.stride[0], _pair(m.padding), m.dilation[0], relu)
                     k += 2 if relu else 1
                 elif isinstance(m, nn.MaxPool2d):
@@ -318,7 +336,6 @@ class Engine(object):
             n_novel = net.OBJ_Target.out_features
             n_out = n_novel + (Csrc if incre else 0)
             self.conf = self._alloc(B, P, n_out, dtype=torch.float32)
-            self.kv = self._alloc(B, Pk, 2 * Csrc, dtype=torch.float32)
             f32 = lambda t: self._hold(t.detach().to(self.dev, torch.float32).contiguous())
             ap = _lib.CtxAttnParams()
             ap.batch, ap.num_priors, ap.num_pooled, ap.dim = B, P, Pk, Csrc
@@ -332,7 +349,11 @@ class Engine(object):
             ap.Wz = f32(net.Wz)
             ap.obj_target_w = f32(net.OBJ_Target.weight)
             ap.scale = float(net.scale.detach().float().cpu().item())
-            ap.kv_scratch, ap.out = self.kv.data_ptr(), self.conf.data_ptr()
+            ap.use_tensor_cores = int(self.precision != 'fp32')
+            ws_bytes = self.L.ctx_attention_workspace_bytes(C.byref(ap))
+            self.attn_ws = self._alloc(ws_bytes + 1024, dtype=torch.uint8)
+            ws_ptr = (self.attn_ws.data_ptr() + 1023) // 1024 * 1024
+            ap.workspace, ap.workspace_bytes, ap.out = ws_ptr, ws_bytes, self.conf.data_ptr()
             _lib.check(self.L.ctx_prog_add_attention(self.prog, C.byref(ap)), 'ctx_prog_add_attention')
             self.layers.append(('context_transformer', 'attention', 4.0 * B * P * Pk * Csrc, (B, P, Pk, Csrc)))
         else:

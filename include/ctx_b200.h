@@ -122,6 +122,9 @@ void ctx_conv2d_tc_plan_destroy(void* plan);
 int ctx_maxpool2d_nhwc(const CtxPoolParams* p, void* stream);
 /* x[N,3,H,W] fp32 NCHW (RFBNet.forward input, :210) -> NHWC of dtype */
 int ctx_nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, int out_dtype, void* stream);
+/* x[N,3,H,W] fp32 -> 3x3/pad-1 patches [N,H,W,32] 16-bit (27 values, channel = (ky*3+kx)*3+ci, + 5 zeros): turns the
+ * Cin = 3 stem conv (vgg() base.0, RFB_Net_vgg.py:331) into a K = 32 tensor-core GEMM */
+int ctx_nchw_to_patch27(const float* in, void* out, int N, int H, int W, int out_dtype, void* stream);
 
 /* ---- Context-Transformer : models/RFB_Net_vgg.py:253-271 (+ :273-285 output activation) ------ */
 typedef struct CtxAttnParams {
@@ -136,9 +139,12 @@ typedef struct CtxAttnParams {
   const float* Wz;                             /* [dim] */
   const float* obj_target_w;                   /* [num_novel, dim] */
   float scale;
-  float* kv_scratch;                           /* [B,Pk,2*dim] fp32 */
+  int use_tensor_cores;                        /* 0: fp32 CUDA-core kernel (1e-4 parity mode); 1: tcgen05 kernel, fp16 hi/lo split operands */
+  void* workspace;                             /* ctx_attention_workspace_bytes(p) bytes, 1024-byte aligned */
+  size_t workspace_bytes;
   float* out;                                  /* [B,P, incre ? dim+num_novel : num_novel] */
 } CtxAttnParams;
+size_t ctx_attention_workspace_bytes(const CtxAttnParams* p);   /* reads batch, num_priors, num_pooled, dim, use_tensor_cores */
 int ctx_attention_forward(const CtxAttnParams* p, void* stream);
 /* row softmax over the last dim (C <= 128) — output activation :279-285 for obj / non-'ours' conf */
 int ctx_softmax_lastdim(const float* in, float* out, long long rows, int cols, void* stream);
@@ -149,6 +155,7 @@ int ctx_prog_add_conv_simt(void* prog, const CtxConvParams* p);
 int ctx_prog_add_conv_tc(void* prog, const CtxConvParams* p);
 int ctx_prog_add_pool(void* prog, const CtxPoolParams* p);
 int ctx_prog_add_nchw_to_nhwc(void* prog, const float* in, void* out, int N, int C, int H, int W, int out_dtype);
+int ctx_prog_add_nchw_to_patch27(void* prog, const float* in, void* out, int N, int H, int W, int out_dtype);
 int ctx_prog_add_attention(void* prog, const CtxAttnParams* p);
 int ctx_prog_add_softmax(void* prog, const float* in, float* out, long long rows, int cols);
 int ctx_prog_num_ops(void* prog);

@@ -1,0 +1,313 @@
+"""GPU parity: Detect / NMS / soft-NMS / fused post-processing / match / ranking / loss through the
+C ABI against the CPU oracle and the golden vectors of the real reference.
+Bar: kept indices, prior indices, class ids, labels, ranks bit-exact; floats within the stated
+tolerance (decode uses expf, encode uses logf: <= 2 ulp from the CPU libm)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import context_transformer_b200 as ctx
+from context_transformer_b200 import _lib
+from oracle import c_oracle, np_oracle, synth
+from oracle.gen_golden import ROW_STRIDE
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _heads(B, P, C, seed=0):
+    return synth.calibrated_heads(B, P, C, seed=seed)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_detect_forward_vs_oracle_and_golden(golden):
+    g = golden('post_voc300.npz')
+    priors = ctx.PriorBox(ctx.VOC_300).forward()
+    loc, conf, obj = _heads(2, priors.size(0), 20)
+    det = ctx.Detect(21, 0, ctx.VOC_300)
+    boxes, scores = det.forward((loc.to(DEV), conf.to(DEV), obj.to(DEV)), priors.to(DEV))
+    assert boxes.is_cuda and tuple(boxes.shape) == (2, 11620, 4) and tuple(scores.shape) == (2, 11620, 21)
+    assert det.boxes is boxes and det.scores is scores
+    ob, os_ = np_oracle.detect(loc.numpy(), conf.numpy(), obj.numpy(), priors.numpy())
+    assert np.array_equal(scores.cpu().numpy(), os_)                       # one fp32 multiply: exact
+    assert np.allclose(boxes.cpu().numpy(), ob, rtol=0, atol=2e-6)         # expf vs libm exp
+    assert np.allclose(boxes.cpu().numpy()[:, ::ROW_STRIDE], g['boxes'], rtol=0, atol=2e-6)
+    assert np.array_equal(scores.cpu().numpy()[:, ::ROW_STRIDE], g['scores'])
+
+
+def test_decode_helper():
+    priors = ctx.PriorBox(ctx.COCO_300).forward()
+    loc = torch.randn(priors.size(0), 4, generator=synth._gen(5, 'loc'))
+    got = ctx.decode(loc.to(DEV), priors.to(DEV), [0.1, 0.2]).cpu().numpy()
+    assert np.allclose(got, np_oracle.decode(loc.numpy(), priors.numpy()), rtol=0, atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n', [1, 2, 63, 64, 65, 300, 2000, 4096, 4097, 9000])
+def test_hard_nms_bit_exact(golden, n):
+    seed = {0: 0, 1: 1, 63: 2, 64: 3, 65: 4, 300: 5, 2000: 6}.get(n, n)
+    d = synth.random_dets(n, seed=seed)
+    for on_equal in (False, True):
+        got = ctx.nms(d, 0.45, force_cpu=on_equal)
+        assert got == c_oracle.cpu_nms(d, 0.45, on_equal)
+        key = 'keep_%s_%d' % ('ge' if on_equal else 'gt', n)
+        g = golden('nms.npz')
+        if key in g.files:
+            assert got == g[key].tolist()
+    dev_keep = ctx.nms_device(torch.from_numpy(d).to(DEV), 0.45).cpu().tolist()
+    assert dev_keep == c_oracle.cpu_nms(d, 0.45, False)
+
+
+def test_hard_nms_threshold_sweep_and_ties():
+    d = synth.random_dets(1500, seed=21)
+    for t in (0.0, 0.1, 0.3, 0.7, 1.0):
+        for on_equal in (False, True):
+            assert ctx.nms(d, t, force_cpu=on_equal) == c_oracle.cpu_nms(d, t, on_equal)
+    # ties in score: order is (score desc, index asc) in both the oracle and the kernel
+    d2 = synth.random_dets(800, seed=22, tie_free=False)
+    d2[:, 4] = np.round(d2[:, 4] * 20) / 20
+    assert ctx.nms(d2, 0.45) == c_oracle.cpu_nms(d2, 0.45, False)
+    # identical boxes: IoU == 1 exactly; ">= 1.0" suppresses, "> 1.0" does not
+    d3 = np.tile(np.array([[10, 10, 50, 60, 0.5]], np.float32), (5, 1))
+    d3[:, 4] = [0.5, 0.9, 0.7, 0.6, 0.8]
+    assert ctx.nms(d3, 1.0, force_cpu=True) == [1]
+    assert ctx.nms(d3, 1.0, force_cpu=False) == [1, 4, 2, 3, 0]
+
+
+def test_legacy_nms_abi_presorted():
+    """void _nms(keep, num, boxes_host, n, dim, thresh, device) — gpu_nms.hpp:1-2 contract."""
+    d = synth.random_dets(700, seed=31)
+    order = np.argsort(-d[:, 4], kind='stable')
+    sorted_d = np.ascontiguousarray(d[order])
+    keep = np.empty(700, np.int32)
+    num = ctypes.c_int(-1)
+    _lib.lib()._nms(keep.ctypes.data, ctypes.addressof(num), sorted_d.ctypes.data, 700, 5, 0.45, 0)
+    got = order[keep[:num.value]].tolist()
+    assert got == c_oracle.cpu_nms(d, 0.45, False)
+
+
+@pytest.mark.parametrize('method', [0, 1, 2])
+@pytest.mark.parametrize('n', [1, 2, 65, 300, 1500])
+def test_soft_nms_bit_exact(golden, method, n):
+    seed = {1: 1, 65: 4, 300: 5}.get(n, n)
+    d = synth.random_dets(n, seed=seed)
+    want, n_want = c_oracle.cpu_soft_nms(d, 0.5, 0.3, 0.001, method)
+    got = d.copy()
+    keep = ctx.cpu_soft_nms(got, sigma=0.5, Nt=0.3, threshold=0.001, method=method)
+    assert keep == list(range(n_want))
+    assert np.array_equal(got[:n_want, :4], want[:, :4])
+    if method == 2:      # gaussian weight goes through exp(): double exp on both sides, allow 1 ulp
+        assert np.allclose(got[:n_want, 4], want[:, 4], rtol=2e-7, atol=0)
+    else:
+        assert np.array_equal(got[:n_want, 4], want[:, 4])
+    key = 'soft_m%d_%d' % (method, n)
+    g = golden('nms.npz')
+    if key in g.files and method != 2:
+        assert np.array_equal(got[:n_want], g[key])
+
+
+# ---------------------------------------------------------------------------------------------
+def _oracle_records(loc, conf, obj, priors, scale, on_equal, thresh=0.01, nms_thresh=0.45, max_per_image=200):
+    boxes, scores = np_oracle.detect(loc, conf, obj, priors)
+    out = []
+    for b in range(loc.shape[0]):
+        sc = scale[b] if np.ndim(scale) == 2 else scale
+        dets, idx = np_oracle.postprocess_image(boxes[b], scores[b], sc, thresh, nms_thresh, max_per_image,
+                                                nms_fn=lambda d, t: c_oracle.cpu_nms(d, t, on_equal))
+        out.append(np_oracle.records_from_dets(dets, idx))
+    return out
+
+
+def _check_records(rec, cnt, pidx, want):
+    rec, cnt, pidx = rec.cpu().numpy(), cnt.cpu().numpy(), pidx.cpu().numpy()
+    for b, (wrec, widx) in enumerate(want):
+        n = len(wrec)
+        assert cnt[b] == n
+        assert np.array_equal(pidx[b, :n], widx.astype(np.int32))           # which prior, in which order: exact
+        assert np.array_equal(rec[b, :n, 5], wrec[:, 5])                    # class ids: exact
+        assert np.array_equal(rec[b, :n, 4], wrec[:, 4])                    # scores: one fp32 multiply, exact
+        assert np.allclose(rec[b, :n, :4], wrec[:, :4], rtol=0, atol=1e-3)  # pixels (<= 500 * 2e-6)
+        assert np.all(pidx[b, n:] == -1)
+
+
+@pytest.mark.parametrize('on_equal', [False, True])
+def test_postprocess_calibrated_vs_oracle_and_golden(golden, on_equal):
+    g = golden('post_voc300.npz')
+    priors = ctx.PriorBox(ctx.VOC_300).forward()
+    loc, conf, obj = _heads(2, priors.size(0), 20)
+    post = ctx.DetectPost(21, 0, ctx.VOC_300, suppress_on_equal=on_equal)
+    rec, cnt, pidx = post.forward((loc.to(DEV), conf.to(DEV), obj.to(DEV)), priors.to(DEV), g['scale'])
+    want = _oracle_records(loc.numpy(), conf.numpy(), obj.numpy(), priors.numpy(), g['scale'], on_equal)
+    _check_records(rec, cnt, pidx, want)
+    conv = 'ge' if on_equal else 'gt'
+    for b in range(2):
+        n = int(cnt[b])
+        assert np.array_equal(pidx[b, :n].cpu().numpy(), g['prior_idx_%s_%d' % (conv, b)])
+        assert np.array_equal(rec[b, :n, 4:].cpu().numpy(), g['records_%s_%d' % (conv, b)][:, 4:])
+        assert np.allclose(rec[b, :n, :4].cpu().numpy(), g['records_%s_%d' % (conv, b)][:, :4], rtol=0, atol=1e-3)
+
+
+def test_postprocess_per_image_scale_and_no_topk():
+    priors = ctx.PriorBox(ctx.COCO_300).forward()
+    B = 3
+    loc, conf, obj = _heads(B, priors.size(0), 20, seed=3)
+    scale = np.array([[500, 375, 500, 375], [640, 480, 640, 480], [300, 300, 300, 300]], np.float32)
+    post = ctx.DetectPost(21, 0, ctx.COCO_300, max_per_image=0, max_out=16384)
+    rec, cnt, pidx = post.forward((loc.to(DEV), conf.to(DEV), obj.to(DEV)), priors.to(DEV), scale)
+    want = _oracle_records(loc.numpy(), conf.numpy(), obj.numpy(), priors.numpy(), scale, False, max_per_image=0)
+    _check_records(rec, cnt, pidx, want)
+
+
+def test_postprocess_dense_worst_case_and_empty():
+    """Random-weight regime: every prior passes the threshold in every class, and the
+    opposite extreme where nothing does."""
+    g = synth._gen(9, 'dense')
+    B, P, C = 2, 1500, 3
+    priors = torch.rand(P, 4, generator=g) * 0.5 + 0.1
+    loc = torch.randn(B, P, 4, generator=g) * 0.5
+    conf = torch.softmax(torch.randn(B, P, C, generator=g), -1)
+    obj = torch.softmax(torch.randn(B, P, 2, generator=g), -1)
+    cfg = {'variance': [0.1, 0.2]}
+    scale = np.array([500, 375, 500, 375], np.float32)
+    post = ctx.DetectPost(C + 1, 0, cfg, score_thresh=0.0, max_per_image=200)
+    rec, cnt, pidx = post.forward((loc.to(DEV), conf.to(DEV), obj.to(DEV)), priors.to(DEV), scale)
+    want = _oracle_records(loc.numpy(), conf.numpy(), obj.numpy(), priors.numpy(), scale, False, thresh=0.0)
+    _check_records(rec, cnt, pidx, want)
+    post_none = ctx.DetectPost(C + 1, 0, cfg, score_thresh=2.0)
+    rec, cnt, pidx = post_none.forward((loc.to(DEV), conf.to(DEV), obj.to(DEV)), priors.to(DEV), scale)
+    assert cnt.cpu().tolist() == [0, 0] and float(rec.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize('method', [1, 2, 3])
+def test_postprocess_soft_nms(method):
+    priors = ctx.PriorBox(ctx.VOC_300).forward()
+    loc, conf, obj = _heads(1, priors.size(0), 20, seed=4)
+    scale = np.array([500, 375, 500, 375], np.float32)
+    post = ctx.DetectPost(21, 0, ctx.VOC_300, nms_thresh=0.3, nms_method=method, max_per_image=0, max_out=16384)
+    rec, cnt, pidx = post.forward((loc.to(DEV), conf.to(DEV), obj.to(DEV)), priors.to(DEV), scale)
+    # soft-NMS decays scores by a function of the IoU, so it is fed the SAME decoded boxes as the kernel
+    # (GPU expf vs libm exp differ by <= 2 ulp in w/h, which would leak into the decayed scores)
+    gb, gs = ctx.Detect(21, 0, ctx.VOC_300).forward((loc.to(DEV), conf.to(DEV), obj.to(DEV)), priors.to(DEV))
+    boxes, scores = gb.cpu().numpy(), gs.cpu().numpy()
+    bx = (boxes[0] * scale).astype(np.float32)
+    rows = []
+    for j in range(1, 21):
+        inds = np.where(scores[0][:, j] > np.float32(0.01))[0]
+        if len(inds) == 0:
+            continue
+        c_dets = np.hstack((bx[inds], scores[0][inds, j][:, None])).astype(np.float32)
+        out, n = c_oracle.cpu_soft_nms(c_dets, 0.5, 0.3, 0.001, 0 if method == 3 else method)
+        rows.append(np.hstack([out, np.full((n, 1), j, np.float32)]))
+    want = np.vstack(rows)
+    n = int(cnt[0])
+    got = rec[0, :n].cpu().numpy()
+    assert n == len(want)
+    assert np.array_equal(got[:, 5], want[:, 5])
+    assert np.array_equal(got[:, :4], want[:, :4])
+    assert np.allclose(got[:, 4], want[:, 4], rtol=3e-7 if method == 2 else 0, atol=0)
+
+
+def test_postprocess_full_size_properties():
+    """BASELINE config 3 size (512x512 priors, B = 16): properties the oracle need not be run for."""
+    priors = ctx.PriorBox(ctx.VOC_512).forward()
+    B, P = 16, priors.size(0)
+    loc, conf, obj = _heads(B, P, 20, seed=7)
+    scale = np.array([512, 512, 512, 512], np.float32)
+    post = ctx.DetectPost(21, 0, ctx.VOC_512)
+    pred = (loc.to(DEV), conf.to(DEV), obj.to(DEV))
+    rec, cnt, pidx = post.forward(pred, priors.to(DEV), scale)
+    rec2, cnt2, pidx2 = post.forward(pred, priors.to(DEV), scale)
+    assert torch.equal(rec, rec2) and torch.equal(cnt, cnt2) and torch.equal(pidx, pidx2)      # deterministic
+    rec, cnt, pidx = rec.cpu().numpy(), cnt.cpu().numpy(), pidx.cpu().numpy()
+    boxes, scores = ctx.Detect(21, 0, ctx.VOC_512).forward(pred, priors.to(DEV))
+    boxes, scores = boxes.cpu().numpy(), scores.cpu().numpy()
+    for b in range(B):
+        n = int(cnt[b])
+        assert 0 < n <= post.max_out
+        r = rec[b, :n]
+        cls = r[:, 5].astype(int)
+        assert np.all(np.diff(cls) >= 0)                                   # class ascending
+        for j in np.unique(cls):
+            s = r[cls == j, 4]
+            assert np.all(np.diff(s) <= 0)                                 # score descending within a class
+            # idempotence: survivors of NMS do not suppress each other
+            keep = c_oracle.cpu_nms(np.ascontiguousarray(r[cls == j, :5]), 0.45, False)
+            assert keep == list(range(len(s)))
+        # every record is the decoded prior it claims to be, with that prior's score
+        assert np.allclose(r[:, :4], boxes[b, pidx[b, :n]] * scale, rtol=0, atol=1e-3)
+        assert np.array_equal(r[:, 4], scores[b, pidx[b, :n], cls])
+        assert np.all(r[:, 4] > np.float32(0.01))
+    # one image against the oracle end to end
+    want = _oracle_records(loc.numpy()[:1], conf.numpy()[:1], obj.numpy()[:1], priors.numpy(), scale, False)
+    _check_records(torch.from_numpy(rec[:1]), torch.from_numpy(cnt[:1]), torch.from_numpy(pidx[:1]), want)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_match_vs_oracle_and_golden(golden):
+    g = golden('match_loss.npz')
+    priors = ctx.PriorBox(ctx.VOC_300).forward()
+    targets = [torch.from_numpy(np.asarray(t, dtype=np.float32)) for t in g['targets']]
+    loc_t, conf_t, obj_t, bti, ovl = ctx.match_batch(0.5, targets, priors.to(DEV), [0.1, 0.2], want_overlap=True)
+    assert np.array_equal(conf_t.cpu().numpy(), g['conf_t'])
+    assert np.array_equal(obj_t.cpu().numpy(), g['obj_t'])
+    assert np.allclose(ovl.cpu().numpy()[:, ::ROW_STRIDE], g['overlap'], rtol=0, atol=1e-6)
+    pos = conf_t[:, :, 0] != 0
+    assert np.array_equal(pos.nonzero().cpu().numpy().astype(np.int32), g['pos_index'])
+    assert np.allclose(loc_t[pos].cpu().numpy(), g['loc_t_pos'], rtol=0, atol=2e-5)
+    for i, t in enumerate(targets):
+        l, c, o, idx, raw = np_oracle.match(0.5, t[:, :4].numpy(), priors.numpy(), (0.1, 0.2), t[:, 4:6].numpy())
+        assert np.array_equal(bti[i].cpu().numpy(), idx.astype(np.int32))
+        assert np.array_equal(ovl[i].cpu().numpy(), raw)                  # IoU in reference op order: exact
+        assert np.allclose(loc_t[i].cpu().numpy(), l, rtol=0, atol=2e-5)  # logf vs libm log
+    # reference in-place signature
+    B, P = len(targets), priors.size(0)
+    lt = torch.zeros(B, P, 4, device=DEV)
+    ct = torch.zeros(B, P, 2, device=DEV)
+    ot = torch.zeros(B, P, dtype=torch.bool, device=DEV)
+    ctx.match(0.5, targets[1][:, :4].to(DEV), priors.to(DEV), [0.1, 0.2], targets[1][:, 4:6].to(DEV), lt, ct, ot, 1)
+    assert torch.equal(ct[1], conf_t[1]) and torch.equal(ot[1], obj_t[1]) and torch.equal(lt[1], loc_t[1])
+    assert float(ct[0].abs().sum()) == 0.0
+
+
+def test_match_collisions_and_many_objects():
+    """Two ground truths sharing a best prior (last one wins, box_utils.py:122-123), 40 objects."""
+    priors = ctx.PriorBox(ctx.VOC_300).forward()
+    t = torch.tensor([[0.30, 0.30, 0.60, 0.60, 3, 1.0], [0.301, 0.301, 0.601, 0.601, 7, 0.5]])
+    many = synth.synthetic_targets(1, seed=5, max_obj=4)[0].repeat(10, 1)
+    many[:, :4] += torch.rand(many.size(0), 4, generator=synth._gen(1, 'jit')) * 0.05
+    many[:, 2:4] = torch.maximum(many[:, 2:4], many[:, :2] + 0.05)
+    for tg in (t, many):
+        loc_t, conf_t, obj_t, bti = ctx.match_batch(0.5, [tg], priors.to(DEV), [0.1, 0.2])
+        l, c, o, idx, _ = np_oracle.match(0.5, tg[:, :4].numpy(), priors.numpy(), (0.1, 0.2), tg[:, 4:6].numpy())
+        assert np.array_equal(bti[0].cpu().numpy(), idx.astype(np.int32))
+        assert np.array_equal(conf_t[0].cpu().numpy(), c)
+        assert np.array_equal(obj_t[0].cpu().numpy(), o)
+
+
+@pytest.mark.parametrize('P', [100, 4096, 11620, 32756])
+def test_hard_negative_rank(P):
+    g = synth._gen(P, 'rank')
+    loss = torch.rand(3, P, generator=g)
+    loss[0, ::7] = 0.0                     # ties (positives are zeroed upstream)
+    loss[1] = torch.round(loss[1] * 50) / 50
+    rank = ctx.hard_negative_rank(loss.to(DEV)).cpu().numpy()
+    assert np.array_equal(rank, np_oracle.hard_negative_rank(loss.numpy()).astype(np.int32))
+
+
+def test_multibox_loss_vs_golden_and_oracle(golden):
+    g = golden('match_loss.npz')
+    priors = ctx.PriorBox(ctx.VOC_300).forward()
+    targets = [torch.from_numpy(np.asarray(t, dtype=np.float32)) for t in g['targets']]
+    B, P = len(targets), priors.size(0)
+    gen = synth._gen(0, 'losspred')
+    loc_p = torch.randn(B, P, 4, generator=gen).to(DEV).requires_grad_()
+    conf_p = torch.randn(B, P, 20, generator=gen).to(DEV).requires_grad_()
+    obj_p = torch.randn(B, P, 2, generator=gen).to(DEV).requires_grad_()
+    crit = ctx.MultiBoxLoss_combined(21, 0.5, True, 0, True, 3, 0.5, False)
+    out = crit((loc_p, conf_p, obj_p), priors.to(DEV), targets)
+    got = np.array([float(out['loss_box_reg']), float(out['loss_cls']), float(out['loss_obj'])])
+    assert np.allclose(got, g['loss'], rtol=2e-5)
+    sum(out.values()).backward()
+    assert loc_p.grad is not None and float(conf_p.grad.abs().sum()) > 0 and float(obj_p.grad.abs().sum()) > 0

@@ -1,0 +1,160 @@
+"""CPU: host-side logic of the product package and the C-ABI library (load + exports only)."""
+import ctypes
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import context_transformer_b200 as ctx
+from context_transformer_b200 import _lib, engine, shard
+from oracle import synth
+from oracle.gen_golden import ROW_STRIDE
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, 'include', 'ctx_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    names = re.findall(r'^\s*(?:[\w\s\*]+?)\b(\w+)\s*\([^;{]*\)\s*;', text, flags=re.M)
+    return sorted(set(n for n in names if n.startswith('ctx_') or n == '_nms'))
+
+
+def test_library_exports_every_declared_symbol():
+    _lib_path = _lib.LIB_PATH
+    if not os.path.exists(_lib_path):
+        from context_transformer_b200 import build
+        build.build_library()
+    declared = _header_functions()
+    assert len(declared) >= 35
+    raw = ctypes.CDLL(_lib_path)
+    for name in declared:
+        assert hasattr(raw, name), 'libctx_b200.so does not export %s' % name
+    assert sorted(_lib.SIGNATURES) == declared
+    L = _lib.lib()
+    assert L.ctx_version() >= 100
+    assert L.ctx_last_error() is not None
+    # pure-host size queries (no GPU needed)
+    assert L.ctx_postprocess_workspace_bytes(2, 11620, 20) > 2 * 11620 * 16
+    assert L.ctx_nms_workspace_bytes(1000) >= 1024 * 8
+    assert L.ctx_rank_workspace_bytes(4, 11620) >= 4 * 16384 * 8
+
+
+def test_struct_layouts_match_header_sizes():
+    # the C structs are plain ints/floats/pointers: ctypes' natural alignment == the compiler's
+    assert ctypes.sizeof(_lib.CtxPostParams) == 14 * 4
+    assert ctypes.sizeof(_lib.CtxOutSeg) == 40
+    assert ctypes.sizeof(_lib.CtxConvParams) == 17 * 4 + 4 + 4 * 8 + 4 * 4 + 3 * 40
+    assert ctypes.sizeof(_lib.CtxPoolParams) == 10 * 4 + 8 + 8 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.CtxAttnParams) == 7 * 4 + 4 + 12 * 8 + 8 + 8 + 8 + 8
+
+
+@pytest.mark.parametrize('name', ['VOC_300', 'VOC_512', 'COCO_300', 'COCO_512'])
+def test_prior_box_bit_exact(golden, name):
+    cfg = getattr(ctx, name)
+    p = ctx.PriorBox(cfg).forward()
+    assert p.dtype == torch.float32 and tuple(p.shape) == (ctx.num_priors(cfg), 4)
+    assert np.array_equal(p.numpy(), golden('priors.npz')[name])
+
+
+def test_prior_box_rejects_bad_variance():
+    cfg = dict(ctx.VOC_300)
+    cfg['variance'] = [0.1, -0.2]
+    with pytest.raises(ValueError):
+        ctx.PriorBox(cfg)
+
+
+def test_build_net_surface():
+    assert ctx.build_net(types.SimpleNamespace(method='ours', phase=2, setting='transfer'), 400, 60) is None
+    net = ctx.build_net(types.SimpleNamespace(method='ours', phase=2, setting='incre'), 300, 15)
+    assert net.size == 300 and net.indicator == 3
+    for name in ('base', 'Norm', 'extras', 'loc', 'conf', 'obj', 'theta', 'phi', 'g', 'OBJ_Target', 'fc_base'):
+        assert hasattr(net, name)
+    assert tuple(net.Wz.shape) == (15,) and float(net.scale) == 5.0 and not net.scale.requires_grad
+    net.OBJ_Target.weight.data.normal_()
+    net.normalize()
+    assert torch.allclose(net.OBJ_Target.weight.norm(dim=1), torch.ones(5), atol=1e-6)
+    # LR groups of utils/solver.py key on these substrings
+    names = [n for n, _ in net.named_parameters()]
+    assert any(n.startswith('base.') for n in names) and any(n.startswith('extras.') for n in names)
+    assert any(n.startswith('Norm.') for n in names)
+
+
+def test_eval_forward_refuses_cpu():
+    net = ctx.build_net(types.SimpleNamespace(method='ft', phase=2, setting='transfer'), 300, 20).eval()
+    x = torch.zeros(1, 3, 300, 300)
+    with pytest.raises(AttributeError):
+        net(x)                                    # device not assigned by the caller yet
+    net.device = 'cpu'
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        net(x)
+
+
+def test_autograd_forward_init_matches_reference(golden):
+    """init=True prototype-extraction path (train.py:252-286) — autograd expression, runs anywhere."""
+    g = golden('net_ours_transfer_300.npz')
+    net = ctx.build_net(types.SimpleNamespace(method='ours', phase=2, setting='transfer'), 300, 60)
+    net.load_state_dict(synth.seeded_state(net.state_dict(), seed=0))
+    net.eval()
+    net.device = 'cpu'
+    with torch.no_grad():
+        conf = net(synth.seeded_input(2, 300, seed=0), init=True)
+    assert np.allclose(conf.numpy()[:, ::ROW_STRIDE], g['conf_init'], rtol=0, atol=2e-5)
+
+
+def test_ours_at_512_raises_like_reference():
+    net = ctx.build_net(types.SimpleNamespace(method='ours', phase=2, setting='transfer'), 512, 60)
+    net.device = 'cpu'
+    net.train()
+    with pytest.raises(IndexError):
+        net(torch.zeros(2, 3, 512, 512))
+
+
+def test_pool_out_ceil_mode():
+    for h, k, s, pad, ceil_mode in [(75, 2, 2, 0, True), (38, 3, 3, 0, True), (19, 2, 2, 0, True), (10, 2, 2, 0, True),
+                                    (5, 2, 2, 0, True), (3, 1, 1, 0, True), (19, 3, 1, 1, False), (300, 2, 2, 0, False)]:
+        want = torch.nn.functional.max_pool2d(torch.zeros(1, 1, h, h), k, s, pad, ceil_mode=ceil_mode).shape[-1]
+        assert engine._pool_out(h, k, s, pad, ceil_mode) == want
+
+
+def test_nms_wrapper_empty_and_validation():
+    assert ctx.nms(np.zeros((0, 5), np.float32), 0.45) == []
+    assert ctx.nms(np.zeros((0, 5), np.float32), 0.45, force_cpu=True) == []
+    with pytest.raises(ValueError):
+        ctx.cpu_soft_nms(np.zeros((3, 4), np.float32))
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.CtxError):
+            ctx.nms(np.ones((3, 5), np.float32), 0.45)
+
+
+def test_detect_requires_cuda_tensors():
+    if torch.cuda.is_available():
+        pytest.skip('CPU-only check')
+    det = ctx.Detect(21, 0, ctx.VOC_300)
+    with pytest.raises(_lib.CtxError):
+        det.forward((torch.zeros(1, 8, 4), torch.zeros(1, 8, 20), torch.zeros(1, 8, 2)), torch.zeros(8, 4))
+
+
+def test_shard_bounds_and_packing():
+    assert shard.shard_bounds(256, 8, 3) == (96, 128)
+    with pytest.raises(ValueError):
+        shard.shard_bounds(10, 4, 0)
+    rec = torch.randn(3, 7, 6)
+    cnt = torch.tensor([0, 7, 11620 * 20], dtype=torch.int32)
+    r2, c2 = shard.unpack_records(shard.pack_records(rec, cnt))
+    assert torch.equal(r2, rec) and torch.equal(c2, cnt)
+    r3, c3 = shard.gather_records(rec, cnt)          # no process group: identity
+    assert torch.equal(r3, rec) and torch.equal(c3, cnt)
+
+
+def test_records_to_all_boxes():
+    rec = torch.zeros(1, 5, 6)
+    rec[0, 0] = torch.tensor([1., 2, 3, 4, .9, 3])
+    rec[0, 1] = torch.tensor([5., 6, 7, 8, .8, 3])
+    rec[0, 2] = torch.tensor([9., 9, 9, 9, .7, 17])
+    ab = ctx.records_to_all_boxes(rec, torch.tensor([3]), 21)
+    assert ab[3][0].shape == (2, 5) and ab[17][0].shape == (1, 5) and ab[1][0].shape == (0, 5)
+    assert ab[3][0][1, 4] == np.float32(.8)
