@@ -48,6 +48,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
 }
@@ -132,5 +137,7 @@ EncodeTiledFn get_encode_fn();
 // 2-D row-major 16-bit tensor [rows][cols], box [box_rows][64 cols] with SWIZZLE_128B; returns 0 on success
 int encode_2d_sw128(CUtensorMap* out, const void* base, bool bf16, unsigned long long rows, unsigned long long cols,
                     unsigned box_rows);
+// NHWC 16-bit activation as a 4-D tensor, box = 64 channels x bw x bh pixels; returns 0 on success
+int encode_nhwc_sw128(CUtensorMap* out, const void* base, bool bf16, int N, int H, int W, int C, unsigned bw, unsigned bh);
 
 }  // namespace ctx

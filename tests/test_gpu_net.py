@@ -53,6 +53,8 @@ CONV_CASES = [  # cin, cout, k, stride, pad, dil, H
     (256, 512, 3, 1, 6, 6, 19), (512, 128, 1, 1, 0, 1, 19), (256, 512, 1, 2, 0, 1, 19),
     (192, 256, 3, 2, 1, 1, 19), (128, 256, 3, 1, 0, 1, 3), (128, 256, 4, 1, 1, 1, 2), (256, 24, 3, 1, 1, 1, 1),
     (64, 360, 3, 1, 1, 1, 10),
+    # large maps, Cin % 64 == 0, stride 1: the TMA activation path (32 x 4 pixel patches of a 31 x 32 map)
+    (64, 64, 3, 1, 1, 1, 31), (128, 208, 3, 1, 3, 3, 31), (64, 96, 1, 1, 0, 1, 31), (192, 64, (3, 1), 1, (1, 0), 1, 31),
 ]
 
 
@@ -68,7 +70,10 @@ def test_conv_kernel_vs_torch(case, precision):
     w = torch.randn(cout, cin, kh, kw, generator=g) * (2.0 / (cin * kh * kw)) ** 0.5
     b = torch.randn(cout, generator=g) * 0.1
     e = _Scratch(precision)
-    src, _ = _nhwc_view(x, e.act_dtype, pad_c=8, coff=8 if cin % 8 == 0 else 0)
+    if H == 31:
+        src, _ = _nhwc_view(x, e.act_dtype, pad_c=64, coff=64)
+    else:
+        src, _ = _nhwc_view(x, e.act_dtype, pad_c=8, coff=8 if cin % 8 == 0 else 0)
     out = e._emit_conv('t', src, w.to(DEV), b.to(DEV), stride, (ph, pw), dil, True)
     e.go()
     got = out.tensor().float().cpu().permute(0, 3, 1, 2)
