@@ -84,6 +84,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   const uint32_t sA = smem_base, sB = smem_base + S * TC_A_STAGE;
   const uint32_t bars = sB + S * B_STAGE;
   const uint32_t full0 = bars, empty0 = bars + 8 * S, accf0 = bars + 16 * S, acce0 = accf0 + 16, tmem_slot = acce0 + 16;
+  // per-channel epilogue vector (bias with BatchNorm folded), staged once per CTA: [ceil32(Cout) + 32] floats
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 16 * S + 64 - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = p.nk;
@@ -100,6 +102,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  for (int c = threadIdx.x; c < ((p.Cout + 31) & ~31) + 32; c += TC_THREADS) s_bias[c] = c < p.Cout ? p.bias[c] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -249,8 +252,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           for (int gq = 0; gq < 4; ++gq) {
             const int c = c0 + gq * 8;
             if (c < p.Cout && gq * 8 < lim) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
               float f[8] = {__uint_as_float(v[gq * 8 + 0]) + b0.x, __uint_as_float(v[gq * 8 + 1]) + b0.y,
                             __uint_as_float(v[gq * 8 + 2]) + b0.z, __uint_as_float(v[gq * 8 + 3]) + b0.w,
                             __uint_as_float(v[gq * 8 + 4]) + b1.x, __uint_as_float(v[gq * 8 + 5]) + b1.y,
@@ -275,7 +278,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           for (int gq = 0; gq < 8; ++gq) {
             const int c = c0 + gq * 4;
             if (c < p.Cout && gq * 4 < lim) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
               float4 f = make_float4(__uint_as_float(v[gq * 4 + 0]) + b0.x, __uint_as_float(v[gq * 4 + 1]) + b0.y,
                                      __uint_as_float(v[gq * 4 + 2]) + b0.z, __uint_as_float(v[gq * 4 + 3]) + b0.w);
               if (p.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
@@ -293,7 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           for (int j = 0; j < 32; ++j) {
             const int c = c0 + j;
             if (c < p.Cout && j < lim) {
-              float f = __uint_as_float(v[j]) + p.bias[c];
+              float f = __uint_as_float(v[j]) + s_bias[c];
               if (p.residual) f += load_as(p.residual, m_lin * p.res_cstride + p.res_coffset + c, p.res_dtype);
               if (p.relu) f = fmaxf(f, 0.f);
 #pragma unroll
@@ -428,7 +431,7 @@ extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out
   t.bn = (cdiv(p->Cout, t.n_tiles_n) + 15) / 16 * 16;
   const int stage_bytes = TC_A_STAGE + t.bn * TC_BK * 2;
   pl->stages = stage_bytes <= 24 * 1024 ? 8 : (stage_bytes <= 32 * 1024 ? 6 : 4);
-  pl->smem = (size_t)pl->stages * stage_bytes + 16 * pl->stages + 64 + 1024;
+  pl->smem = (size_t)pl->stages * stage_bytes + 16 * pl->stages + 64 + 4 * (((size_t)p->Cout + 31) / 32 * 32 + 32) + 1024;
 
   int tw = 0, th = 0;
   t.a_mode = choose_patch(p, &tw, &th) ? A_TMA : A_GATHER;
