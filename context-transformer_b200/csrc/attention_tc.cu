@@ -171,52 +171,61 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t tS = tmem, tO = tmem + 128;              // S0: cols 0-63, S1: 64-127, O: 128-191
 
   if (warp == 4) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer ================= (whole warp converged, one elected lane issues)
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * AT_TILE_Q);
       tma_load_2d(sQh, &tm_q, 0, b * p.P + q0, q_full);
       tma_load_2d(sQl, &tm_q, 0, (int)p.q_rows + b * p.P + q0, q_full);
-      for (int j = 0; j < T; ++j) {
-        const int s = j & 1;
-        mbar_wait(kv_empty + 8 * s, ((j >> 1) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < T; ++j) {
+      const int s = j & 1;
+      mbar_wait(kv_empty + 8 * s, ((j >> 1) & 1) ^ 1);
+      if (elect_one()) {
         const uint32_t dst = sKV + s * 3 * AT_TILE_K;
         mbar_arrive_expect_tx(kv_full + 8 * s, 3 * AT_TILE_K);
         tma_load_2d(dst, &tm_k, 0, b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
         tma_load_2d(dst + AT_TILE_K, &tm_k, 0, (int)p.k_rows + b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
         tma_load_2d(dst + 2 * AT_TILE_K, &tm_v, j * AT_BK, b * AT_DP, kv_full + 8 * s);
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(false, AT_BQ, AT_BK);     // fp16 operands, M128 x N64 (keys or features)
-      mbar_wait(q_full, 0);
-      for (int j = 0; j <= T; ++j) {
-        if (j < T) {
-          const int s = j & 1;
-          mbar_wait(kv_full + 8 * s, (j >> 1) & 1);
-          mbar_wait(s_empty + 8 * s, ((j >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t kh = sKV + s * 3 * AT_TILE_K, kl = kh + AT_TILE_K;
+    // ================= MMA issuer ================= (whole warp converged, one elected lane issues)
+    const uint32_t idesc = make_idesc_f16(false, AT_BQ, AT_BK);     // fp16 operands, M128 x N64 (keys or features)
+    const uint64_t dQh = make_sw128_desc(sQh), dQl = make_sw128_desc(sQl), dP = make_sw128_desc(sP), dKV = make_sw128_desc(sKV);
+    mbar_wait(q_full, 0);
+    for (int j = 0; j <= T; ++j) {
+      if (j < T) {
+        const int s = j & 1;
+        mbar_wait(kv_full + 8 * s, (j >> 1) & 1);
+        mbar_wait(s_empty + 8 * s, ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t kh = dKV + (uint64_t)((s * 3 * AT_TILE_K) >> 4), kl = kh + (uint64_t)(AT_TILE_K >> 4);
           const uint32_t d = tS + s * AT_BK;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(d, make_sw128_desc(sQh + k * 32), make_sw128_desc(kh + k * 32), idesc, k ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16(d, dQh + 2 * k, kh + 2 * k, idesc, k ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(d, make_sw128_desc(sQl + k * 32), make_sw128_desc(kh + k * 32), idesc, 1u);
+          for (int k = 0; k < 4; ++k) umma_f16(d, dQl + 2 * k, kh + 2 * k, idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(d, make_sw128_desc(sQh + k * 32), make_sw128_desc(kl + k * 32), idesc, 1u);
+          for (int k = 0; k < 4; ++k) umma_f16(d, dQh + 2 * k, kl + 2 * k, idesc, 1u);
           umma_commit(s_full + 8 * s);
         }
-        if (j > 0) {
-          const int jj = j - 1, s = jj & 1;
-          mbar_wait(p_full, jj & 1);
-          tc_fence_after();
-          const uint32_t vt = sKV + s * 3 * AT_TILE_K + 2 * AT_TILE_K;
+        __syncwarp();
+      }
+      if (j > 0) {
+        const int jj = j - 1, s = jj & 1;
+        mbar_wait(p_full, jj & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t vt = dKV + (uint64_t)((s * 3 * AT_TILE_K + 2 * AT_TILE_K) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tO, make_sw128_desc(sP + k * 32), make_sw128_desc(vt + k * 32), idesc, (jj | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16(tO, dP + 2 * k, vt + 2 * k, idesc, (jj | k) ? 1u : 0u);
           umma_commit(kv_empty + 8 * s);
           umma_commit(pv_done);
         }
+        __syncwarp();
       }
     }
   } else {

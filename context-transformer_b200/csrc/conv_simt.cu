@@ -20,7 +20,7 @@ namespace ctx {
 constexpr int BM = 64, BN = 64, BK = 16, PADM = 68;
 
 struct ConvGeom {
-  int N, H, W, Cin, in_cstride, in_coffset, Cout, CoutP, KH, KW, stride, pad_h, pad_w, dil, Ho, Wo, relu;
+  int N, H, W, Cin, in_cstride, in_coffset, Cout, CoutP, KH, KW, stride, pad_h, pad_w, dil, Ho, Wo, relu, relu_cend;
   int K, M;
   int res_dtype, res_cstride, res_coffset;
 };
@@ -129,7 +129,7 @@ conv_simt_kernel(const TIn* __restrict__ in, const float* __restrict__ wgt, cons
       float v = acc[i][j];
       if (bias) v += bias[c];
       if (residual) v += load_as(residual, (long long)m * g.res_cstride + g.res_coffset + c, g.res_dtype);
-      if (g.relu) v = fmaxf(v, 0.f);
+      if (g.relu && c < g.relu_cend) v = fmaxf(v, 0.f);
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         if (s < segs.nseg && c >= segs.seg[s].c_begin && c < segs.seg[s].c_end) {
@@ -207,9 +207,10 @@ maxpool_nhwc_vec8_kernel(CtxPoolParams p) {
   }
 }
 
-// First-layer patch extraction for the tensor-core path: x[N,3,H,W] fp32 NCHW -> patches[N,H,W,32] 16-bit with
-// channel = (ky*3 + kx)*3 + ci for the 3x3 / pad 1 neighbourhood (27 values) and 5 zero channels, so that
-// conv1_1 (Cin = 3, reference base.0) becomes a K = 32 GEMM row per pixel instead of a CUDA-core convolution.
+// First-layer patch extraction for the tensor-core path: x[N,3,H,W] fp32 NCHW -> patches[N,H,W,64] 16-bit with
+// channel = (ky*3 + kx)*3 + ci for the 3x3 / pad 1 neighbourhood (27 values) and 37 zero channels (one full
+// 64-channel K-step = one 128-byte swizzle row, so the conv kernel's TMA activation path applies), so that
+// conv1_1 (Cin = 3, reference base.0) becomes a K = 64 GEMM row per pixel instead of a CUDA-core convolution.
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 patch27_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int N, int H, int W) {
@@ -235,9 +236,11 @@ patch27_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int N, 
       if (BF16) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]); o[e] = *reinterpret_cast<uint32_t*>(&h); }
       else { __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]); o[e] = *reinterpret_cast<uint32_t*>(&h); }
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + i * 32);
+    uint4* dst = reinterpret_cast<uint4*>(out + i * 64);
 #pragma unroll
     for (int e = 0; e < 4; ++e) dst[e] = make_uint4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+#pragma unroll
+    for (int e = 4; e < 8; ++e) dst[e] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -288,7 +291,7 @@ int conv_simt_launch(const CtxConvParams* p, cudaStream_t st) {
   ConvGeom g;
   g.N = p->N; g.H = p->H; g.W = p->W; g.Cin = p->Cin; g.in_cstride = p->in_cstride; g.in_coffset = p->in_coffset;
   g.Cout = p->Cout; g.CoutP = (p->Cout + 3) & ~3; g.KH = p->KH; g.KW = p->KW; g.stride = p->stride;
-  g.pad_h = p->pad_h; g.pad_w = p->pad_w; g.dil = p->dil; g.Ho = p->Ho; g.Wo = p->Wo; g.relu = p->relu;
+  g.pad_h = p->pad_h; g.pad_w = p->pad_w; g.dil = p->dil; g.Ho = p->Ho; g.Wo = p->Wo; g.relu = p->relu; g.relu_cend = p->relu_channels > 0 ? p->relu_channels : p->Cout;
   g.K = p->KH * p->KW * p->Cin; g.M = p->N * p->Ho * p->Wo;
   g.res_dtype = p->res_dtype; g.res_cstride = p->res_cstride; g.res_coffset = p->res_coffset;
   SegTable segs; segs.nseg = p->nseg;

@@ -13,6 +13,9 @@
 //              channel tails, written straight into the 128B-swizzled K-major layout of the UMMA
 //              descriptor.  M is the flattened (n, oy, ox) pixel index of the whole batch: no tile waste
 //              on the small pyramid levels, any stride / dilation / kernel shape.
+//              Mode STEM (Cin = 3 first layer): the same warps read the raw fp32 NCHW image, build each pixel's
+//              27-value 3x3x3 patch in registers and st.shared it as one 64-channel K-step row, so conv1_1
+//              runs on the tensor cores without an im2col tensor in HBM.
 //   warp 4     TMA producer: the BN x 64 weight tile of each K-step (cp.async.bulk.tensor.2d), and in
 //              mode TMA also the activation tile: the output tile is a TW x TH pixel patch of one image
 //              and the A tile of tap (ky, kx) is the 4-D box {64 ch, TW, TH, 1} at
@@ -36,14 +39,14 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_THREADS = 320;
 constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;     // 16 KB
-constexpr int A_GATHER = 0, A_TMA = 1;
+constexpr int A_GATHER = 0, A_TMA = 1, A_STEM = 2;
 
 struct TcParams {
   const void* in;
   const float* bias;
   const void* residual;
   int N, H, W, Cin, in_cstride, in_coffset;
-  int Cout, KH, KW, stride, pad_h, pad_w, dil, Ho, Wo, relu;
+  int Cout, KH, KW, stride, pad_h, pad_w, dil, Ho, Wo, relu, relu_cend;
   int M, cin_blocks, nk;
   int bn, n_tiles_n, num_tiles;
   int a_mode, TW, TH, tiles_x, tiles_y;       // TMA mode: output patch TW x TH, tiles per image
@@ -168,57 +171,104 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       __syncwarp();
       if (lane == 0)
         for (uint32_t q = (g > (uint32_t)LOOKAHEAD ? g - LOOKAHEAD : 0u); q < g; ++q) mbar_arrive(full0 + 8 * (q % S));
+    } else if (p.a_mode == A_STEM) {
+      // one output pixel per thread: 27 coalesced fp32 loads of the 3x3x3 neighbourhood -> one 128-byte K-step row
+      const int r = threadIdx.x;                 // 0..127
+      const int HW = p.H * p.W;
+      const float* img = reinterpret_cast<const float*>(p.in);
+      const bool bf16 = p.is_bf16 != 0;
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++g) {
+        const int m = (tile / p.n_tiles_n) * TC_BM + r;
+        float v[28];
+#pragma unroll
+        for (int e = 0; e < 28; ++e) v[e] = 0.f;
+        if (m < p.M) {
+          const int n = m / HW, rem = m - n * HW;
+          const int y = rem / p.W, x = rem - y * p.W;
+          const float* base = img + (long long)n * 3 * HW;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int iy = y + ky - 1, ix = x + kx - 1;
+              if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = __ldg(base + (long long)c * HW + iy * p.W + ix);
+              }
+            }
+        }
+        const uint32_t s = g % S;
+        mbar_wait(empty0 + 8 * s, ((g / S) & 1) ^ 1);
+        const uint32_t row = sA + s * TC_A_STAGE + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+          if (ch < 4) {
+            w0 = pack2(v[ch * 8 + 0], v[ch * 8 + 1], bf16); w1 = pack2(v[ch * 8 + 2], v[ch * 8 + 3], bf16);
+            if (ch < 3) { w2 = pack2(v[ch * 8 + 4], v[ch * 8 + 5], bf16); w3 = pack2(v[ch * 8 + 6], v[ch * 8 + 7], bf16); }
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((ch ^ (r & 7)) << 4)), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full0 + 8 * s);
+      }
     }
   } else if (warp == 4) {
     // ================= TMA producer (weights; activations too in mode TMA) =================
-    if (lane == 0) {
-      uint32_t g = 0;
-      const uint32_t tx_bytes = (uint32_t)B_STAGE + (p.a_mode == A_TMA ? (uint32_t)TC_A_STAGE : 0u);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles_n, n0 = (tile - mt * p.n_tiles_n) * BN;
-        int n_img = 0, x0 = 0, y0 = 0;
-        if (p.a_mode == A_TMA) {
-          const int per_img = p.tiles_x * p.tiles_y;
-          n_img = mt / per_img;
-          const int t = mt - n_img * per_img;
-          y0 = (t / p.tiles_x) * p.TH - p.pad_h;
-          x0 = (t % p.tiles_x) * p.TW - p.pad_w;
-        }
-        int cc = 0, ky = 0, kx = 0;
-        for (int it = 0; it < nk; ++it, ++g) {
-          const uint32_t s = g % S;
-          mbar_wait(empty0 + 8 * s, ((g / S) & 1) ^ 1);
+    uint32_t g = 0;
+    const uint32_t tx_bytes = (uint32_t)B_STAGE + (p.a_mode == A_TMA ? (uint32_t)TC_A_STAGE : 0u);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles_n, n0 = (tile - mt * p.n_tiles_n) * BN;
+      int n_img = 0, x0 = 0, y0 = 0;
+      if (p.a_mode == A_TMA) {
+        const int per_img = p.tiles_x * p.tiles_y;
+        n_img = mt / per_img;
+        const int t = mt - n_img * per_img;
+        y0 = (t / p.tiles_x) * p.TH - p.pad_h;
+        x0 = (t % p.tiles_x) * p.TW - p.pad_w;
+      }
+      int cc = 0, ky = 0, kx = 0;
+      for (int it = 0; it < nk; ++it, ++g) {
+        const uint32_t s = g % S;
+        mbar_wait(empty0 + 8 * s, ((g / S) & 1) ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(full0 + 8 * s, tx_bytes);
           tma_load_2d(sB + s * B_STAGE, &tmap_w, it * TC_BK, n0, full0 + 8 * s);
           if (p.a_mode == A_TMA)
             tma_load_4d(sA + s * TC_A_STAGE, &tmap_a, p.in_coffset + cc * TC_BK, x0 + kx * p.dil, y0 + ky * p.dil, n_img,
                         full0 + 8 * s);
-          if (++cc == p.cin_blocks) { cc = 0; if (++kx == p.KW) { kx = 0; ++ky; } }
         }
+        __syncwarp();
+        if (++cc == p.cin_blocks) { cc = 0; if (++kx == p.KW) { kx = 0; ++ky; } }
       }
     }
   } else if (warp == 5) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(p.is_bf16 != 0, TC_BM, BN);
-      uint32_t g = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
-        const uint32_t buf = lt & 1;
-        mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+    // whole warp converged; one elected lane issues (see elect_one)
+    const uint32_t idesc = make_idesc_f16(p.is_bf16 != 0, TC_BM, BN);
+    const uint64_t adesc0 = make_sw128_desc(sA), bdesc0 = make_sw128_desc(sB);
+    uint32_t g = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1;
+      mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * 256;
+      for (int it = 0; it < nk; ++it, ++g) {
+        const uint32_t s = g % S;
+        mbar_wait(full0 + 8 * s, (g / S) & 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * 256;
-        for (int it = 0; it < nk; ++it, ++g) {
-          const uint32_t s = g % S;
-          mbar_wait(full0 + 8 * s, (g / S) & 1);
-          tc_fence_after();
-          const uint32_t a = sA + s * TC_A_STAGE, b = sB + s * B_STAGE;
+        if (elect_one()) {
+          const uint64_t ad = adesc0 + (uint64_t)((s * TC_A_STAGE) >> 4), bd = bdesc0 + (uint64_t)((s * B_STAGE) >> 4);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            umma_f16(tmem_d, make_sw128_desc(a + k * 32), make_sw128_desc(b + k * 32), idesc, (it | k) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k) umma_f16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (it | k) ? 1u : 0u);
           umma_commit(empty0 + 8 * s);
         }
-        umma_commit(accf0 + 8 * buf);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(accf0 + 8 * buf);
+      __syncwarp();
     }
   } else {
     // ================= epilogue =================
@@ -263,7 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 const float2 r0 = unpack2(rv.x, bf16), r1 = unpack2(rv.y, bf16), r2 = unpack2(rv.z, bf16), r3 = unpack2(rv.w, bf16);
                 f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y; f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
               }
-              if (p.relu) {
+              if (p.relu && c < p.relu_cend) {           // relu_cend is a multiple of 8 on this path
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
               }
@@ -281,7 +331,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
               const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
               float4 f = make_float4(__uint_as_float(v[gq * 4 + 0]) + b0.x, __uint_as_float(v[gq * 4 + 1]) + b0.y,
                                      __uint_as_float(v[gq * 4 + 2]) + b0.z, __uint_as_float(v[gq * 4 + 3]) + b0.w);
-              if (p.relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+              if (p.relu && c < p.relu_cend) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
               int sgi = 0;
               if (p.segs.nseg > 1 && c >= p.segs.seg[1].c_begin) sgi = 1;
               if (p.segs.nseg > 2 && c >= p.segs.seg[2].c_begin) sgi = 2;
@@ -298,7 +348,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             if (c < p.Cout && j < lim) {
               float f = __uint_as_float(v[j]) + s_bias[c];
               if (p.residual) f += load_as(p.residual, m_lin * p.res_cstride + p.res_coffset + c, p.res_dtype);
-              if (p.relu) f = fmaxf(f, 0.f);
+              if (p.relu && c < p.relu_cend) f = fmaxf(f, 0.f);
 #pragma unroll
               for (int sgi = 0; sgi < 3; ++sgi) {
                 if (sgi < p.segs.nseg && c >= p.segs.seg[sgi].c_begin && c < p.segs.seg[sgi].c_end) {
@@ -348,6 +398,10 @@ static int num_sms() {
 
 static int tc_supported(const CtxConvParams* p) {
   if (!p) return 0;
+  if (p->in_nchw)       // stem mode: raw fp32 NCHW input, 3x3 / s1 / p1, 16-bit output
+    return p->in_dtype == CTX_F32 && p->Cin == 3 && p->KH == 3 && p->KW == 3 && p->stride == 1 && p->pad_h == 1 && p->pad_w == 1 &&
+           p->dil == 1 && p->nseg >= 1 && (p->seg[0].dtype == CTX_BF16 || p->seg[0].dtype == CTX_F16) &&
+           ((uintptr_t)p->weight) % 16 == 0;
   if (p->in_dtype != CTX_BF16 && p->in_dtype != CTX_F16) return 0;
   if (p->Cin % 8 || p->in_cstride % 8 || p->in_coffset % 8) return 0;
   if (p->KH * p->KW > 32) return 0;
@@ -400,21 +454,23 @@ extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out
   t.N = p->N; t.H = p->H; t.W = p->W; t.Cin = p->Cin; t.in_cstride = p->in_cstride; t.in_coffset = p->in_coffset;
   t.Cout = p->Cout; t.KH = p->KH; t.KW = p->KW; t.stride = p->stride; t.pad_h = p->pad_h; t.pad_w = p->pad_w; t.dil = p->dil;
   t.Ho = p->Ho; t.Wo = p->Wo; t.relu = p->relu;
+  t.relu_cend = p->relu_channels > 0 ? p->relu_channels : p->Cout;
   t.M = p->N * p->Ho * p->Wo;
   t.cin_blocks = (p->Cin + TC_BK - 1) / TC_BK;
-  t.nk = p->KH * p->KW * t.cin_blocks;
+  t.nk = p->in_nchw ? 1 : p->KH * p->KW * t.cin_blocks;       // stem: all 27 taps*channels in one 64-wide K-step
   t.res_cstride = p->res_cstride; t.res_coffset = p->res_coffset; t.res_dtype = p->res_dtype;
-  t.is_bf16 = p->in_dtype == CTX_BF16;
+  const int op_dtype = p->in_nchw ? p->seg[0].dtype : p->in_dtype;     // operand (and 16-bit output) type
+  t.is_bf16 = op_dtype == CTX_BF16;
   t.segs.nseg = p->nseg;
   for (int s = 0; s < 3; ++s) t.segs.seg[s] = p->seg[s < p->nseg ? s : 0];
   const CtxOutSeg& s0 = p->seg[0];
-  t.fast_out = p->nseg == 1 && s0.dtype == p->in_dtype && s0.c_begin == 0 && s0.c_end == p->Cout && p->Cout % 8 == 0 &&
+  t.fast_out = t.relu_cend % 8 == 0 && p->nseg == 1 && s0.dtype == op_dtype && s0.c_begin == 0 && s0.c_end == p->Cout && p->Cout % 8 == 0 &&
                s0.pix_stride % 8 == 0 && s0.ch_offset % 8 == 0 && s0.img_stride % 8 == 0 && ((uintptr_t)s0.ptr) % 16 == 0 &&
                ((uintptr_t)p->bias) % 16 == 0 &&
-               (!p->residual || (p->res_dtype == p->in_dtype && p->res_cstride % 8 == 0 && p->res_coffset % 8 == 0 &&
+               (!p->residual || (p->res_dtype == op_dtype && p->res_cstride % 8 == 0 && p->res_coffset % 8 == 0 &&
                                  ((uintptr_t)p->residual) % 16 == 0));
   t.vec_f32 = 0;
-  if (!t.fast_out && !p->residual && p->Cout % 4 == 0 && ((uintptr_t)p->bias) % 16 == 0) {
+  if (!t.fast_out && !p->residual && t.relu_cend % 4 == 0 && p->Cout % 4 == 0 && ((uintptr_t)p->bias) % 16 == 0) {
     bool ok = true;
     int expect = 0;
     for (int s = 0; s < p->nseg; ++s) {
@@ -434,7 +490,7 @@ extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out
   pl->smem = (size_t)pl->stages * stage_bytes + 16 * pl->stages + 64 + 4 * (((size_t)p->Cout + 31) / 32 * 32 + 32) + 1024;
 
   int tw = 0, th = 0;
-  t.a_mode = choose_patch(p, &tw, &th) ? A_TMA : A_GATHER;
+  t.a_mode = p->in_nchw ? A_STEM : (choose_patch(p, &tw, &th) ? A_TMA : A_GATHER);
   t.TW = tw; t.TH = th;
   t.tiles_x = t.a_mode == A_TMA ? cdiv(p->Wo, tw) : 0;
   t.tiles_y = t.a_mode == A_TMA ? cdiv(p->Ho, th) : 0;
@@ -443,7 +499,7 @@ extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out
   pl->grid = std::min(t.num_tiles, num_sms());
 
   // weights: [Cout_pad][KH*KW*Cin_pad] 16-bit, K-major; box = 64 (K) x BN (Cout), SWIZZLE_128B, OOB rows read as zero
-  const unsigned long long ktot = (unsigned long long)p->KH * p->KW * t.cin_blocks * TC_BK;
+  const unsigned long long ktot = (unsigned long long)t.nk * TC_BK;
   const unsigned long long cout_pad = (unsigned long long)((p->Cout + 15) / 16 * 16);
   int rc = encode_2d_sw128(&pl->tmap_w, p->weight, t.is_bf16 != 0, cout_pad, ktot, (unsigned)t.bn);
   if (!rc && t.a_mode == A_TMA)

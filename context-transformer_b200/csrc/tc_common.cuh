@@ -87,6 +87,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One lane of a fully converged warp (deterministic leader).  The tcgen05 / TMA issue loops run with the whole warp
+// converged and only the issuing instructions predicated on this, so the uniform-datapath instructions
+// (UTCHMMA, UTCBAR, UTMALDG) need no divergence handling.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // K-major, SWIZZLE_128B shared-memory operand descriptor (rows of 128 B, 8-row groups 1024 B apart).
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |

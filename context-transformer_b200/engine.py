@@ -126,7 +126,8 @@ class Engine(object):
             w, b = w * scale, b * scale
         return w, b
 
-    def _emit_conv(self, name, src, w, b, stride, pad, dil, relu, segs=None, out=None, residual=None):
+    def _emit_conv(self, name, src, w, b, stride, pad, dil, relu, segs=None, out=None, residual=None, relu_channels=0,
+                   algo_flops=None, in_nchw=False):
         """w: folded fp32 [Cout,Cin,KH,KW]; b: fp32 [Cout].  segs: list of (tensor, c_begin, c_end, img_stride,
         pix_stride, ch_offset) for multi-destination epilogues; otherwise writes ``out`` (a View) or a new one."""
         Cout, Cin, KH, KW = w.shape
@@ -138,8 +139,9 @@ class Engine(object):
         p.N, p.H, p.W, p.Cin = src.N, src.H, src.W, Cin
         p.in_cstride, p.in_coffset = src.cstride, src.coff
         p.Cout, p.KH, p.KW, p.stride, p.pad_h, p.pad_w, p.dil = Cout, KH, KW, stride, ph, pw, dil
-        p.Ho, p.Wo, p.relu = Ho, Wo, int(relu)
+        p.Ho, p.Wo, p.relu, p.relu_channels = Ho, Wo, int(relu), int(relu_channels)
         p.in_dtype = _lib.dtype_code(src.buf.dtype)
+        p.in_nchw = int(in_nchw)
         setattr(p, 'in', src.buf.data_ptr())
         bias = b.contiguous()
         self.keep.append(bias)
@@ -162,13 +164,19 @@ class Engine(object):
             p.seg[i].c_begin, p.seg[i].c_end = c0, c1
             p.seg[i].img_stride, p.seg[i].pix_stride, p.seg[i].ch_offset = img_stride, pix_stride, ch_off
             p.seg[i].dtype = _lib.dtype_code(t.dtype)
-        flops = 2.0 * src.N * Ho * Wo * Cout * Cin * KH * KW
+        flops = algo_flops if algo_flops is not None else 2.0 * src.N * Ho * Wo * Cout * Cin * KH * KW
         use_tc = self.precision != 'fp32' and self.L.ctx_conv2d_tc_supported(C.byref(p)) == 1
+        if in_nchw and not use_tc:
+            raise _lib.CtxError('stem conv: tensor-core STEM mode unavailable for this geometry')
         if use_tc:
             cin_p = (Cin + 63) // 64 * 64
             cout_p = (Cout + 15) // 16 * 16
-            wt = torch.zeros(cout_p, KH * KW, cin_p, dtype=self.act_dtype, device=self.dev)
-            wt[:Cout, :, :Cin] = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin).to(self.act_dtype)
+            if in_nchw:                 # stem: one 64-wide K-step, k = (ky*3 + kx)*3 + ci
+                wt = torch.zeros(cout_p, 64, dtype=self.act_dtype, device=self.dev)
+                wt[:Cout, :27] = w.permute(0, 2, 3, 1).reshape(Cout, 27).to(self.act_dtype)
+            else:
+                wt = torch.zeros(cout_p, KH * KW, cin_p, dtype=self.act_dtype, device=self.dev)
+                wt[:Cout, :, :Cin] = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin).to(self.act_dtype)
             self.keep.append(wt)
             p.weight = wt.data_ptr()
             _lib.check(self.L.ctx_prog_add_conv_tc(self.prog, C.byref(p)), 'ctx_prog_add_conv_tc(%s)' % name)
@@ -215,15 +223,43 @@ class Engine(object):
         Wo = (src.W - 1) // stride + 1
         cat_c = sum(br[-1].out_channels for br in branches)
         cat = self._new_view(src.N, Ho, Wo, cat_c)
+
+        # 1x1 convs that read the block input (branch entries + shortcut) are evaluated as ONE conv per
+        # stride: output channels = [entries (ReLU) ..., shortcut (no ReLU)], later layers read channel slices.
+        def is_pointwise(bc):
+            c = bc.conv
+            return c.kernel_size == (1, 1) and c.padding == (0, 0) and c.dilation == (1, 1)
+        members = {}                                            # stride -> [(key, BasicConv)]
+        for bi, br in enumerate(branches):
+            if len(br) > 1 and is_pointwise(br[0]) and br[0].relu is not None:
+                members.setdefault(br[0].conv.stride[0], []).append((bi, br[0]))
+        if is_pointwise(m.shortcut) and m.shortcut.relu is None:
+            members.setdefault(stride, []).append(('shortcut', m.shortcut))
+        entry_out = {}
+        for st, group in sorted(members.items()):
+            if len(group) < 2 or any(bc.out_channels % 64 for _, bc in group):
+                continue
+            ws, bs = zip(*[self._fold(bc.conv, bc.bn) for _, bc in group])
+            relu_c = sum(bc.out_channels for key, bc in group if key != 'shortcut')
+            fused = self._emit_conv('%s.entry_s%d[%s]' % (name, st, '+'.join(str(k) for k, _ in group)), src,
+                                    torch.cat(ws, 0), torch.cat(bs, 0), st, (0, 0), 1, relu_c > 0, relu_channels=relu_c)
+            off = 0
+            for key, bc in group:
+                entry_out[key] = fused.slice(off, bc.out_channels)
+                off += bc.out_channels
+
         off = 0
         for bi, br in enumerate(branches):
             t = src
             for li, layer in enumerate(br):
                 last = li == len(br) - 1
+                if li == 0 and bi in entry_out:
+                    t = entry_out[bi]
+                    continue
                 t = self._basic_conv('%s.branch%d.%d' % (name, bi, li), layer, t,
                                      out=cat.slice(off, layer.out_channels) if last else None)
             off += br[-1].out_channels
-        short = self._basic_conv(name + '.shortcut', m.shortcut, src)
+        short = entry_out['shortcut'] if 'shortcut' in entry_out else self._basic_conv(name + '.shortcut', m.shortcut, src)
         # relu(ConvLinear(cat) * scale + short): scale folds into the weights, the add + ReLU into the epilogue
         return self._basic_conv(name + '.ConvLinear', m.ConvLinear, cat, residual=short, relu=True, scale=float(m.scale))
 
@@ -236,12 +272,9 @@ class Engine(object):
                         and stem.kernel_size == (3, 3) and stem.stride == (1, 1) and stem.padding == (1, 1)
                         and stem.dilation == (1, 1))
         if stem_as_gemm:
-            # Cin = 3 cannot feed the tensor cores: lay the input out as 3x3 patches (K = 27 -> 32) and run
-            # the stem conv as a 1x1 conv over them
-            x = self._new_view(B, S, S, 32)
-            _lib.check(self.L.ctx_prog_add_nchw_to_patch27(self.prog, self.x_in.data_ptr(), x.buf.data_ptr(), B, S, S,
-                                                           self.act_code), 'ctx_prog_add_nchw_to_patch27')
-            self.layers.append(('input.patch27', 'layout', 0.0, (B, 3, S, S)))
+            # Cin = 3 cannot feed the tensor cores channel-wise: the conv kernel's STEM mode reads the raw NCHW
+            # fp32 input and builds each pixel's 3x3x3 patch (K = 27 -> one 64-wide K-step) on the fly
+            x = View(self.x_in.view(-1), B, S, S, 3)
         else:
             x = self._new_view(B, S, S, 3)
             _lib.check(self.L.ctx_prog_add_nchw_to_nhwc(self.prog, self.x_in.data_ptr(), x.buf.data_ptr(), B, 3, S, S,
@@ -257,9 +290,7 @@ class Engine(object):
                     relu = k + 1 < len(net.base) and isinstance(net.base[k + 1], nn.ReLU)
                     w, b = self._fold(m, None)
                     if k == 0 and stem_as_gemm:
-                        wp = torch.zeros(w.size(0), 32, 1, 1, device=self.dev)
-                        wp[:, :27, 0, 0] = w.permute(0, 2, 3, 1).reshape(w.size(0), 27)    # (ky, kx, ci) order of patch27
-                        x = self._emit_conv('base.0', x, wp, b, 1, (0, 0), 1, relu)
+                        x = self._emit_conv('base.0', x, w, b, 1, (1, 1), 1, relu, in_nchw=True)
                         k += 2 if relu else 1
                         continue
                     x = self._emit_conv('base.%d' % k, x, w, b, m.stride[0], _pair(m.padding), m.dilation[0], relu)

@@ -96,7 +96,10 @@ typedef struct CtxConvParams {
   int Cout, KH, KW, stride, pad_h, pad_w, dil;
   int Ho, Wo;
   int relu;
+  int relu_channels;         /* with relu != 0: ReLU only on output channels < relu_channels (0 = all) — fused entry convs */
   int in_dtype;
+  int in_nchw;               /* 1: `in` is the raw fp32 NCHW network input [N,3,H,W] (RFBNet.forward x, :210) and this is the
+                              * 3x3 / stride 1 / pad 1 stem conv: the tensor-core kernel builds the 27-value patches itself   */
   const void* in;
   const void* weight;        /* SIMT path: fp32 [KH*KW*Cin][Cout]; TC path: 16-bit [Cout_pad][KH*KW][Cin_pad] */
   const float* bias;         /* [Cout] (BatchNorm folded in) or NULL */
@@ -122,8 +125,8 @@ void ctx_conv2d_tc_plan_destroy(void* plan);
 int ctx_maxpool2d_nhwc(const CtxPoolParams* p, void* stream);
 /* x[N,3,H,W] fp32 NCHW (RFBNet.forward input, :210) -> NHWC of dtype */
 int ctx_nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, int out_dtype, void* stream);
-/* x[N,3,H,W] fp32 -> 3x3/pad-1 patches [N,H,W,32] 16-bit (27 values, channel = (ky*3+kx)*3+ci, + 5 zeros): turns the
- * Cin = 3 stem conv (vgg() base.0, RFB_Net_vgg.py:331) into a K = 32 tensor-core GEMM */
+/* x[N,3,H,W] fp32 -> 3x3/pad-1 patches [N,H,W,64] 16-bit (27 values, channel = (ky*3+kx)*3+ci, + 37 zeros): turns the
+ * Cin = 3 stem conv (vgg() base.0, RFB_Net_vgg.py:331) into a K = 64 tensor-core GEMM */
 int ctx_nchw_to_patch27(const float* in, void* out, int N, int H, int W, int out_dtype, void* stream);
 
 /* ---- Context-Transformer : models/RFB_Net_vgg.py:253-271 (+ :273-285 output activation) ------ */
