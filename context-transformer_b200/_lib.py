@@ -86,6 +86,7 @@ SIGNATURES = {
     'ctx_prog_add_nchw_to_patch27': (_I, [_P, _P, _P, _I, _I, _I, _I]),
     'ctx_attention_workspace_bytes': (_SZ, [C.POINTER(CtxAttnParams)]),
     'ctx_attention_forward': (_I, [C.POINTER(CtxAttnParams), _P]),
+    'ctx_debug_set_attention_timeline': (None, [_P]),
     'ctx_softmax_lastdim': (_I, [_P, _P, _LL, _I, _P]),
     'ctx_prog_create': (_I, [C.POINTER(_P)]),
     'ctx_prog_add_conv_simt': (_I, [_P, C.POINTER(CtxConvParams)]),

@@ -222,6 +222,10 @@ int attention_simt_launch(const CtxAttnParams* p, cudaStream_t st) {
 
 }  // namespace ctx
 
+namespace ctx { void attention_set_debug_buffer(void* p); }
+/* development aid: device buffer of >= 512 int64 that receives clock64() stamps of CTA (0,0) of the tensor-core kernel */
+extern "C" void ctx_debug_set_attention_timeline(void* device_buffer) { ctx::attention_set_debug_buffer(device_buffer); }
+
 extern "C" size_t ctx_attention_workspace_bytes(const CtxAttnParams* p) {
   if (!p || p->batch <= 0 || p->num_priors <= 0 || p->num_pooled <= 0 || p->dim <= 0) return 1024;
   if (p->use_tensor_cores) return ctx::attention_tc_workspace_bytes(p->batch, p->num_priors, p->num_pooled);

@@ -1,73 +1,44 @@
 // attention_tc.cu — Context-Transformer block (models/RFB_Net_vgg.py:253-271) on the sm_100a tensor
-// cores: spatially pooled keys/values, softmax(Q K^T) V, residual, L2-norm, cosine classifier and the
-// class softmax as ONE warp-specialised kernel; the [B, P, Pk] affinity matrix never leaves the SM.
+// cores: theta projection, softmax(Q K^T) V over the spatially pooled keys, residual, L2-norm, cosine
+// classifier and the class softmax as ONE warp-specialised kernel; neither Q nor the [B, P, Pk]
+// affinity matrix (86 MB / image upstream) ever exists in HBM.
 //
-//   proj kernels (CUDA cores, fp32): Q = theta(conf)+conf, K = phi(pool)+pool, V = g(pool)+pool, each
-//        written as fp16 operands.  The reference's logits are un-scaled dot products of raw class
-//        scores (|s| up to ~1.5e3), so a plain 16-bit Q K^T is not accurate enough; Q and K are
-//        therefore split into fp16 hi + lo parts and S = Qh Kh^T + Ql Kh^T + Qh Kl^T is accumulated in
-//        fp32 by three tcgen05 MMAs (error ~2^-22 relative; measured final |dconf| 4e-5 vs fp32).
-//   attention kernel: CTA = 128 queries of one image, keys streamed in tiles of 64.
-//        warp 4  TMA producer   : Qh/Ql tile once, then {Kh, Kl, V^T} tiles through a 2-stage ring
-//        warp 5  MMA issuer     : S[j%2] = Q K_j^T (12 UMMAs, M128 N64 K16) into a double-buffered TMEM
-//                                 accumulator, then O += P_j V_j (4 UMMAs) once the softmax warps have
-//                                 published P_j; tcgen05.commit drives every hand-off mbarrier
-//        warps 0-3 softmax      : one query row per thread: tcgen05.ld the S row, streaming softmax with
-//                                 a lazily updated reference maximum (O in TMEM is rescaled only when a
-//                                 row's maximum grows by more than 8), p = ex2(s*log2e - ref), P written
-//                                 as the fp16 A operand of the PV MMA (128B-swizzled K-major tile);
-//                                 finally the epilogue: O/l, z = conf + O*Wz, z/||z||, OBJ_Target * scale
-//                                 [, fc_base(conf)+conf for 'incre'], class softmax, store.
+// Numerics.  The reference's logits are un-scaled dot products of raw class scores (|s| up to ~1.5e3 on
+// the seeded weights), so a plain 16-bit Q K^T is not accurate enough.  Every fp32 operand X is split
+// into fp16 hi + lo parts and X Y^T = Xh Yh^T + Xl Yh^T + Xh Yl^T is accumulated in fp32 by three
+// tcgen05 MMAs (error ~2^-22 relative; measured final |dconf| 4e-5 against the fp32 reference).
+//
+//   proj_kv kernel (CUDA cores, fp32, tiny): K = phi(pool)+pool as fp16 hi/lo, V = g(pool)+pool as fp16 V^T.
+//   attention kernel: CTA = 2 x 128 queries of one image (two "q-tiles" that share the key stream and
+//   interleave on the tensor core), keys streamed in tiles of 128 through a 2/3-stage TMA ring.  320 threads:
+//     warps 0-7  softmax (4 per q-tile, one query row per thread)
+//                prologue: load the conf row, split hi/lo, stage it as an A operand; after the projection
+//                MMA (Q = conf (theta+I)^T, 12 UMMAs) read Q from TMEM, add the bias, split hi/lo and stage
+//                it as the A operand of the logits MMAs.
+//                pass A: row maximum of the hi-only logits Qh Kh^T (4 UMMAs M128 N128 / tile) -> softmax reference.
+//                pass B: exact logits (12 UMMAs / tile), p = ex2(s*log2e - ref) against that FIXED reference
+//                (the O accumulator in TMEM never needs a running-maximum rescale, so PV of tile j overlaps
+//                the exponentials of tile j+1); P is written as the fp16 A operand of the PV MMA.
+//                epilogue: O/l, z = conf + O*Wz, z/||z||, OBJ_Target*scale [, fc_base(conf)+conf], class softmax.
+//     warp 8     TMA producer: theta weights once, then {Kh} (pass A) / {Kh, Kl, V^T} (pass B) tiles.
+//     warp 9     TMEM allocator + MMA issuer (one elected lane); tcgen05.commit drives every hand-off mbarrier.
 #include "tc_common.cuh"
 
 namespace ctx {
 
-constexpr int AT_BQ = 128;        // queries per CTA
-constexpr int AT_BK = 64;         // keys per tile
+constexpr int AT_BQ = 128;        // queries per q-tile
+constexpr int AT_QT = 2;          // q-tiles per CTA
+constexpr int AT_BK = 128;        // keys per tile (UMMA N = 128: half the shared-memory operand traffic per MAC of N = 64)
 constexpr int AT_DP = 64;         // padded feature dim
-constexpr int AT_THREADS = 192;
+constexpr int AT_RING = 96 * 1024; // key/value ring bytes: 2 stages {Kh, Vt, Kl} (split) or 3 stages {Kh, Vt}
+constexpr int AT_THREADS = 320;
 constexpr int AT_TILE_Q = AT_BQ * AT_DP * 2;      // 16 KB
-constexpr int AT_TILE_K = AT_BK * AT_DP * 2;      // 8 KB
+constexpr int AT_TILE_K = AT_BK * AT_DP * 2;      // 16 KB: 128 keys x 64 features
+constexpr int AT_TILE_W = AT_DP * AT_DP * 2;      // 8 KB: 64 x 64 (theta' half, V^T key block)
+constexpr int AT_STAGE_SPLIT = 3 * AT_TILE_K, AT_STAGE_FAST = 2 * AT_TILE_K;   // stage layout: Kh | Vt[2] | Kl
 constexpr float AT_LOG2E = 1.4426950408889634f;
-constexpr float AT_RESCALE = 8.0f;                // lazy-rescale threshold (natural-log units)
 
-// ---- projections (fp32 CUDA cores) -> fp16 hi/lo operands ------------------------------------------
-// rows: B*P queries.  Qhl: [2][B*P][64] fp16 (hi, lo), feature columns D..63 zero.
-template <int D>
-__global__ void __launch_bounds__(128)
-proj_q_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, long long rows,
-              __half* __restrict__ qhl) {
-  __shared__ float s_w[D * D], s_b[D];
-  for (int i = threadIdx.x; i < D * D; i += blockDim.x) s_w[i] = w[i];
-  for (int i = threadIdx.x; i < D; i += blockDim.x) s_b[i] = bias[i];
-  __syncthreads();
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  float xv[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) xv[d] = x[r * D + d];
-  __half* hi = qhl + r * AT_DP;
-  __half* lo = qhl + (rows + r) * AT_DP;
-  for (int o0 = 0; o0 < AT_DP; o0 += 8) {
-    __align__(16) __half h[8], l[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int o = o0 + e;
-      float q = 0.f;
-      if (o < D) {
-        float a = 0.f;
-#pragma unroll
-        for (int d = 0; d < D; ++d) a = fmaf(s_w[o * D + d], xv[d], a);
-        q = (a + s_b[o]) + xv[o];
-      }
-      h[e] = __float2half_rn(q);
-      l[e] = __float2half_rn(q - __half2float(h[e]));
-    }
-    *reinterpret_cast<uint4*>(hi + o0) = *reinterpret_cast<uint4*>(h);
-    *reinterpret_cast<uint4*>(lo + o0) = *reinterpret_cast<uint4*>(l);
-  }
-}
-
+// ---- K / V projection (fp32 CUDA cores) -> fp16 operands --------------------------------------------
 // rows: B*Pk_pad keys (rows >= Pk of an image are zero).  Khl: [2][B*Pk_pad][64]; Vt: [B][64][Pk_pad].
 template <int D>
 __global__ void __launch_bounds__(128)
@@ -110,222 +81,388 @@ proj_kv_kernel(const float* __restrict__ pooled, const float* __restrict__ phi_w
   }
 }
 
+// theta' = theta + I (the "+conf" residual of Q = theta(conf) + conf), padded to 64 x 64, as fp16 hi/lo: wq[2][64][64]
+__global__ void prep_wq_kernel(const float* __restrict__ theta_w, int D, __half* __restrict__ wq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= AT_DP * AT_DP) return;
+  const int o = i / AT_DP, d = i - o * AT_DP;
+  float w = 0.f;
+  if (o < D && d < D) w = theta_w[o * D + d] + (o == d ? 1.f : 0.f);
+  const __half h = __float2half_rn(w);
+  wq[i] = h;
+  wq[AT_DP * AT_DP + i] = __float2half_rn(w - __half2float(h));
+}
+
 // ---- fused attention --------------------------------------------------------------------------------
 struct AttnTcParams {
   int B, P, Pk, Pk_pad, ntiles;
   int num_novel, incre, apply_softmax;
-  long long q_rows, k_rows;         // B*P, B*Pk_pad (row offset of the "lo" halves)
-  const float* conf;                // [B,P,D] fp32 (residual input x)
-  const float *Wz, *obj_w, *fc_w, *fc_b;
+  int bulk_x;                       // conf blocks are 16-byte aligned / sized: staged with 1-D bulk copies
+  int split;                        // 1: logits = Qh Kh^T + Ql Kh^T + Qh Kl^T (fp32-grade); 0: Qh Kh^T only (fp16-grade, 3x fewer MMAs)
+  long long k_rows;                 // B*Pk_pad (row offset of the "lo" half of K)
+  const float* conf;                // [B,P,D] fp32: projection input and residual x
+  const float *theta_b, *Wz, *obj_w, *fc_w, *fc_b;
   float scale;
   float* out;
+  long long* dbg;                   // optional timeline buffer (ctx_debug_set_buffer), CTA (0,0) only
 };
 
+#define AT_DBG(slot) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[(slot)] = clock64(); } while (0)
+
+// one row (64 fp32 values) -> fp16 hi and lo rows of two 128B-swizzled K-major operand tiles
+__device__ __forceinline__ void store_split_row(uint32_t tile_hi, uint32_t tile_lo, int r, const float (&x)[64]) {
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = x[ch * 8 + 2 * e], b = x[ch * 8 + 2 * e + 1];
+      const __half2 hh = __floats2half2_rn(a, b);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+      h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    const uint32_t off = r * 128 + ((ch ^ (r & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+  }
+}
+
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+  tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+  tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+  tmem_ld_wait();
+}
+
 template <int D>
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQh = base, sQl = base + AT_TILE_Q;
-  const uint32_t sKV = base + 2 * AT_TILE_Q;                 // 2 stages x {Kh, Kl, Vt} = 2 x 24 KB
-  const uint32_t sP = sKV + 2 * 3 * AT_TILE_K;               // 128 x 64 fp16 = 16 KB
-  const uint32_t bars = sP + AT_TILE_Q;
-  const uint32_t q_full = bars, kv_full = bars + 8, kv_empty = bars + 24, s_full = bars + 40, s_empty = bars + 56,
-                 p_full = bars + 72, pv_done = bars + 80, tmem_slot = bars + 88;
-  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-  float* s_obj = reinterpret_cast<float*>(gen_base + (bars - base) + 128);     // epilogue weights: obj [n_novel][D], fc [D][D]+[D]
+  // [QhA QlA QhB QlB] 64 KB (epilogue: classifier weights per q-tile)
+  // [P_A P_B] 2 x 32 KB, each two 128x64 K-blocks (prologue: conf hi / lo tiles of the projection)
+  // ring 96 KB: 2 x {Kh 16, Vt 2 x 8, Kl 16} or 3 x {Kh, Vt} (prologue: the last stage holds theta' hi/lo)
+  const uint32_t sQ = base, sP = sQ + 4 * AT_TILE_Q, sKV = sP + 4 * AT_TILE_Q;
+  const uint32_t bars = sKV + AT_RING;
+  const int NST = p.split ? 2 : 3;                       // ring depth
+  const uint32_t STAGE = p.split ? AT_STAGE_SPLIT : AT_STAGE_FAST;
+  const uint32_t w_full = bars, x_full = bars + 8, xq_done = bars + 24, q_ready = bars + 40, kv_full = bars + 56,
+                 kv_empty = kv_full + 8 * 3, s_full = kv_empty + 8 * 3, s_empty = s_full + 16,
+                 p_full = s_empty + 16, pv_done = p_full + 16, tmem_slot = pv_done + 16, xin_full = tmem_slot + 8;
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256 - smem_u32(smem_raw)));   // [64] theta bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y, q0 = blockIdx.x * AT_BQ;
+  const int b = blockIdx.y, q0 = blockIdx.x * (AT_QT * AT_BQ);
   const int T = p.ntiles;
 
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); }
-  if (warp == 5) {
+  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); }
+  if (warp == 9) {
     if (lane == 0) {
-      mbar_init(q_full, 1);
-      for (int s = 0; s < 2; ++s) {
-        mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1);
-        mbar_init(s_full + 8 * s, 1); mbar_init(s_empty + 8 * s, 4);
+      mbar_init(w_full, 1);
+      for (int t = 0; t < AT_QT; ++t) {
+        mbar_init(x_full + 8 * t, 4); mbar_init(xq_done + 8 * t, 1); mbar_init(q_ready + 8 * t, 4);
+        mbar_init(p_full + 8 * t, 4); mbar_init(pv_done + 8 * t, 1);
+        mbar_init(s_full + 8 * t, 1); mbar_init(s_empty + 8 * t, 4); mbar_init(xin_full + 8 * t, 1);
       }
-      mbar_init(p_full, 4);
-      mbar_init(pv_done, 1);
+      for (int s = 0; s < 3; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  // epilogue weights (read long after this barrier)
-  for (int i = threadIdx.x; i < p.num_novel * D; i += blockDim.x) s_obj[i] = p.obj_w[i];
-  if (p.incre) {
-    float* s_fc = s_obj + p.num_novel * D;
-    for (int i = threadIdx.x; i < D * D; i += blockDim.x) s_fc[i] = p.fc_w[i];
-    for (int i = threadIdx.x; i < D; i += blockDim.x) s_fc[D * D + i] = p.fc_b[i];
-  }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_bias[i] = i < D ? p.theta_b[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
-  const uint32_t tS = tmem, tO = tmem + 128;              // S0: cols 0-63, S1: 64-127, O: 128-191
+  // TMEM columns: S of q-tile t at 128 t (128 keys) ; O of q-tile t at 256 + 64 t
+  const uint32_t tO = tmem + 256;
 
-  if (warp == 4) {
-    // ================= TMA producer ================= (whole warp converged, one elected lane issues)
+  if (warp == 8) {
+    // ================= TMA producer =================
+    const uint32_t wstage = sKV + (NST - 1) * STAGE;        // theta' lives in the last ring stage during the projection
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, 2 * AT_TILE_Q);
-      tma_load_2d(sQh, &tm_q, 0, b * p.P + q0, q_full);
-      tma_load_2d(sQl, &tm_q, 0, (int)p.q_rows + b * p.P + q0, q_full);
+      for (int t = 0; t < AT_QT; ++t) {                     // conf rows of q-tile t: one contiguous block -> the Q_t region
+        const int rows = min(AT_BQ, p.P - (q0 + t * AT_BQ));
+        const uint32_t bytes = rows > 0 ? (uint32_t)rows * D * 4u : 0u;
+        mbar_arrive_expect_tx(xin_full + 8 * t, p.bulk_x ? bytes : 0u);
+        if (p.bulk_x && bytes) bulk_load(sQ + 2 * t * AT_TILE_Q, p.conf + ((size_t)b * p.P + q0 + t * AT_BQ) * D, bytes, xin_full + 8 * t);
+      }
+      mbar_arrive_expect_tx(w_full, 2 * AT_TILE_W);
+      tma_load_2d(wstage, &tm_w, 0, 0, w_full);                   // theta' hi
+      tma_load_2d(wstage + AT_TILE_W, &tm_w, 0, AT_DP, w_full);   // theta' lo
     }
     __syncwarp();
-    for (int j = 0; j < T; ++j) {
-      const int s = j & 1;
-      mbar_wait(kv_empty + 8 * s, ((j >> 1) & 1) ^ 1);
+    for (int u = 0; u < 2 * T; ++u) {
+      const int s = u % NST, j = u < T ? u : u - T;
+      if (u == NST - 1) { mbar_wait(xq_done, 0); mbar_wait(xq_done + 8, 0); }
+      mbar_wait(kv_empty + 8 * s, ((u / NST) & 1) ^ 1);
       if (elect_one()) {
-        const uint32_t dst = sKV + s * 3 * AT_TILE_K;
-        mbar_arrive_expect_tx(kv_full + 8 * s, 3 * AT_TILE_K);
+        const uint32_t dst = sKV + s * STAGE;
+        mbar_arrive_expect_tx(kv_full + 8 * s, u < T ? AT_TILE_K : STAGE);
         tma_load_2d(dst, &tm_k, 0, b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
-        tma_load_2d(dst + AT_TILE_K, &tm_k, 0, (int)p.k_rows + b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
-        tma_load_2d(dst + 2 * AT_TILE_K, &tm_v, j * AT_BK, b * AT_DP, kv_full + 8 * s);
+        if (u >= T) {
+          tma_load_2d(dst + AT_TILE_K, &tm_v, j * AT_BK, b * AT_DP, kv_full + 8 * s);
+          tma_load_2d(dst + AT_TILE_K + AT_TILE_W, &tm_v, j * AT_BK + 64, b * AT_DP, kv_full + 8 * s);
+          if (p.split) tma_load_2d(dst + 2 * AT_TILE_K, &tm_k, 0, (int)p.k_rows + b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
+        }
       }
       __syncwarp();
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ================= MMA issuer ================= (whole warp converged, one elected lane issues)
-    const uint32_t idesc = make_idesc_f16(false, AT_BQ, AT_BK);     // fp16 operands, M128 x N64 (keys or features)
-    const uint64_t dQh = make_sw128_desc(sQh), dQl = make_sw128_desc(sQl), dP = make_sw128_desc(sP), dKV = make_sw128_desc(sKV);
-    mbar_wait(q_full, 0);
-    for (int j = 0; j <= T; ++j) {
-      if (j < T) {
-        const int s = j & 1;
-        mbar_wait(kv_full + 8 * s, (j >> 1) & 1);
-        mbar_wait(s_empty + 8 * s, ((j >> 1) & 1) ^ 1);
+    const uint32_t idesc_s = make_idesc_f16(false, AT_BQ, AT_BK);    // logits: M128 x N128 keys
+    const uint32_t idesc_d = make_idesc_f16(false, AT_BQ, AT_DP);    // projection / PV: M128 x N64 features
+    const uint64_t dQ = make_sw128_desc(sQ), dP = make_sw128_desc(sP), dKV = make_sw128_desc(sKV);
+    // ---- projection: Q_t = conf_t (theta + I)^T, hi/lo split, into the first 64 columns of S_t
+    mbar_wait(w_full, 0);
+    for (int t = 0; t < AT_QT; ++t) {
+      mbar_wait(x_full + 8 * t, 0);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t xh = dP + (uint64_t)((t * 2 * AT_TILE_Q) >> 4), xl = xh + (uint64_t)(AT_TILE_Q >> 4);
+        const uint64_t wh = dKV + (uint64_t)(((NST - 1) * STAGE) >> 4), wl = wh + (uint64_t)(AT_TILE_W >> 4);
+        const uint32_t d = tmem + t * AT_BK;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(d, xh + 2 * k, wh + 2 * k, idesc_d, k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(d, xl + 2 * k, wh + 2 * k, idesc_d, 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(d, xh + 2 * k, wl + 2 * k, idesc_d, 1u);
+        umma_commit(xq_done + 8 * t);
+      }
+      __syncwarp();
+    }
+    // ---- pass A: S = Qh Kh^T only — good to ~|q||k| 2^-10, enough for a softmax reference maximum
+    for (int u = 0; u < T; ++u) {
+      const int s = u % NST;
+      mbar_wait(kv_full + 8 * s, (u / NST) & 1);
+      for (int t = 0; t < AT_QT; ++t) {
+        if (u == 0) mbar_wait(q_ready + 8 * t, 0);
+        mbar_wait(s_empty + 8 * t, (u & 1) ^ 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t kh = dKV + (uint64_t)((s * 3 * AT_TILE_K) >> 4), kl = kh + (uint64_t)(AT_TILE_K >> 4);
-          const uint32_t d = tS + s * AT_BK;
+          const uint64_t kh = dKV + (uint64_t)((s * STAGE) >> 4), qh = dQ + (uint64_t)((2 * t * AT_TILE_Q) >> 4);
+          const uint32_t d = tmem + t * AT_BK;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(d, dQh + 2 * k, kh + 2 * k, idesc, k ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(d, dQl + 2 * k, kh + 2 * k, idesc, 1u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(d, dQh + 2 * k, kl + 2 * k, idesc, 1u);
-          umma_commit(s_full + 8 * s);
+          for (int k = 0; k < 4; ++k) umma_f16(d, qh + 2 * k, kh + 2 * k, idesc_s, k ? 1u : 0u);
+          umma_commit(s_full + 8 * t);
+          if (t == AT_QT - 1) umma_commit(kv_empty + 8 * s);
         }
         __syncwarp();
       }
-      if (j > 0) {
-        const int jj = j - 1, s = jj & 1;
-        mbar_wait(p_full, jj & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t vt = dKV + (uint64_t)((s * 3 * AT_TILE_K + 2 * AT_TILE_K) >> 4);
+    }
+    // ---- pass B: exact logits (12 UMMAs per q-tile and key tile) and O += P V (8 UMMAs)
+    for (int j = 0; j <= T; ++j) {
+      if (j < T) {
+        const int u = T + j, s = u % NST;
+        mbar_wait(kv_full + 8 * s, (u / NST) & 1);
+        if (lane == 0) AT_DBG(j * 16 + 0);
+        for (int t = 0; t < AT_QT; ++t) {
+          mbar_wait(s_empty + 8 * t, (u & 1) ^ 1);
+          tc_fence_after();
+          if (lane == 0) AT_DBG(j * 16 + 1 + t);
+          if (elect_one()) {
+            const uint64_t kh = dKV + (uint64_t)((s * STAGE) >> 4), kl = kh + (uint64_t)((2 * AT_TILE_K) >> 4);
+            const uint64_t qh = dQ + (uint64_t)((2 * t * AT_TILE_Q) >> 4), ql = qh + (uint64_t)(AT_TILE_Q >> 4);
+            const uint32_t d = tmem + t * AT_BK;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tO, dP + 2 * k, vt + 2 * k, idesc, (jj | k) ? 1u : 0u);
-          umma_commit(kv_empty + 8 * s);
-          umma_commit(pv_done);
+            for (int k = 0; k < 4; ++k) umma_f16(d, qh + 2 * k, kh + 2 * k, idesc_s, k ? 1u : 0u);
+            if (p.split) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(d, ql + 2 * k, kh + 2 * k, idesc_s, 1u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(d, qh + 2 * k, kl + 2 * k, idesc_s, 1u);
+            }
+            umma_commit(s_full + 8 * t);
+          }
+          __syncwarp();
         }
-        __syncwarp();
+      }
+      if (j > 0) {
+        const int jj = j - 1, s = (T + jj) % NST;
+        for (int t = 0; t < AT_QT; ++t) {
+          if (lane == 0 && t == 0) AT_DBG(jj * 16 + 3);
+          mbar_wait(p_full + 8 * t, jj & 1);
+          tc_fence_after();
+          if (lane == 0) AT_DBG(jj * 16 + 4 + t);
+          if (elect_one()) {
+            const uint64_t vt = dKV + (uint64_t)((s * STAGE + AT_TILE_K) >> 4), pp = dP + (uint64_t)((t * 2 * AT_TILE_Q) >> 4);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)      // keys 0-63: P / Vt block 0, keys 64-127: block 1
+              umma_f16(tO + t * AT_DP, pp + (uint64_t)((k >> 2) * (AT_TILE_Q >> 4)) + 2 * (k & 3),
+                       vt + (uint64_t)((k >> 2) * (AT_TILE_W >> 4)) + 2 * (k & 3), idesc_d, (jj | k) ? 1u : 0u);
+            umma_commit(pv_done + 8 * t);
+            if (t == AT_QT - 1) umma_commit(kv_empty + 8 * s);
+          }
+          __syncwarp();
+          if (lane == 0 && t == 1) AT_DBG(jj * 16 + 6);
+        }
       }
     }
   } else {
-    // ================= softmax warps + epilogue =================
-    const int r = warp * 32 + lane;
-    const int q = q0 + r;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    float ref = -INFINITY;          // reference maximum (natural-log units), lazily updated
-    float l = 0.f;
-    for (int j = 0; j < T; ++j) {
-      const int s = j & 1;
-      mbar_wait(s_full + 8 * s, (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t v[64];
-      tmem_ld32(tS + lane_sel + s * AT_BK, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-      tmem_ld32(tS + lane_sel + s * AT_BK + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-      tmem_ld_wait();
-      tc_fence_before();
+    // ================= softmax warps (4 per q-tile) + epilogue =================
+    const int t = warp >> 2, qd = warp & 3;
+    const int r = qd * 32 + lane;                        // row inside the q-tile == TMEM lane
+    const int q = q0 + t * AT_BQ + r;                    // query (prior) index inside the image
+    const bool q_ok = q < p.P;
+    const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
+    const uint32_t tS = tmem + lane_sel + t * AT_BK;
+    const uint32_t sPt = sP + t * 2 * AT_TILE_Q;
+    const float* xrow = p.conf + ((size_t)b * p.P + (q_ok ? q : 0)) * D;
+    uint32_t v[64];
+    if (warp == 0 && lane == 0) AT_DBG(500);
+
+    // ---- prologue: stage the conf row (hi / lo -> the two K-blocks of P_t), then Q hi/lo from the projection
+    {
+      float x[64];
+      mbar_wait(xin_full + 8 * t, 0);
+      const float* xs = p.bulk_x ? reinterpret_cast<const float*>(smem_raw + (sQ + 2 * t * AT_TILE_Q - smem_u32(smem_raw))) + r * D : xrow;
+#pragma unroll
+      for (int d = 0; d < 64; ++d) x[d] = (d < D && q_ok) ? xs[d] : 0.f;
+      if (warp == 0 && lane == 0) AT_DBG(501);
+      store_split_row(sPt, sPt + AT_TILE_Q, r, x);
+      fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty + 8 * s);
-      const int nvalid = p.Pk - j * AT_BK;                   // keys of this tile that exist
-      float mx = -INFINITY;
+      if (lane == 0) mbar_arrive(x_full + 8 * t);
+      if (warp == 0 && lane == 0) AT_DBG(502);
+      mbar_wait(xq_done + 8 * t, 0);
+      tc_fence_after();
+      if (warp == 0 && lane == 0) AT_DBG(503);
+      tmem_ld64(tS, v);
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float sv = __uint_as_float(v[c]);
-        if (c >= nvalid) sv = -INFINITY;
-        v[c] = __float_as_uint(sv);
-        mx = fmaxf(mx, sv);
-      }
-      float factor = 1.f;
-      const bool grow = mx > ref + AT_RESCALE;
-      if (grow) {
-        factor = (ref == -INFINITY) ? 0.f : __expf(ref - mx);
-        ref = mx;
-        l *= factor;
-      }
-      // the P buffer and O are free once PV_{j-1} has completed
-      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
-      if (j > 0 && __any_sync(0xffffffffu, grow)) {
-        tc_fence_after();
-        uint32_t o[32];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          tmem_ld32(tO + lane_sel + h * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
-          tmem_st32(tO + lane_sel + h * 32, o);
-        }
-        tmem_st_wait();
-      }
-      const float ref2 = ref * AT_LOG2E;
-      float sum = 0.f;
-      const uint32_t prow = sP + r * 128;
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(v[ch * 8 + 2 * e]), AT_LOG2E, -ref2));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(v[ch * 8 + 2 * e + 1]), AT_LOG2E, -ref2));
-          sum += p0 + p1;
-          __half2 hh = __floats2half2_rn(p0, p1);
-          pk[e] = *reinterpret_cast<uint32_t*>(&hh);
-        }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((ch ^ (r & 7)) << 4)), "r"(pk[0]), "r"(pk[1]),
-                     "r"(pk[2]), "r"(pk[3]) : "memory");
-      }
-      l += sum;
+      for (int d = 0; d < 64; ++d) x[d] = __uint_as_float(v[d]) + s_bias[d];
+      store_split_row(sQ + (2 * t) * AT_TILE_Q, sQ + (2 * t + 1) * AT_TILE_Q, r, x);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(q_ready + 8 * t);
     }
 
+    if (warp == 0 && lane == 0) AT_DBG(504);
+    // ---- pass A: approximate row maximum over all keys
+    float ref = -INFINITY;
+    for (int u = 0; u < T; ++u) {
+      mbar_wait(s_full + 8 * t, u & 1);
+      tc_fence_after();
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains for ILP
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        tmem_ld64(tS + hb * 64, v);
+        if (hb == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty + 8 * t);
+        }
+        const int nvalid = p.Pk - u * AT_BK - hb * 64;         // keys of this half that exist
+        if (nvalid < 64) {                                     // ragged tail only
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (c >= nvalid) v[c] = 0xff800000u;               // -inf
+        }
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+          m4[0] = fmaxf(m4[0], __uint_as_float(v[c])); m4[1] = fmaxf(m4[1], __uint_as_float(v[c + 1]));
+          m4[2] = fmaxf(m4[2], __uint_as_float(v[c + 2])); m4[3] = fmaxf(m4[3], __uint_as_float(v[c + 3]));
+        }
+      }
+      ref = fmaxf(ref, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+    }
+    if (warp == 0 && lane == 0) AT_DBG(505);
+    // ---- pass B: p = exp(s - ref) against the fixed reference
+    const float ref2 = ref * AT_LOG2E;
+    float l4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < T; ++j) {
+      const int u = T + j;
+      if (warp == 0 && lane == 0) AT_DBG(j * 16 + 7);
+      mbar_wait(s_full + 8 * t, u & 1);
+      tc_fence_after();
+      if (warp == 0 && lane == 0) AT_DBG(j * 16 + 8);
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        tmem_ld64(tS + hb * 64, v);
+        if (warp == 0 && lane == 0) AT_DBG(j * 16 + 9 + 3 * hb);
+        if (hb == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty + 8 * t);
+        }
+        const int nvalid = p.Pk - j * AT_BK - hb * 64;
+        if (nvalid < 64) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (c >= nvalid) v[c] = 0xff800000u;               // -inf -> ex2 gives exactly 0
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * e]), AT_LOG2E, -ref2));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * e + 1]), AT_LOG2E, -ref2));
+          l4[(2 * e) & 3] += p0;
+          l4[(2 * e + 1) & 3] += p1;
+          __half2 hh = __floats2half2_rn(p0, p1);
+          v[e] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        if (warp == 0 && lane == 0) AT_DBG(j * 16 + 10 + 3 * hb);
+        if (hb == 0 && j > 0) mbar_wait(pv_done + 8 * t, (j - 1) & 1);   // PV_{j-1} has finished reading P_t
+        if (warp == 0 && lane == 0) AT_DBG(j * 16 + 11 + 3 * hb);
+        const uint32_t prow = sPt + hb * AT_TILE_Q + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((ch ^ (r & 7)) << 4)), "r"(v[4 * ch]),
+                       "r"(v[4 * ch + 1]), "r"(v[4 * ch + 2]), "r"(v[4 * ch + 3]) : "memory");
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full + 8 * t);
+    }
+    const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+    if (warp == 0 && lane == 0) AT_DBG(506);
+
     // ---- epilogue: z = x + (O/l)*Wz ; z/||z|| ; OBJ_Target*scale ; [fc_base] ; [softmax] ----
-    mbar_wait(pv_done, (T - 1) & 1);
+    mbar_wait(pv_done + 8 * t, (T - 1) & 1);                 // all MMAs of this q-tile are complete: Q_t is dead
     tc_fence_after();
-    uint32_t o[64];
-    tmem_ld32(tO + lane_sel, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
-    tmem_ld32(tO + lane_sel + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
-    tmem_ld_wait();
-    if (q < p.P) {
-      const float* xrow = p.conf + ((size_t)b * p.P + q) * D;
+    // Q_t and P_t are free now.  Q_t <- the conf rows again (bulk copy), P_t <- classifier weights + output staging.
+    if (p.bulk_x && r == 0) {
+      const int rows = min(AT_BQ, p.P - (q0 + t * AT_BQ));
+      const uint32_t bytes = rows > 0 ? (uint32_t)rows * D * 4u : 0u;
+      mbar_arrive_expect_tx(xin_full + 8 * t, bytes);
+      if (bytes) bulk_load(sQ + 2 * t * AT_TILE_Q, p.conf + ((size_t)b * p.P + q0 + t * AT_BQ) * D, bytes, xin_full + 8 * t);
+    }
+    float* s_obj = reinterpret_cast<float*>(smem_raw + (sPt - smem_u32(smem_raw)));      // [num_novel][D]
+    float* s_wz = s_obj + p.num_novel * D;                                                // [D]
+    float* s_fc = s_wz + D;                                                               // incre: [D][D] + [D]
+    const int n_out = p.num_novel + (p.incre ? D : 0);
+    float* s_out = s_fc + (p.incre ? D * D + D : 0);                                      // [128][n_out]
+    for (int i = r; i < p.num_novel * D; i += AT_BQ) s_obj[i] = p.obj_w[i];
+    for (int i = r; i < D; i += AT_BQ) s_wz[i] = p.Wz[i];
+    if (p.incre) {
+      for (int i = r; i < D * D; i += AT_BQ) s_fc[i] = p.fc_w[i];
+      for (int i = r; i < D; i += AT_BQ) s_fc[D * D + i] = p.fc_b[i];
+    }
+    if (warp == 0 && lane == 0) AT_DBG(507);
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
+    tmem_ld64(tO + lane_sel + t * AT_DP, v);
+    if (p.bulk_x) mbar_wait(xin_full + 8 * t, 1);
+    if (warp == 0 && lane == 0) AT_DBG(508);
+    if (q_ok) {
+      const float* xs = p.bulk_x ? reinterpret_cast<const float*>(smem_raw + (sQ + 2 * t * AT_TILE_Q - smem_u32(smem_raw))) + r * D : xrow;
       const float inv_l = 1.0f / l;
       float x[D], z[D];
       float nrm = 0.f;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        x[d] = xrow[d];
-        z[d] = x[d] + (__uint_as_float(o[d]) * inv_l) * p.Wz[d];
+        x[d] = xs[d];
+        z[d] = x[d] + (__uint_as_float(v[d]) * inv_l) * s_wz[d];
         nrm = fmaf(z[d], z[d], nrm);
       }
       const float inv_n = 1.0f / sqrtf(nrm);
-      const int n_out = p.num_novel + (p.incre ? D : 0);
-      float* orow = p.out + ((size_t)b * p.P + q) * n_out;
       float outv[64];
       int no = 0;
       if (p.incre) {
-        const float* s_fc = s_obj + p.num_novel * D;
         for (int c = 0; c < D; ++c) {
           float a = 0.f;
 #pragma unroll
@@ -347,27 +484,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const float inv = 1.0f / sm;
         for (int c = 0; c < no; ++c) outv[c] *= inv;
       }
-      for (int c = 0; c < no; ++c) orow[c] = outv[c];
+      for (int c = 0; c < no; ++c) s_out[r * n_out + c] = outv[c];
     }
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
+    {   // the q-tile's output rows are one contiguous block: coalesced copy
+      const int rows = min(AT_BQ, p.P - (q0 + t * AT_BQ));
+      float* oblk = p.out + ((size_t)b * p.P + q0 + t * AT_BQ) * n_out;
+      for (int i = r; i < rows * n_out; i += AT_BQ) oblk[i] = s_out[i];
+    }
+    if (warp == 0 && lane == 0) AT_DBG(509);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 512);
   }
 }
 
 static size_t attn_tc_smem(int D, int num_novel, int incre) {
-  return 1024 + 2 * AT_TILE_Q + 2 * 3 * AT_TILE_K + AT_TILE_Q + 128 + sizeof(float) * (num_novel * D + (incre ? D * D + D : 0)) + 64;
+  (void)D; (void)num_novel; (void)incre;      // classifier weights alias the Q region in the epilogue (<= 32 KB per q-tile)
+  return 1024 + 4 * AT_TILE_Q + 4 * AT_TILE_Q + AT_RING + 256 + 256 + 64;
 }
 
 size_t attention_tc_workspace_bytes(int B, int P, int Pk) {
   const size_t Pk_pad = (size_t)(Pk + AT_BK - 1) / AT_BK * AT_BK;
-  return align_up((size_t)2 * B * P * AT_DP * 2, 1024) + align_up((size_t)2 * B * Pk_pad * AT_DP * 2, 1024) +
-         align_up((size_t)B * AT_DP * Pk_pad * 2, 1024);
+  (void)P;
+  return align_up((size_t)2 * B * Pk_pad * AT_DP * 2, 1024) + align_up((size_t)B * AT_DP * Pk_pad * 2, 1024) +
+         align_up((size_t)2 * AT_DP * AT_DP * 2, 1024);
 }
+
+static long long* g_attn_dbg = nullptr;
+void attention_set_debug_buffer(void* p) { g_attn_dbg = (long long*)p; }
 
 template <int D>
 static int attention_tc_launch_t(const CtxAttnParams* a, cudaStream_t st) {
@@ -379,30 +528,34 @@ static int attention_tc_launch_t(const CtxAttnParams* a, cudaStream_t st) {
     return CTX_ERR_WORKSPACE;
   }
   CTX_REQUIRE(((uintptr_t)a->workspace) % 1024 == 0, "attention: workspace must be 1024-byte aligned");
-  CTX_REQUIRE((long long)2 * B * P < (1ll << 31) && (long long)2 * B * Pk_pad < (1ll << 31), "attention: too many rows");
+  CTX_REQUIRE((long long)2 * B * Pk_pad < (1ll << 31), "attention: too many rows");
   char* ws = (char*)a->workspace;
-  __half* qhl = (__half*)ws;
-  __half* khl = (__half*)(ws + align_up((size_t)2 * B * P * AT_DP * 2, 1024));
-  __half* vt = (__half*)((char*)khl + align_up((size_t)2 * B * Pk_pad * AT_DP * 2, 1024));
-  const long long q_rows = (long long)B * P, k_rows = (long long)B * Pk_pad;
-  proj_q_kernel<D><<<cdiv(q_rows, 128), 128, 0, st>>>(a->conf, a->theta_w, a->theta_b, q_rows, qhl);
+  __half* khl = (__half*)ws;
+  __half* vt = (__half*)(ws + align_up((size_t)2 * B * Pk_pad * AT_DP * 2, 1024));
+  __half* wq = (__half*)((char*)vt + align_up((size_t)B * AT_DP * Pk_pad * 2, 1024));
+  const long long k_rows = (long long)B * Pk_pad;
+  prep_wq_kernel<<<cdiv(AT_DP * AT_DP, 256), 256, 0, st>>>(a->theta_w, D, wq);
   CTX_LAUNCH_CHECK();
   proj_kv_kernel<D><<<cdiv(k_rows, 128), 128, 0, st>>>(a->pooled, a->phi_w, a->phi_b, a->g_w, a->g_b, B, Pk, Pk_pad, khl, vt);
   CTX_LAUNCH_CHECK();
-  CUtensorMap tq, tk, tv;
-  int rc = encode_2d_sw128(&tq, qhl, false, 2ull * q_rows, AT_DP, AT_BQ);
+  CUtensorMap tw, tk, tv;
+  int rc = encode_2d_sw128(&tw, wq, false, 2ull * AT_DP, AT_DP, AT_DP);
   if (!rc) rc = encode_2d_sw128(&tk, khl, false, 2ull * k_rows, AT_DP, AT_BK);
-  if (!rc) rc = encode_2d_sw128(&tv, vt, false, (unsigned long long)B * AT_DP, (unsigned long long)Pk_pad, AT_DP);
+  if (!rc) rc = encode_2d_sw128(&tv, vt, false, (unsigned long long)B * AT_DP, (unsigned long long)Pk_pad, AT_DP);   // box: 64 keys x 64 features
   if (rc) return rc;
   AttnTcParams p;
   p.B = B; p.P = P; p.Pk = Pk; p.Pk_pad = Pk_pad; p.ntiles = Pk_pad / AT_BK;
   p.num_novel = a->num_novel; p.incre = a->incre; p.apply_softmax = a->apply_softmax;
-  p.q_rows = q_rows; p.k_rows = k_rows;
-  p.conf = a->conf; p.Wz = a->Wz; p.obj_w = a->obj_target_w; p.fc_w = a->fc_base_w; p.fc_b = a->fc_base_b;
+  p.k_rows = k_rows;
+  p.split = a->use_tensor_cores == 2;
+  p.bulk_x = ((uintptr_t)a->conf % 16 == 0) && ((size_t)P * D * 4 % 16 == 0) && ((size_t)AT_BQ * D * 4 % 16 == 0) &&
+             ((size_t)(P % AT_BQ) * D * 4 % 16 == 0);
+  p.conf = a->conf; p.theta_b = a->theta_b; p.Wz = a->Wz; p.obj_w = a->obj_target_w; p.fc_w = a->fc_base_w; p.fc_b = a->fc_base_b;
   p.scale = a->scale; p.out = a->out;
+  p.dbg = g_attn_dbg;
   const size_t smem = attn_tc_smem(D, a->num_novel, a->incre);
   CTX_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_tc_kernel<D><<<dim3(cdiv(P, AT_BQ), B), AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  attention_tc_kernel<D><<<dim3(cdiv(P, AT_QT * AT_BQ), B), AT_THREADS, smem, st>>>(tw, tk, tv, p);
   CTX_LAUNCH_CHECK();
   return CTX_OK;
 }

@@ -8,7 +8,7 @@
 //
 // One CTA per SM walks a static round-robin list of (128 output pixels) x (BN output channels) tiles;
 // K is walked in steps of 64 channels of one filter tap through a ring of S shared-memory stages
-// {A tile 16 KB, B tile BN*128 B}.  Warp roles (320 threads):
+// {A tile 16 KB, B tile BN*128 B}.  Warp roles (448 threads):
 //   warps 0-3  im2col gather producers (mode GATHER): 16-byte cp.async with zero-fill for padding /
 //              channel tails, written straight into the 128B-swizzled K-major layout of the UMMA
 //              descriptor.  M is the flattened (n, oy, ox) pixel index of the whole batch: no tile waste
@@ -26,7 +26,8 @@
 //              kind::f16) per K-step, tcgen05.commit's the stage back to the producers and, after the
 //              last K-step of a tile, the accumulator to the epilogue.  Two accumulators (2 x 256 TMEM
 //              columns) let tile i+1 start while tile i drains.
-//   warps 6-9  epilogue: tcgen05.ld the accumulator, + bias (BatchNorm folded) [+ residual] [ReLU],
+//   warps 6-13 epilogue, two sets of four warps (set 0 drains accumulator 0 = even tiles, set 1 accumulator 1 =
+//              odd tiles, so two tiles drain concurrently): tcgen05.ld the accumulator, + bias (BatchNorm folded) [+ residual] [ReLU],
 //              convert, vectorised NHWC store — or up to three fp32 segments for the fused
 //              loc / conf / obj heads (writes land directly in the concatenated [B,P,*] buffers).
 #include "tc_common.cuh"
@@ -37,7 +38,7 @@ namespace ctx {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;        // 4 producer + TMA + MMA + 2 x 4 epilogue warps
 constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;     // 16 KB
 constexpr int A_GATHER = 0, A_TMA = 1, A_STEM = 2;
 
@@ -275,8 +276,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;
     const bool bf16 = p.is_bf16 != 0;
-    uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+    const uint32_t eset = (warp - 6) >> 2;        // epilogue set: drains accumulator `eset`, i.e. local tiles eset, eset+2, ...
+    uint32_t lt = eset;
+    for (int tile = blockIdx.x + (int)eset * (int)gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, lt += 2) {
       const uint32_t buf = lt & 1;
       const int mt = tile / p.n_tiles_n, n0 = (tile - mt * p.n_tiles_n) * BN;
       int n_img, pix;

@@ -142,13 +142,16 @@ typedef struct CtxAttnParams {
   const float* Wz;                             /* [dim] */
   const float* obj_target_w;                   /* [num_novel, dim] */
   float scale;
-  int use_tensor_cores;                        /* 0: fp32 CUDA-core kernel (1e-4 parity mode); 1: tcgen05 kernel, fp16 hi/lo split operands */
+  int use_tensor_cores;                        /* 0: fp32 CUDA-core kernel (1e-4 parity mode); 1: tcgen05 kernel, fp16 logits
+                                                * (|dconf| ~6e-3 max / 2e-5 mean); 2: tcgen05 kernel, fp16 hi/lo split logits (4e-5) */
   void* workspace;                             /* ctx_attention_workspace_bytes(p) bytes, 1024-byte aligned */
   size_t workspace_bytes;
   float* out;                                  /* [B,P, incre ? dim+num_novel : num_novel] */
 } CtxAttnParams;
 size_t ctx_attention_workspace_bytes(const CtxAttnParams* p);   /* reads batch, num_priors, num_pooled, dim, use_tensor_cores */
 int ctx_attention_forward(const CtxAttnParams* p, void* stream);
+/* development aid: device buffer (>= 512 int64) receiving clock64() stamps of CTA (0,0) of the tensor-core kernel; NULL disables */
+void ctx_debug_set_attention_timeline(void* device_buffer);
 /* row softmax over the last dim (C <= 128) — output activation :279-285 for obj / non-'ours' conf */
 int ctx_softmax_lastdim(const float* in, float* out, long long rows, int cols, void* stream);
 

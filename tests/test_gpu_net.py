@@ -154,7 +154,7 @@ def test_attention_kernel_vs_torch(setting, d, n_novel):
     dv = lambda t: t.to(DEV).contiguous()
     t_ = [dv(t) for t in (conf, pool, tw, tb, pw, pb, gw, gb, fw, fb, Wz, ot)]
     n_out = want.size(-1)
-    for apply_softmax, use_tc in ((0, 0), (1, 0), (0, 1), (1, 1)):
+    for apply_softmax, use_tc in ((0, 0), (1, 0), (0, 1), (1, 1), (0, 2), (1, 2)):
         out = torch.empty(B, P, n_out, device=DEV)
         ap = _lib.CtxAttnParams()
         ap.batch, ap.num_priors, ap.num_pooled, ap.dim = B, P, Pk, d
@@ -167,9 +167,15 @@ def test_attention_kernel_vs_torch(setting, d, n_novel):
         _lib.check(L.ctx_attention_forward(C.byref(ap), _lib.current_stream_ptr()))
         torch.cuda.synchronize()
         w_ = torch.softmax(want, -1) if apply_softmax else want
-        # tensor-core path: fp16 hi/lo split Q and K (logits ~fp32-exact), fp16 P and V -> 1e-3 on the raw
-        # cosine logits (|.| <= 5), 2e-4 on probabilities
-        tol = dict(rtol=1e-4, atol=2e-5) if not use_tc else (dict(rtol=0, atol=2e-4) if apply_softmax else dict(rtol=0, atol=2e-3))
+        # tensor-core path, mode 2: fp16 hi/lo split Q and K (logits ~fp32-exact), fp16 P and V -> 2e-3 on the raw
+        # cosine logits (|.| <= 5), 2e-4 on probabilities.  mode 1: plain fp16 logits (|s| ~ 1e2 here, so ~0.05 absolute
+        # logit error): an order looser, used by the 16-bit engine modes whose conv stack is no more accurate than that.
+        if not use_tc:
+            tol = dict(rtol=1e-4, atol=2e-5)
+        elif use_tc == 2:
+            tol = dict(rtol=0, atol=2e-4) if apply_softmax else dict(rtol=0, atol=2e-3)
+        else:
+            tol = dict(rtol=0, atol=2e-2) if apply_softmax else dict(rtol=0, atol=2e-1)
         assert torch.allclose(out.cpu(), w_, **tol), (use_tc, apply_softmax, float((out.cpu() - w_).abs().max()))
 
 
