@@ -74,6 +74,7 @@ proj_kv_kernel(const float* __restrict__ pooled, const float* __restrict__ phi_w
       }
       h[e] = __float2half_rn(k);
       l[e] = __float2half_rn(k - __half2float(h[e]));
+      if (o == D) v = valid ? 1.f : 0.f;                     // "ones" feature: the PV MMA then accumulates sum_j p_j in O[:, D]
       vt[((long long)b * AT_DP + o) * Pk_pad + j] = __float2half_rn(v);
     }
     *reinterpret_cast<uint4*>(hi + o0) = *reinterpret_cast<uint4*>(h);
@@ -135,7 +136,7 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
   tmem_ld_wait();
 }
 
-template <int D>
+template <int D, int NN>       // feature dim, novel classes (rows of OBJ_Target)
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p) {
@@ -149,13 +150,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   const int NST = p.split ? 2 : 3;                       // ring depth
   const uint32_t STAGE = p.split ? AT_STAGE_SPLIT : AT_STAGE_FAST;
   const uint32_t w_full = bars, x_full = bars + 8, xq_done = bars + 24, q_ready = bars + 40, kv_full = bars + 56,
-                 kv_empty = kv_full + 8 * 3, s_full = kv_empty + 8 * 3, s_empty = s_full + 16,
-                 p_full = s_empty + 16, pv_done = p_full + 16, tmem_slot = pv_done + 16, xin_full = tmem_slot + 8;
+                 kv_empty = kv_full + 8 * 3, s_full = kv_empty + 8 * 3, s_empty = s_full + 32,
+                 p_full = s_empty + 32, pv_done = p_full + 16, tmem_slot = pv_done + 16, xin_full = tmem_slot + 8;
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256 - smem_u32(smem_raw)));   // [64] theta bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, q0 = blockIdx.x * (AT_QT * AT_BQ);
   const int T = p.ntiles;
+  const int nA0 = (T + 1) >> 1;                          // uses of S buffer 0 during pass A (phase offset for pass B)
 
   if (warp == 8 && lane == 0) { tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); }
   if (warp == 9) {
@@ -164,7 +166,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       for (int t = 0; t < AT_QT; ++t) {
         mbar_init(x_full + 8 * t, 4); mbar_init(xq_done + 8 * t, 1); mbar_init(q_ready + 8 * t, 4);
         mbar_init(p_full + 8 * t, 4); mbar_init(pv_done + 8 * t, 1);
-        mbar_init(s_full + 8 * t, 1); mbar_init(s_empty + 8 * t, 4); mbar_init(xin_full + 8 * t, 1);
+        for (int sb = 0; sb < 2; ++sb) { mbar_init(s_full + 8 * (2 * t + sb), 1); mbar_init(s_empty + 8 * (2 * t + sb), 4); }
+        mbar_init(xin_full + 8 * t, 1);
       }
       for (int s = 0; s < 3; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
       fence_barrier_init();
@@ -243,14 +246,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       mbar_wait(kv_full + 8 * s, (u / NST) & 1);
       for (int t = 0; t < AT_QT; ++t) {
         if (u == 0) mbar_wait(q_ready + 8 * t, 0);
-        mbar_wait(s_empty + 8 * t, (u & 1) ^ 1);
+        // pass A ping-pongs S_t between its own columns and the (still unused) O / spare columns: u even -> 128 t,
+        // u odd -> 256 + 128 t; a buffer is free once the softmax warps have read tile u-2
+        mbar_wait(s_empty + 8 * (2 * t + (u & 1)), ((u >> 1) & 1) ^ 1);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t kh = dKV + (uint64_t)((s * STAGE) >> 4), qh = dQ + (uint64_t)((2 * t * AT_TILE_Q) >> 4);
-          const uint32_t d = tmem + t * AT_BK;
+          const uint32_t d = tmem + t * AT_BK + (u & 1) * 256;
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(d, qh + 2 * k, kh + 2 * k, idesc_s, k ? 1u : 0u);
-          umma_commit(s_full + 8 * t);
+          umma_commit(s_full + 8 * (2 * t + (u & 1)));
           if (t == AT_QT - 1) umma_commit(kv_empty + 8 * s);
         }
         __syncwarp();
@@ -263,7 +268,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         mbar_wait(kv_full + 8 * s, (u / NST) & 1);
         if (lane == 0) AT_DBG(j * 16 + 0);
         for (int t = 0; t < AT_QT; ++t) {
-          mbar_wait(s_empty + 8 * t, (u & 1) ^ 1);
+          mbar_wait(s_empty + 8 * (2 * t), ((nA0 + j) & 1) ^ 1);       // pass B uses S buffer 0 only (buffer 1 became O)
           tc_fence_after();
           if (lane == 0) AT_DBG(j * 16 + 1 + t);
           if (elect_one()) {
@@ -278,7 +283,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma_f16(d, qh + 2 * k, kl + 2 * k, idesc_s, 1u);
             }
-            umma_commit(s_full + 8 * t);
+            umma_commit(s_full + 8 * (2 * t));
           }
           __syncwarp();
         }
@@ -347,16 +352,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     // ---- pass A: approximate row maximum over all keys
     float ref = -INFINITY;
     for (int u = 0; u < T; ++u) {
-      mbar_wait(s_full + 8 * t, u & 1);
+      const int sb = u & 1;
+      mbar_wait(s_full + 8 * (2 * t + sb), (u >> 1) & 1);
       tc_fence_after();
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains for ILP
 #pragma unroll
       for (int hb = 0; hb < 2; ++hb) {
-        tmem_ld64(tS + hb * 64, v);
+        tmem_ld64(tS + sb * 256 + hb * 64, v);
         if (hb == 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(s_empty + 8 * t);
+          if (lane == 0) mbar_arrive(s_empty + 8 * (2 * t + sb));
         }
         const int nvalid = p.Pk - u * AT_BK - hb * 64;         // keys of this half that exist
         if (nvalid < 64) {                                     // ragged tail only
@@ -375,11 +381,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     if (warp == 0 && lane == 0) AT_DBG(505);
     // ---- pass B: p = exp(s - ref) against the fixed reference
     const float ref2 = ref * AT_LOG2E;
-    float l4[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < T; ++j) {
       const int u = T + j;
       if (warp == 0 && lane == 0) AT_DBG(j * 16 + 7);
-      mbar_wait(s_full + 8 * t, u & 1);
+      mbar_wait(s_full + 8 * (2 * t), (nA0 + j) & 1);
       tc_fence_after();
       if (warp == 0 && lane == 0) AT_DBG(j * 16 + 8);
 #pragma unroll
@@ -389,7 +394,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         if (hb == 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(s_empty + 8 * t);
+          if (lane == 0) mbar_arrive(s_empty + 8 * (2 * t));
         }
         const int nvalid = p.Pk - j * AT_BK - hb * 64;
         if (nvalid < 64) {
@@ -401,8 +406,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         for (int e = 0; e < 32; ++e) {
           const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * e]), AT_LOG2E, -ref2));
           const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * e + 1]), AT_LOG2E, -ref2));
-          l4[(2 * e) & 3] += p0;
-          l4[(2 * e + 1) & 3] += p1;
           __half2 hh = __floats2half2_rn(p0, p1);
           v[e] = *reinterpret_cast<uint32_t*>(&hh);
         }
@@ -419,7 +422,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full + 8 * t);
     }
-    const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
     if (warp == 0 && lane == 0) AT_DBG(506);
 
     // ---- epilogue: z = x + (O/l)*Wz ; z/||z|| ; OBJ_Target*scale ; [fc_base] ; [softmax] ----
@@ -433,11 +435,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       if (bytes) bulk_load(sQ + 2 * t * AT_TILE_Q, p.conf + ((size_t)b * p.P + q0 + t * AT_BQ) * D, bytes, xin_full + 8 * t);
     }
     float* s_obj = reinterpret_cast<float*>(smem_raw + (sPt - smem_u32(smem_raw)));      // [num_novel][D]
-    float* s_wz = s_obj + p.num_novel * D;                                                // [D]
+    float* s_wz = s_obj + NN * D;                                                // [D]
     float* s_fc = s_wz + D;                                                               // incre: [D][D] + [D]
-    const int n_out = p.num_novel + (p.incre ? D : 0);
+    const int n_out = NN + (p.incre ? D : 0);
     float* s_out = s_fc + (p.incre ? D * D + D : 0);                                      // [128][n_out]
-    for (int i = r; i < p.num_novel * D; i += AT_BQ) s_obj[i] = p.obj_w[i];
+    for (int i = r; i < NN * D; i += AT_BQ) s_obj[i] = p.obj_w[i];
     for (int i = r; i < D; i += AT_BQ) s_wz[i] = p.Wz[i];
     if (p.incre) {
       for (int i = r; i < D * D; i += AT_BQ) s_fc[i] = p.fc_w[i];
@@ -450,7 +452,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     if (warp == 0 && lane == 0) AT_DBG(508);
     if (q_ok) {
       const float* xs = p.bulk_x ? reinterpret_cast<const float*>(smem_raw + (sQ + 2 * t * AT_TILE_Q - smem_u32(smem_raw))) + r * D : xrow;
-      const float inv_l = 1.0f / l;
+      static_assert(D < AT_DP, "the row sum lives in the padding feature column D");
+      const float inv_l = 1.0f / __uint_as_float(v[D]);        // sum_j p_j, accumulated by the PV MMA (ones feature of V)
       float x[D], z[D];
       float nrm = 0.f;
 #pragma unroll
@@ -460,31 +463,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         nrm = fmaf(z[d], z[d], nrm);
       }
       const float inv_n = 1.0f / sqrtf(nrm);
-      float outv[64];
-      int no = 0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) z[d] *= inv_n;
+      float* orow_s = s_out + r * n_out;
       if (p.incre) {
         for (int c = 0; c < D; ++c) {
           float a = 0.f;
 #pragma unroll
           for (int d = 0; d < D; ++d) a = fmaf(s_fc[c * D + d], x[d], a);
-          outv[no++] = (a + s_fc[D * D + c]) + x[c];
+          orow_s[c] = (a + s_fc[D * D + c]) + x[c];
         }
       }
-      for (int c = 0; c < p.num_novel; ++c) {
+      float nov[NN];
+#pragma unroll
+      for (int c = 0; c < NN; ++c) {
         float a = 0.f;
 #pragma unroll
-        for (int d = 0; d < D; ++d) a = fmaf(s_obj[c * D + d], z[d] * inv_n, a);
-        outv[no++] = a * p.scale;
+        for (int d = 0; d < D; ++d) a = fmaf(s_obj[c * D + d], z[d], a);
+        nov[c] = a * p.scale;
       }
       if (p.apply_softmax) {
         float mxo = -INFINITY;
-        for (int c = 0; c < no; ++c) mxo = fmaxf(mxo, outv[c]);
+#pragma unroll
+        for (int c = 0; c < NN; ++c) mxo = fmaxf(mxo, nov[c]);
+        if (p.incre) for (int c = 0; c < D; ++c) mxo = fmaxf(mxo, orow_s[c]);
         float sm = 0.f;
-        for (int c = 0; c < no; ++c) { outv[c] = expf(outv[c] - mxo); sm += outv[c]; }
+#pragma unroll
+        for (int c = 0; c < NN; ++c) { nov[c] = __expf(nov[c] - mxo); sm += nov[c]; }
+        if (p.incre) for (int c = 0; c < D; ++c) { const float e = __expf(orow_s[c] - mxo); orow_s[c] = e; sm += e; }
         const float inv = 1.0f / sm;
-        for (int c = 0; c < no; ++c) outv[c] *= inv;
+#pragma unroll
+        for (int c = 0; c < NN; ++c) nov[c] *= inv;
+        if (p.incre) for (int c = 0; c < D; ++c) orow_s[c] *= inv;
       }
-      for (int c = 0; c < no; ++c) s_out[r * n_out + c] = outv[c];
+      const int off = p.incre ? D : 0;
+#pragma unroll
+      for (int c = 0; c < NN; ++c) orow_s[off + c] = nov[c];
     }
     asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
     {   // the q-tile's output rows are one contiguous block: coalesced copy
@@ -518,7 +532,7 @@ size_t attention_tc_workspace_bytes(int B, int P, int Pk) {
 static long long* g_attn_dbg = nullptr;
 void attention_set_debug_buffer(void* p) { g_attn_dbg = (long long*)p; }
 
-template <int D>
+template <int D, int NN>
 static int attention_tc_launch_t(const CtxAttnParams* a, cudaStream_t st) {
   const int B = a->batch, P = a->num_priors, Pk = a->num_pooled;
   const int Pk_pad = (Pk + AT_BK - 1) / AT_BK * AT_BK;
@@ -554,17 +568,17 @@ static int attention_tc_launch_t(const CtxAttnParams* a, cudaStream_t st) {
   p.scale = a->scale; p.out = a->out;
   p.dbg = g_attn_dbg;
   const size_t smem = attn_tc_smem(D, a->num_novel, a->incre);
-  CTX_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_tc_kernel<D><<<dim3(cdiv(P, AT_QT * AT_BQ), B), AT_THREADS, smem, st>>>(tw, tk, tv, p);
+  CTX_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<D, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_tc_kernel<D, NN><<<dim3(cdiv(P, AT_QT * AT_BQ), B), AT_THREADS, smem, st>>>(tw, tk, tv, p);
   CTX_LAUNCH_CHECK();
   return CTX_OK;
 }
 
 int attention_tc_launch(const CtxAttnParams* a, cudaStream_t st) {
-  if (a->dim == 60) return attention_tc_launch_t<60>(a, st);
-  if (a->dim == 15) return attention_tc_launch_t<15>(a, st);
-  if (a->dim == 20) return attention_tc_launch_t<20>(a, st);
-  set_error("attention: dim %d not instantiated (60 transfer / 15 incre / 20)", a->dim);
+  if (a->dim == 60 && a->num_novel == 20) return attention_tc_launch_t<60, 20>(a, st);     // transfer (RFB_Net_vgg.py:157-163)
+  if (a->dim == 15 && a->num_novel == 5) return attention_tc_launch_t<15, 5>(a, st);       // incre (:172-179)
+  if (a->dim == 20 && a->num_novel == 20) return attention_tc_launch_t<20, 20>(a, st);
+  set_error("attention: (dim %d, novel %d) not instantiated (60/20 transfer, 15/5 incre, 20/20)", a->dim, a->num_novel);
   return CTX_ERR_UNSUPPORTED;
 }
 
