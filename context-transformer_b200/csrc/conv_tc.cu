@@ -33,6 +33,7 @@
 #include "tc_common.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace ctx {
 
@@ -49,7 +50,8 @@ struct TcParams {
   int N, H, W, Cin, in_cstride, in_coffset;
   int Cout, KH, KW, stride, pad_h, pad_w, dil, Ho, Wo, relu, relu_cend;
   int M, cin_blocks, nk;
-  int bn, n_tiles_n, num_tiles;
+  int bn, n_tiles_n, num_tiles;          // num_tiles counts tile GROUPS: `cluster` M-adjacent tiles of one N tile
+  int m_tiles, cluster;                  // cluster = 2: CTA pairs, one 2-CTA MMA per K-step (opt-in)
   int a_mode, TW, TH, tiles_x, tiles_y;       // TMA mode: output patch TW x TH, tiles per image
   int res_cstride, res_coffset, res_dtype;
   int is_bf16;
@@ -67,7 +69,7 @@ __device__ __forceinline__ bool tile_row_pixel(const TcParams& p, int mt, int r,
     const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
     const int oy = ty * p.TH + r / p.TW, ox = tx * p.TW + r % p.TW;
     pix = oy * p.Wo + ox;
-    return oy < p.Ho && ox < p.Wo;
+    return n_img < p.N && oy < p.Ho && ox < p.Wo;
   }
   const int m = mt * TC_BM + r;
   const int HoWo = p.Ho * p.Wo;
@@ -77,41 +79,52 @@ __device__ __forceinline__ bool tile_row_pixel(const TcParams& p, int mt, int r,
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <int S>
+template <int S, int CL>       // ring stages; CTAs per MMA (1, or 2 = cta_group::2 pairs in a cluster of two)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const TcParams p) {
   constexpr int LOOKAHEAD = S - 2;      // gathers that may still be in flight when the next one is issued
   extern __shared__ uint8_t smem_raw[];
   const int BN = p.bn;
-  const int B_STAGE = BN * TC_BK * 2;
+  const int B_STAGE = (BN / CL) * TC_BK * 2;           // CTA pairs: each CTA stages its own N-half of the weight tile
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024-B alignment
   const uint32_t sA = smem_base, sB = smem_base + S * TC_A_STAGE;
   const uint32_t bars = sB + S * B_STAGE;
-  const uint32_t full0 = bars, empty0 = bars + 8 * S, accf0 = bars + 16 * S, acce0 = accf0 + 16, tmem_slot = acce0 + 16;
+  const uint32_t full0 = bars, empty0 = bars + 8 * S, pfull0 = bars + 16 * S, accf0 = bars + 24 * S, acce0 = accf0 + 16,
+                 tmem_slot = acce0 + 16;
   // per-channel epilogue vector (bias with BatchNorm folded), staged once per CTA: [ceil32(Cout) + 32] floats
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 16 * S + 64 - smem_u32(smem_raw)));
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 24 * S + 64 - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = p.nk;
+  const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int group0 = blockIdx.x / CL, ngroups = gridDim.x / CL;   // persistent walk over tile groups
 
   if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmap_w); if (p.a_mode == A_TMA) tma_prefetch_desc(&tmap_a); }
   if (warp == 5) {
     if (lane == 0) {
-      const uint32_t full_count = p.a_mode == A_TMA ? 1u : 5u;
-      for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, full_count); mbar_init(empty0 + 8 * s, 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 4); }
+      // arrivals per phase: the (leader's) TMA thread, plus four producer warps per CTA unless the TMA unit stages A too;
+      // in pair mode every producer of either CTA signals the LEADER's barrier (the peer's own full barriers stay unused)
+      const uint32_t full_count = p.a_mode == A_TMA ? 1u : 1u + 4u * (uint32_t)CL;
+      for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, full_count); mbar_init(empty0 + 8 * s, 1); mbar_init(pfull0 + 8 * s, 1); }
+      // pair mode: the leader's MMA also waits for the peer's four epilogue warps (remote arrivals)
+      for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 4u * (uint32_t)CL); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (CL == 2) { tmem_alloc_2cta(tmem_slot, 512); tmem_relinquish_2cta(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   for (int c = threadIdx.x; c < ((p.Cout + 31) & ~31) + 32; c += TC_THREADS) s_bias[c] = c < p.Cout ? p.bias[c] : 0.f;
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();                          // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto arrive_full = [&](uint32_t bar) {            // producer-warp arrival on the barrier the MMA issuer waits on
+    if (CL == 2 && rank == 1) mbar_arrive_remote(bar, 0); else mbar_arrive(bar);
+  };
 
   if (warp < 4) {
     // ================= im2col gather producers =================
@@ -122,8 +135,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       const int HoWo = p.Ho * p.Wo;
       const uint16_t* in = reinterpret_cast<const uint16_t*>(p.in);
       uint32_t g = 0;                            // K-steps issued so far (across tiles)
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles_n) * TC_BM;
+      for (int tile = group0; tile < p.num_tiles; tile += ngroups) {
+        const int m0 = ((tile / p.n_tiles_n) * CL + rank) * TC_BM;
         long long base[8];
         uint32_t mask[8];
 #pragma unroll
@@ -162,7 +175,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             cp_async_wait<LOOKAHEAD>();
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * ((g - LOOKAHEAD) % S));
+            if (lane == 0) arrive_full(full0 + 8 * ((g - LOOKAHEAD) % S));
           }
           if (++cc == p.cin_blocks) { cc = 0; ++tap; if (++kx == p.KW) { kx = 0; ++ky; } }
         }
@@ -171,7 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       fence_proxy_async();
       __syncwarp();
       if (lane == 0)
-        for (uint32_t q = (g > (uint32_t)LOOKAHEAD ? g - LOOKAHEAD : 0u); q < g; ++q) mbar_arrive(full0 + 8 * (q % S));
+        for (uint32_t q = (g > (uint32_t)LOOKAHEAD ? g - LOOKAHEAD : 0u); q < g; ++q) arrive_full(full0 + 8 * (q % S));
     } else if (p.a_mode == A_STEM) {
       // one output pixel per thread: 27 coalesced fp32 loads of the 3x3x3 neighbourhood -> one 128-byte K-step row
       const int r = threadIdx.x;                 // 0..127
@@ -179,8 +192,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       const float* img = reinterpret_cast<const float*>(p.in);
       const bool bf16 = p.is_bf16 != 0;
       uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++g) {
-        const int m = (tile / p.n_tiles_n) * TC_BM + r;
+      for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++g) {
+        const int m = ((tile / p.n_tiles_n) * CL + rank) * TC_BM + r;
         float v[28];
 #pragma unroll
         for (int e = 0; e < 28; ++e) v[e] = 0.f;
@@ -213,15 +226,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(full0 + 8 * s);
+        if (lane == 0) arrive_full(full0 + 8 * s);
       }
     }
   } else if (warp == 4) {
     // ================= TMA producer (weights; activations too in mode TMA) =================
     uint32_t g = 0;
-    const uint32_t tx_bytes = (uint32_t)B_STAGE + (p.a_mode == A_TMA ? (uint32_t)TC_A_STAGE : 0u);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles_n, n0 = (tile - mt * p.n_tiles_n) * BN;
+    // pair mode: the leader's barrier counts the bytes landing in BOTH CTAs
+    const uint32_t tx_bytes = (uint32_t)CL * ((uint32_t)B_STAGE + (p.a_mode == A_TMA ? (uint32_t)TC_A_STAGE : 0u));
+    for (int tile = group0; tile < p.num_tiles; tile += ngroups) {
+      const int mg = tile / p.n_tiles_n, n0 = (tile - mg * p.n_tiles_n) * BN, mt = mg * CL + rank;
       int n_img = 0, x0 = 0, y0 = 0;
       if (p.a_mode == A_TMA) {
         const int per_img = p.tiles_x * p.tiles_y;
@@ -235,11 +249,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const uint32_t s = g % S;
         mbar_wait(empty0 + 8 * s, ((g / S) & 1) ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(full0 + 8 * s, tx_bytes);
-          tma_load_2d(sB + s * B_STAGE, &tmap_w, it * TC_BK, n0, full0 + 8 * s);
-          if (p.a_mode == A_TMA)
-            tma_load_4d(sA + s * TC_A_STAGE, &tmap_a, p.in_coffset + cc * TC_BK, x0 + kx * p.dil, y0 + ky * p.dil, n_img,
-                        full0 + 8 * s);
+          // this CTA stages rows [rank * BN/CL, +BN/CL) of the weight tile (a 2-CTA MMA reads both halves)
+          if (CL == 2 && rank == 1) {
+            tma_load_2d_2cta(sB + s * B_STAGE, &tmap_w, it * TC_BK, n0 + (BN / CL), full0 + 8 * s);
+            if (p.a_mode == A_TMA)
+              tma_load_4d_2cta(sA + s * TC_A_STAGE, &tmap_a, p.in_coffset + cc * TC_BK, x0 + kx * p.dil, y0 + ky * p.dil, n_img,
+                               full0 + 8 * s);
+          } else {
+            mbar_arrive_expect_tx(full0 + 8 * s, tx_bytes);
+            tma_load_2d(sB + s * B_STAGE, &tmap_w, it * TC_BK, n0, full0 + 8 * s);
+            if (p.a_mode == A_TMA)
+              tma_load_4d(sA + s * TC_A_STAGE, &tmap_a, p.in_coffset + cc * TC_BK, x0 + kx * p.dil, y0 + ky * p.dil, n_img,
+                          full0 + 8 * s);
+          }
         }
         __syncwarp();
         if (++cc == p.cin_blocks) { cc = 0; if (++kx == p.KW) { kx = 0; ++ky; } }
@@ -247,29 +269,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
   } else if (warp == 5) {
     // ================= MMA issuer =================
-    // whole warp converged; one elected lane issues (see elect_one)
-    const uint32_t idesc = make_idesc_f16(p.is_bf16 != 0, TC_BM, BN);
-    const uint64_t adesc0 = make_sw128_desc(sA), bdesc0 = make_sw128_desc(sB);
-    uint32_t g = 0, lt = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
-      const uint32_t buf = lt & 1;
-      mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + buf * 256;
-      for (int it = 0; it < nk; ++it, ++g) {
-        const uint32_t s = g % S;
-        mbar_wait(full0 + 8 * s, (g / S) & 1);
+    // whole warp converged; one elected lane issues (see elect_one).  Pair mode: only the leader CTA (rank 0) issues —
+    // one tcgen05.mma.cta_group::2 drives both SMs' tensor cores (M = 256: 128 rows from each CTA, B halves from each
+    // CTA's shared memory); the peer's producers and TMA loads signal the leader's full barriers directly.
+    if (!(CL == 2 && rank == 1)) {
+      const uint32_t idesc = make_idesc_f16(p.is_bf16 != 0, TC_BM * CL, BN);
+      const uint64_t adesc0 = make_sw128_desc(sA), bdesc0 = make_sw128_desc(sB);
+      uint32_t g = 0, lt = 0;
+      for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++lt) {
+        const uint32_t buf = lt & 1;
+        mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);            // (pair mode: both CTAs' epilogues) have drained it
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t ad = adesc0 + (uint64_t)((s * TC_A_STAGE) >> 4), bd = bdesc0 + (uint64_t)((s * B_STAGE) >> 4);
+        const uint32_t tmem_d = tmem_base + buf * 256;
+        for (int it = 0; it < nk; ++it, ++g) {
+          const uint32_t s = g % S;
+          mbar_wait(full0 + 8 * s, (g / S) & 1);                   // pair mode: arrivals come from both CTAs
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = adesc0 + (uint64_t)((s * TC_A_STAGE) >> 4), bd = bdesc0 + (uint64_t)((s * B_STAGE) >> 4);
+            if (CL == 2) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) umma_f16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (it | k) ? 1u : 0u);
-          umma_commit(empty0 + 8 * s);
+              for (int k = 0; k < TC_BK / 16; ++k) umma_f16_2cta(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (it | k) ? 1u : 0u);
+              umma_commit_2cta(empty0 + 8 * s, (uint16_t)3);
+            } else {
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) umma_f16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (it | k) ? 1u : 0u);
+              umma_commit(empty0 + 8 * s);
+            }
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          if (CL == 2) umma_commit_2cta(accf0 + 8 * buf, (uint16_t)3);
+          else umma_commit(accf0 + 8 * buf);
         }
         __syncwarp();
       }
-      if (elect_one()) umma_commit(accf0 + 8 * buf);
-      __syncwarp();
     }
   } else {
     // ================= epilogue =================
@@ -278,9 +313,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     const bool bf16 = p.is_bf16 != 0;
     const uint32_t eset = (warp - 6) >> 2;        // epilogue set: drains accumulator `eset`, i.e. local tiles eset, eset+2, ...
     uint32_t lt = eset;
-    for (int tile = blockIdx.x + (int)eset * (int)gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, lt += 2) {
+    for (int tile = group0 + (int)eset * ngroups; tile < p.num_tiles; tile += 2 * ngroups, lt += 2) {
       const uint32_t buf = lt & 1;
-      const int mt = tile / p.n_tiles_n, n0 = (tile - mt * p.n_tiles_n) * BN;
+      const int mg = tile / p.n_tiles_n, n0 = (tile - mg * p.n_tiles_n) * BN, mt = mg * CL + rank;
       int n_img, pix;
       const bool row_ok = tile_row_pixel(p, mt, r, n_img, pix);
       const long long m_lin = (long long)n_img * p.Ho * p.Wo + pix;
@@ -365,15 +400,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+      if (lane == 0) {
+        if (CL == 2 && rank == 1) mbar_arrive_remote(acce0 + 8 * buf, 0);     // the leader's MMA owns the accumulator hand-off
+        else mbar_arrive(acce0 + 8 * buf);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();                          // no CTA exits while its peer can still multicast into it
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CL == 2) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -424,10 +463,22 @@ static bool choose_patch(const CtxConvParams* p, int* tw, int* th) {
   return best * 10 <= (long long)p->Wo * p->Ho * 11;
 }
 
-template <int S>
+template <int S, int CL>
 static int launch_tc(const TcPlan* pl, cudaStream_t st) {
-  CTX_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
-  conv_tc_kernel<S><<<pl->grid, TC_THREADS, pl->smem, st>>>(pl->tmap_w, pl->tmap_a, pl->p);
+  CTX_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<S, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)pl->grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = pl->smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)pl->p.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pl->p.cluster > 1 ? 1 : 0;
+  CTX_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_kernel<S, CL>, pl->tmap_w, pl->tmap_a, pl->p));
   CTX_LAUNCH_CHECK();
   return CTX_OK;
 }
@@ -487,9 +538,6 @@ extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out
   // N tile: split Cout evenly over ceil(Cout / 256) tiles, rounded up to the UMMA granularity of 16
   t.n_tiles_n = cdiv(p->Cout, 256);
   t.bn = (cdiv(p->Cout, t.n_tiles_n) + 15) / 16 * 16;
-  const int stage_bytes = TC_A_STAGE + t.bn * TC_BK * 2;
-  pl->stages = stage_bytes <= 24 * 1024 ? 8 : (stage_bytes <= 32 * 1024 ? 6 : 4);
-  pl->smem = (size_t)pl->stages * stage_bytes + 16 * pl->stages + 64 + 4 * (((size_t)p->Cout + 31) / 32 * 32 + 32) + 1024;
 
   int tw = 0, th = 0;
   t.a_mode = p->in_nchw ? A_STEM : (choose_patch(p, &tw, &th) ? A_TMA : A_GATHER);
@@ -497,13 +545,24 @@ extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out
   t.tiles_x = t.a_mode == A_TMA ? cdiv(p->Wo, tw) : 0;
   t.tiles_y = t.a_mode == A_TMA ? cdiv(p->Ho, th) : 0;
   const int m_tiles = t.a_mode == A_TMA ? p->N * t.tiles_x * t.tiles_y : cdiv(t.M, TC_BM);
-  t.num_tiles = m_tiles * t.n_tiles_n;
-  pl->grid = std::min(t.num_tiles, num_sms());
+  t.m_tiles = m_tiles;
+  {
+    // CTA pairs (one tcgen05.mma.cta_group::2 spanning both SMs of a cluster of two, each CTA staging half of the weight
+    // tile) are implemented and parity-tested, but on this network they measure within 2 % of the single-CTA path
+    // (profiles/README.md), so they stay opt-in: CTX_CONV_CLUSTER=2.
+    const char* e = getenv("CTX_CONV_CLUSTER");
+    t.cluster = (e && e[0] == '2' && m_tiles >= 2 && t.bn % 32 == 0 && t.bn >= 128) ? 2 : 1;
+  }
+  t.num_tiles = cdiv(m_tiles, t.cluster) * t.n_tiles_n;
+  const int stage_bytes = TC_A_STAGE + (t.bn / t.cluster) * TC_BK * 2;
+  pl->stages = stage_bytes <= 24 * 1024 ? 8 : (stage_bytes <= 32 * 1024 ? 6 : 4);
+  pl->smem = (size_t)pl->stages * stage_bytes + 24 * pl->stages + 64 + 4 * (((size_t)p->Cout + 31) / 32 * 32 + 32) + 1024;
+  pl->grid = std::min(t.num_tiles, num_sms() / t.cluster) * t.cluster;
 
   // weights: [Cout_pad][KH*KW*Cin_pad] 16-bit, K-major; box = 64 (K) x BN (Cout), SWIZZLE_128B, OOB rows read as zero
   const unsigned long long ktot = (unsigned long long)t.nk * TC_BK;
   const unsigned long long cout_pad = (unsigned long long)((p->Cout + 15) / 16 * 16);
-  int rc = encode_2d_sw128(&pl->tmap_w, p->weight, t.is_bf16 != 0, cout_pad, ktot, (unsigned)t.bn);
+  int rc = encode_2d_sw128(&pl->tmap_w, p->weight, t.is_bf16 != 0, cout_pad, ktot, (unsigned)(t.bn / t.cluster));
   if (!rc && t.a_mode == A_TMA)
     rc = encode_nhwc_sw128(&pl->tmap_a, p->in, t.is_bf16 != 0, p->N, p->H, p->W, p->in_cstride, (unsigned)tw, (unsigned)th);
   if (rc) { delete pl; return rc; }
@@ -515,9 +574,14 @@ extern "C" int ctx_conv2d_tc_plan_run(void* plan, void* stream) {
   CTX_REQUIRE(plan, "ctx_conv2d_tc_plan_run: null plan");
   const TcPlan* pl = (const TcPlan*)plan;
   cudaStream_t st = (cudaStream_t)stream;
-  if (pl->stages == 8) return launch_tc<8>(pl, st);
-  if (pl->stages == 6) return launch_tc<6>(pl, st);
-  return launch_tc<4>(pl, st);
+  if (pl->p.cluster == 2) {
+    if (pl->stages == 8) return launch_tc<8, 2>(pl, st);
+    if (pl->stages == 6) return launch_tc<6, 2>(pl, st);
+    return launch_tc<4, 2>(pl, st);
+  }
+  if (pl->stages == 8) return launch_tc<8, 1>(pl, st);
+  if (pl->stages == 6) return launch_tc<6, 1>(pl, st);
+  return launch_tc<4, 1>(pl, st);
 }
 
 extern "C" void ctx_conv2d_tc_plan_destroy(void* plan) { delete (TcPlan*)plan; }

@@ -86,6 +86,26 @@ def test_conv_kernel_vs_torch(case, precision):
         assert torch.allclose(got, want, rtol=1e-2, atol=1e-2)            # bf16 output rounding (8 bits)
 
 
+@pytest.mark.parametrize('case', [(256, 512, 3, 1, 6, 6, 19), (512, 128, 1, 1, 0, 1, 19), (128, 224, 3, 1, 3, 3, 31), (192, 256, 3, 2, 1, 1, 19)],
+                         ids=str)
+def test_conv_cta_pair_mode(case, monkeypatch):
+    """Opt-in cta_group::2 path: one MMA spans the two SMs of a cluster, each CTA stages half of the weight tile."""
+    monkeypatch.setenv('CTX_CONV_CLUSTER', '2')
+    cin, cout, k, stride, pad, dil, H = case
+    g = synth._gen(7, 'pair%s' % (case,))
+    x = torch.randn(5, cin, H, H + 1, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    e = _Scratch('bf16')
+    src, _ = _nhwc_view(x, e.act_dtype, pad_c=64, coff=64)
+    out = e._emit_conv('t', src, w.to(DEV), b.to(DEV), stride, (pad, pad), dil, True)
+    assert e.layers[-1][1] == 'conv_tc'
+    e.go()
+    got = out.tensor().float().cpu().permute(0, 3, 1, 2)
+    want = F.relu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, stride, pad, dil))
+    assert torch.allclose(got, want, rtol=1e-2, atol=1e-2)
+
+
 def test_conv_residual_segments_and_slices():
     """ConvLinear epilogue (+shortcut, ReLU) and a three-segment head conv."""
     g = synth._gen(2, 'segs')
