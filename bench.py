@@ -282,7 +282,57 @@ def main():
 
     for _ in range(args.warmup):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e_serial = timed(step_e2e, args.steps)              # one batch at a time: per-batch latency
+
+    # Streaming form of the same call chain (what a serving / evaluation loop does): the pinned input of batch k+1 is
+    # copied on a side stream while batch k computes, records go back asynchronously; every step still pays its own
+    # H2D and D2H inside the timed region.  No explicit L2 flush here: each step streams > 2 GB of activations through
+    # the 126 MB L2, so nothing survives from one step to the next.
+    copy_stream = torch.cuda.Stream(device=dev)
+    x_bufs = [torch.empty_like(x_dev) for _ in range(2)]
+    out_bufs = [torch.empty_like(out_host).pin_memory() for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(k):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[k & 1])
+            x_bufs[k & 1].copy_(x_host, non_blocking=True)
+            ready[k & 1].record(copy_stream)
+
+    def run_stream(steps):
+        main = torch.cuda.current_stream()
+        for e in consumed:
+            e.record(main)
+        prefetch(0)
+        for k in range(steps):
+            if k + 1 < steps:
+                prefetch(k + 1)
+            main.wait_event(ready[k & 1])
+            pred = net(x_bufs[k & 1])
+            consumed[k & 1].record(main)
+            rec, cnt, _ = post.forward(pred, priors, scale)
+            if world > 1:
+                rec, cnt = shard.gather_records(rec, cnt)
+            if k >= 2:
+                done[k & 1].synchronize()                     # the host consumed batch k-2's records: its buffer is free
+            out_bufs[k & 1].copy_(shard.pack_records(rec, cnt), non_blocking=True)
+            done[k & 1].record(main)
+        main.synchronize()
+
+    run_stream(args.warmup)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    run_stream(args.steps)
+    ev1.record()
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tt)
     e2e_value = n_gpus * B * args.steps / (ms_e2e / 1000.0)
     h2d = x_host.numel() * 4
     d2h = out_host.numel() * 4
@@ -332,8 +382,10 @@ def main():
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps,
-                    'includes': 'H2D input, forward, DetectPost (decode+score+NMS+top-200), %sD2H records'
-                                % ('all-gather, ' if world > 1 else '')},
+                    'serial_ms_per_step': ms_e2e_serial / args.steps,
+                    'includes': 'every step: H2D of the pinned input (side stream, overlapping the previous batch), forward, '
+                                'DetectPost (decode+score+NMS+top-200), %sD2H of the records; serial_ms_per_step is the same '
+                                'chain with one batch in flight' % ('all-gather, ' if world > 1 else '')},
             'gpu_launches': int(launches), 'roofline': roofline}
 
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
