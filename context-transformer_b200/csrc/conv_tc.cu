@@ -119,6 +119,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   __syncthreads();
   if (CL == 2) cluster_sync_all();                          // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, bias staging)
+  // overlapped the tail of the previous kernel in the stream; its outputs are visible after the wait.  Let the next
+  // kernel start its own prologue as soon as SMs drain.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -471,13 +476,15 @@ static int launch_tc(const TcPlan* pl, cudaStream_t st) {
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = pl->smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)pl->p.cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = (unsigned)pl->p.cluster;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pl->p.cluster > 1 ? 1 : 0;
+  cfg.numAttrs = pl->p.cluster > 1 ? 2 : 1;
   CTX_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_kernel<S, CL>, pl->tmap_w, pl->tmap_a, pl->p));
   CTX_LAUNCH_CHECK();
   return CTX_OK;
