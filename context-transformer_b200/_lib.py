@@ -37,7 +37,7 @@ class CtxConvParams(C.Structure):
                 ('in_cstride', C.c_int), ('in_coffset', C.c_int),
                 ('Cout', C.c_int), ('KH', C.c_int), ('KW', C.c_int), ('stride', C.c_int),
                 ('pad_h', C.c_int), ('pad_w', C.c_int), ('dil', C.c_int),
-                ('Ho', C.c_int), ('Wo', C.c_int), ('relu', C.c_int), ('relu_channels', C.c_int), ('in_dtype', C.c_int), ('in_nchw', C.c_int),
+                ('Ho', C.c_int), ('Wo', C.c_int), ('relu', C.c_int), ('pool2', C.c_int), ('relu_channels', C.c_int), ('in_dtype', C.c_int), ('in_nchw', C.c_int),
                 ('in', C.c_void_p), ('weight', C.c_void_p), ('bias', C.c_void_p), ('residual', C.c_void_p),
                 ('res_dtype', C.c_int), ('res_cstride', C.c_int), ('res_coffset', C.c_int),
                 ('nseg', C.c_int), ('seg', CtxOutSeg * 3)]

@@ -271,6 +271,7 @@ softmax_lastdim_kernel(const float* __restrict__ in, float* __restrict__ out, lo
 
 static int validate_conv(const CtxConvParams* p) {
   CTX_REQUIRE(p, "conv: null params");
+  CTX_REQUIRE(!p->pool2, "conv (CUDA-core path): fused pooling is a tensor-core-path feature");
   CTX_REQUIRE(p->in && p->weight, "conv: null tensor pointer");
   CTX_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0 && p->Cin > 0 && p->Cout > 0, "conv: bad dims");
   CTX_REQUIRE(p->KH > 0 && p->KW > 0 && p->stride > 0 && p->dil > 0 && p->pad_h >= 0 && p->pad_w >= 0, "conv: bad geometry");

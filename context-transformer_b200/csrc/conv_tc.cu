@@ -55,6 +55,7 @@ struct TcParams {
   int a_mode, TW, TH, tiles_x, tiles_y;       // TMA mode: output patch TW x TH, tiles per image
   int res_cstride, res_coffset, res_dtype;
   int is_bf16;
+  int pool2;                   // fused MaxPool2d(2,2): TMA mode with TW = 16 (2x2 windows live inside one warp)
   int fast_out;                // single 16-bit segment, 8-channel aligned: 128-bit stores
   int vec_f32;                 // fp32 segments, 4-channel aligned: 128-bit stores
   SegTable segs;
@@ -335,11 +336,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         uint32_t v[32];
         tmem_ld32(tmem_d + (uint32_t)(cb * 32), v);
         tmem_ld_wait();
-        if (!row_ok) continue;
+        if (!row_ok && !p.pool2) continue;
         if (p.fast_out) {
           const CtxOutSeg& sg = p.segs.seg[0];
-          uint16_t* out = reinterpret_cast<uint16_t*>(sg.ptr) + (long long)n_img * sg.img_stride + (long long)pix * sg.pix_stride + sg.ch_offset;
-          const uint16_t* res = p.residual ? reinterpret_cast<const uint16_t*>(p.residual) + m_lin * p.res_cstride + p.res_coffset : nullptr;
+          // pool2: row r of the tile is pixel (r / 16, r % 16) of a 16 x 8 patch, so the 2 x 2 window partners are lanes
+          // ^1 (x) and ^16 (y) of the same warp; the even/even lane stores the pooled pixel
+          long long opix = pix;
+          bool store = row_ok;
+          if (p.pool2) {
+            const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
+            opix = (long long)(oy >> 1) * (p.Wo >> 1) + (ox >> 1);
+            store = row_ok && !(lane & 17);
+          }
+          uint16_t* out = reinterpret_cast<uint16_t*>(sg.ptr) + (long long)n_img * sg.img_stride + opix * sg.pix_stride + sg.ch_offset;
+          const uint16_t* res = (p.residual && row_ok) ? reinterpret_cast<const uint16_t*>(p.residual) + m_lin * p.res_cstride + p.res_coffset : nullptr;
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {
             const int c = c0 + gq * 8;
@@ -359,11 +369,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
               }
-              uint4 o;
-              o.x = pack2(f[0], f[1], bf16); o.y = pack2(f[2], f[3], bf16); o.z = pack2(f[4], f[5], bf16); o.w = pack2(f[6], f[7], bf16);
-              *reinterpret_cast<uint4*>(out + c) = o;
+              if (p.pool2) {                             // max is exact in any precision: pool the fp32 values
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 1));
+                  f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 16));
+                }
+              }
+              if (store) {
+                uint4 o;
+                o.x = pack2(f[0], f[1], bf16); o.y = pack2(f[2], f[3], bf16); o.z = pack2(f[4], f[5], bf16); o.w = pack2(f[6], f[7], bf16);
+                *reinterpret_cast<uint4*>(out + c) = o;
+              }
             }
           }
+        } else if (!row_ok) {
+          continue;
         } else if (p.vec_f32) {
           // fp32 segments whose boundaries, strides and offsets are multiples of 4 channels (the fused heads)
 #pragma unroll
@@ -442,6 +463,8 @@ static int num_sms() {
   return cached;
 }
 
+static bool choose_patch(const CtxConvParams* p, int* tw, int* th);
+
 static int tc_supported(const CtxConvParams* p) {
   if (!p) return 0;
   if (p->in_nchw)       // stem mode: raw fp32 NCHW input, 3x3 / s1 / p1, 16-bit output
@@ -452,6 +475,10 @@ static int tc_supported(const CtxConvParams* p) {
   if (p->Cin % 8 || p->in_cstride % 8 || p->in_coffset % 8) return 0;
   if (p->KH * p->KW > 32) return 0;
   if (((uintptr_t)p->in) % 16 || ((uintptr_t)p->weight) % 16) return 0;
+  if (p->pool2) {                        // fused 2x2 pooling: TMA patch mode, one 16-bit output segment
+    int tw, th;
+    if (!choose_patch(p, &tw, &th) || p->nseg != 1 || p->residual || p->seg[0].dtype != p->in_dtype || p->Cout % 8) return 0;
+  }
   return 1;
 }
 
@@ -459,6 +486,11 @@ static int tc_supported(const CtxConvParams* p) {
 // output map with <= 10 % waste.
 static bool choose_patch(const CtxConvParams* p, int* tw, int* th) {
   if (p->stride != 1 || p->Cin % 64 || p->in_coffset % 64) return false;
+  if (p->pool2) {                       // 2 x 2 windows must sit inside one warp of the epilogue: 16 x 8 patches
+    if ((p->Ho | p->Wo) & 1) return false;
+    *tw = 16; *th = 8;
+    return (long long)cdiv(p->Wo, 16) * 16 * cdiv(p->Ho, 8) * 8 * 100 <= (long long)p->Wo * p->Ho * 112;
+  }
   long long best = -1;
   for (int w = 128; w >= 4; w >>= 1) {
     const int h = 128 / w;
@@ -515,6 +547,7 @@ extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out
   t.Cout = p->Cout; t.KH = p->KH; t.KW = p->KW; t.stride = p->stride; t.pad_h = p->pad_h; t.pad_w = p->pad_w; t.dil = p->dil;
   t.Ho = p->Ho; t.Wo = p->Wo; t.relu = p->relu;
   t.relu_cend = p->relu_channels > 0 ? p->relu_channels : p->Cout;
+  t.pool2 = p->pool2 != 0;
   t.M = p->N * p->Ho * p->Wo;
   t.cin_blocks = (p->Cin + TC_BK - 1) / TC_BK;
   t.nk = p->in_nchw ? 1 : p->KH * p->KW * t.cin_blocks;       // stem: all 27 taps*channels in one 64-wide K-step
@@ -573,6 +606,11 @@ extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out
   if (!rc && t.a_mode == A_TMA)
     rc = encode_nhwc_sw128(&pl->tmap_a, p->in, t.is_bf16 != 0, p->N, p->H, p->W, p->in_cstride, (unsigned)tw, (unsigned)th);
   if (rc) { delete pl; return rc; }
+  if (t.pool2 && !(t.a_mode == A_TMA && t.TW == 16 && t.fast_out)) {
+    delete pl;
+    set_error("conv_tc: fused pooling needs the TMA patch mode and a single 16-bit output segment");
+    return CTX_ERR_UNSUPPORTED;
+  }
   *plan_out = pl;
   return CTX_OK;
 }

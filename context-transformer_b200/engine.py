@@ -127,7 +127,7 @@ class Engine(object):
         return w, b
 
     def _emit_conv(self, name, src, w, b, stride, pad, dil, relu, segs=None, out=None, residual=None, relu_channels=0,
-                   algo_flops=None, in_nchw=False):
+                   algo_flops=None, in_nchw=False, pool2=False):
         """w: folded fp32 [Cout,Cin,KH,KW]; b: fp32 [Cout].  segs: list of (tensor, c_begin, c_end, img_stride,
         pix_stride, ch_offset) for multi-destination epilogues; otherwise writes ``out`` (a View) or a new one."""
         Cout, Cin, KH, KW = w.shape
@@ -140,6 +140,7 @@ class Engine(object):
         p.in_cstride, p.in_coffset = src.cstride, src.coff
         p.Cout, p.KH, p.KW, p.stride, p.pad_h, p.pad_w, p.dil = Cout, KH, KW, stride, ph, pw, dil
         p.Ho, p.Wo, p.relu, p.relu_channels = Ho, Wo, int(relu), int(relu_channels)
+        p.pool2 = int(pool2)
         p.in_dtype = _lib.dtype_code(src.buf.dtype)
         p.in_nchw = int(in_nchw)
         setattr(p, 'in', src.buf.data_ptr())
@@ -153,10 +154,12 @@ class Engine(object):
             p.res_cstride, p.res_coffset = residual.cstride, residual.coff
         result = None
         if segs is None:
+            Hq, Wq = (Ho // 2, Wo // 2) if pool2 else (Ho, Wo)
             if out is None:
-                out = self._new_view(src.N, Ho, Wo, Cout)
-            assert (out.N, out.H, out.W, out.C) == (src.N, Ho, Wo, Cout), name
-            segs = [(out.buf, 0, Cout, Ho * Wo * out.cstride, out.cstride, out.coff)]
+                out = self._new_view(src.N, Hq, Wq, Cout)
+            assert (out.N, out.H, out.W, out.C) == (src.N, Hq, Wq, Cout), name
+            Ho_seg, Wo_seg = Hq, Wq
+            segs = [(out.buf, 0, Cout, Ho_seg * Wo_seg * out.cstride, out.cstride, out.coff)]
             result = out
         p.nseg = len(segs)
         for i, (t, c0, c1, img_stride, pix_stride, ch_off) in enumerate(segs):
@@ -166,6 +169,8 @@ class Engine(object):
             p.seg[i].dtype = _lib.dtype_code(t.dtype)
         flops = algo_flops if algo_flops is not None else 2.0 * src.N * Ho * Wo * Cout * Cin * KH * KW
         use_tc = self.precision != 'fp32' and self.L.ctx_conv2d_tc_supported(C.byref(p)) == 1
+        if pool2 and not use_tc:
+            return None                     # caller falls back to conv + separate pool
         if in_nchw and not use_tc:
             raise _lib.CtxError('stem conv: tensor-core STEM mode unavailable for this geometry')
         if use_tc:
@@ -292,6 +297,17 @@ class Engine(object):
                     if k == 0 and stem_as_gemm:
                         x = self._emit_conv('base.0', x, w, b, 1, (1, 1), 1, relu, in_nchw=True)
                         k += 2 if relu else 1
+                        continue
+                    nxt = k + (2 if relu else 1)
+                    pool = net.base[nxt] if nxt < hi else None
+                    fused = None
+                    if (self.precision != 'fp32' and isinstance(pool, nn.MaxPool2d) and pool.kernel_size == 2 and pool.stride == 2
+                            and pool.padding == 0 and x.H % 2 == 0 and x.W % 2 == 0 and m.stride[0] == 1):
+                        # conv -> ReLU -> MaxPool2d(2,2): the pooled map is all that leaves the conv's epilogue
+                        fused = self._emit_conv('base.%d+pool%d' % (k, nxt), x, w, b, 1, _pair(m.padding), m.dilation[0], relu, pool2=True)
+                    if fused is not None:
+                        x = fused
+                        k = nxt + 1
                         continue
                     x = self._emit_conv('base.%d' % k, x, w, b, m.stride[0], _pair(m.padding), m.dilation[0], relu)
                     k += 2 if relu else 1

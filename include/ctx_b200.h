@@ -96,6 +96,8 @@ typedef struct CtxConvParams {
   int Cout, KH, KW, stride, pad_h, pad_w, dil;
   int Ho, Wo;
   int relu;
+  int pool2;                 /* 1: the epilogue also applies MaxPool2d(2, 2) (vgg 'M', RFB_Net_vgg.py:327-328): the output
+                              * segment describes the POOLED [N, Ho/2, Wo/2, Cout] tensor (tensor-core path only)        */
   int relu_channels;         /* with relu != 0: ReLU only on output channels < relu_channels (0 = all) — fused entry convs */
   int in_dtype;
   int in_nchw;               /* 1: `in` is the raw fp32 NCHW network input [N,3,H,W] (RFBNet.forward x, :210) and this is the

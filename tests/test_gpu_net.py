@@ -106,6 +106,27 @@ def test_conv_cta_pair_mode(case, monkeypatch):
     assert torch.allclose(got, want, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize('case', [(64, 64, 32, 48), (128, 128, 30, 64), (64, 96, 24, 32)], ids=str)
+def test_conv_fused_maxpool(case):
+    """conv3x3 -> ReLU -> MaxPool2d(2,2) with the pooling done in the conv epilogue (vgg 'M' layers)."""
+    cin, cout, H, W = case
+    g = synth._gen(8, 'pool2%s' % (case,))
+    x = torch.randn(3, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    e = _Scratch('bf16')
+    buf = x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)
+    src = View(buf.view(-1), 3, H, W, cin)
+    out = e._emit_conv('t', src, w.to(DEV), b.to(DEV), 1, (1, 1), 1, True, pool2=True)
+    assert out is not None and (out.H, out.W) == (H // 2, W // 2)
+    # maps that 16 x 8 patches tile badly are declined (the engine then emits conv + pool separately)
+    assert e._emit_conv('u', View(buf.view(-1)[:3 * 6 * 10 * cin], 3, 6, 10, cin), w.to(DEV), b.to(DEV), 1, (1, 1), 1, True, pool2=True) is None
+    e.go()
+    got = out.tensor().float().cpu().permute(0, 3, 1, 2)
+    want = F.max_pool2d(F.relu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, 1, 1)), 2, 2)
+    assert torch.allclose(got, want, rtol=1e-2, atol=1e-2)
+
+
 def test_conv_residual_segments_and_slices():
     """ConvLinear epilogue (+shortcut, ReLU) and a three-segment head conv."""
     g = synth._gen(2, 'segs')

@@ -47,7 +47,7 @@ def test_struct_layouts_match_header_sizes():
     # the C structs are plain ints/floats/pointers: ctypes' natural alignment == the compiler's
     assert ctypes.sizeof(_lib.CtxPostParams) == 14 * 4
     assert ctypes.sizeof(_lib.CtxOutSeg) == 40
-    assert ctypes.sizeof(_lib.CtxConvParams) == 19 * 4 + 4 + 4 * 8 + 4 * 4 + 3 * 40
+    assert ctypes.sizeof(_lib.CtxConvParams) == 20 * 4 + 4 * 8 + 4 * 4 + 3 * 40
     assert ctypes.sizeof(_lib.CtxPoolParams) == 10 * 4 + 8 + 8 + 8 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.CtxAttnParams) == 7 * 4 + 4 + 12 * 8 + 8 + 8 + 8 + 8
 
