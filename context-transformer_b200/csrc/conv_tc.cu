@@ -198,12 +198,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       const float* img = reinterpret_cast<const float*>(p.in);
       const bool bf16 = p.is_bf16 != 0;
       uint32_t g = 0;
-      for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++g) {
-        const int m = ((tile / p.n_tiles_n) * CL + rank) * TC_BM + r;
-        float v[28];
+      // the 27 loads of the NEXT tile are issued before the current tile is packed and stored (software pipelining:
+      // with one pixel per thread there is no other memory-level parallelism in this role)
+      auto load_patch = [&](int tile, float (&v)[28]) {
 #pragma unroll
         for (int e = 0; e < 28; ++e) v[e] = 0.f;
-        if (m < p.M) {
+        const int m = ((tile / p.n_tiles_n) * CL + rank) * TC_BM + r;
+        if (tile < p.num_tiles && m < p.M) {
           const int n = m / HW, rem = m - n * HW;
           const int y = rem / p.W, x = rem - y * p.W;
           const float* base = img + (long long)n * 3 * HW;
@@ -218,6 +219,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
               }
             }
         }
+      };
+      float vnext[28];
+      load_patch(group0, vnext);
+      for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++g) {
+        float v[28];
+#pragma unroll
+        for (int e = 0; e < 28; ++e) v[e] = vnext[e];
+        load_patch(tile + ngroups, vnext);
         const uint32_t s = g % S;
         mbar_wait(empty0 + 8 * s, ((g / S) & 1) ^ 1);
         const uint32_t row = sA + s * TC_A_STAGE + r * 128;
