@@ -179,6 +179,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp16', 'fp32'])
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--size', type=int, default=SIZE, choices=[300, 512], help='extra (non-contract) workload: 512 uses the ft head (BASELINE config 3)')
+    ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='images per GPU (contract default 32)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='plain launches instead of one CUDA-graph replay')
     ap.add_argument('--quick', action='store_true', help='device-resident forward only (for ncu): no e2e, per-op or CPU legs')
@@ -205,17 +207,23 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     n_gpus = world
 
-    margs = types.SimpleNamespace(method='ours', phase=2, setting='transfer', precision=args.precision)
-    net = ctx.build_net(margs, SIZE, NUM_SRC_CLASSES)
+    size = args.size
+    if size == 512:      # the Context-Transformer head is undefined upstream at 512: plain fine-tune head, 20 classes
+        margs = types.SimpleNamespace(method='ft', phase=2, setting='transfer', precision=args.precision)
+        net = ctx.build_net(margs, 512, 20)
+    else:
+        margs = types.SimpleNamespace(method='ours', phase=2, setting='transfer', precision=args.precision)
+        net = ctx.build_net(margs, SIZE, NUM_SRC_CLASSES)
     net.load_state_dict(bench_state(net))
     net.eval()
     net.device = str(dev)
     net.use_cuda_graph = not args.no_graph
     net.to(dev)
-    priors = ctx.PriorBox(ctx.VOC_300).forward().to(dev)
-    post = ctx.DetectPost(21, 0, ctx.VOC_300)
-    B = BATCH_PER_GPU
-    x_host = synth.seeded_input(B, SIZE, seed=rank).pin_memory()
+    cfg = ctx.VOC_512 if size == 512 else ctx.VOC_300
+    priors = ctx.PriorBox(cfg).forward().to(dev)
+    post = ctx.DetectPost(21, 0, cfg)
+    B = args.batch
+    x_host = synth.seeded_input(B, size, seed=rank).pin_memory()
     x_dev = x_host.to(dev)
     eng = net.engine(B)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -377,7 +385,7 @@ def main():
     line = {'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': n_gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'fp16': 'f16', 'fp32': 'f32'}[args.precision], 'data': 'synthetic',
-            'config': workload_config(args.precision, n_gpus, {'detections_per_batch_e2e': n_det[0],
+            'config': workload_config(args.precision, n_gpus, {'detections_per_batch_e2e': n_det[0], 'image_size': size, 'batch_per_gpu': B,
                                                                 'cuda_graph': bool(eng.graph_ready)}),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,

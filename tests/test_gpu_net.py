@@ -299,6 +299,41 @@ def test_full_forward_16bit_tolerance(golden, precision):
     assert agree > (0.97 if precision == 'fp16' else 0.90)
 
 
+def test_512_fp16_full_detect_soft_nms():
+    """BASELINE config 3: RFB_Net_vgg 512x512, fp16, full Detect with per-class soft-NMS (ft head; 'ours' is undefined
+    upstream at 512).  Forward against the fp32 torch oracle with the fp16 bars, post-processing against the oracle run
+    on the SAME forward outputs (index-exact)."""
+    from oracle import c_oracle, np_oracle
+    net = _build(NET_CASES[3], 'fp16')                         # ft_512
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    x = synth.seeded_input(2, 512, seed=4)
+    pred = net(x.cuda())
+    with torch.no_grad():
+        want = torch_net.forward(sd, x, 512, 20, 'ft', 2, 'transfer')
+    for got, w, tol in zip(pred, want, (5e-2, 3e-2, 3e-2)):
+        assert (got.cpu() - w).abs().max() < tol
+    priors = ctx.PriorBox(ctx.VOC_512).forward()
+    scale = np.array([512, 512, 512, 512], np.float32)
+    post = ctx.DetectPost(21, 0, ctx.VOC_512, score_thresh=0.2, nms_thresh=0.3, nms_method=1, max_per_image=0, max_out=8192)
+    rec, cnt, _ = post.forward(pred, priors.cuda(), scale)
+    gb, gs = ctx.Detect(21, 0, ctx.VOC_512).forward(pred, priors.cuda())
+    boxes, scores = gb.cpu().numpy(), gs.cpu().numpy()
+    for b in range(2):
+        rows = []
+        bx = (boxes[b] * scale).astype(np.float32)
+        for j in range(1, 21):
+            inds = np.where(scores[b][:, j] > np.float32(0.2))[0]
+            if len(inds) == 0:
+                continue
+            c_dets = np.hstack((bx[inds], scores[b][inds, j][:, None])).astype(np.float32)
+            out, n = c_oracle.cpu_soft_nms(c_dets, 0.5, 0.3, 0.001, 1)
+            rows.append(np.hstack([out, np.full((n, 1), j, np.float32)]))
+        wrec = np.vstack(rows) if rows else np.zeros((0, 6), np.float32)
+        n = int(cnt[b])
+        assert n == len(wrec) and n > 0
+        assert np.array_equal(rec[b, :n].cpu().numpy(), wrec)
+
+
 def test_end_to_end_detections_match_oracle():
     """test.py:130-161 in one go: forward -> DetectPost, against oracle post-processing of the SAME forward."""
     from oracle import c_oracle, np_oracle
