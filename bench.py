@@ -359,7 +359,8 @@ def main():
             b.record()
             b.synchronize()
             ts.append(a.elapsed_time(b))
-        per_op.append({'op': name, 'kind': kind, 'gflop': flops / 1e9, 'ms': min(ts), 'shape': list(shape)})
+        per_op.append({'op': name, 'kind': kind, 'gflop': flops / 1e9, 'ms': min(ts), 'shape': list(shape),
+                       'tile': eng.conv_config(i) if kind == 'conv_tc' else None})
     conv_ops = [o for o in per_op if o['kind'].startswith('conv')]
     conv_ms = sum(o['ms'] for o in conv_ops)
     conv_flops = sum(o['gflop'] for o in conv_ops) * 1e9

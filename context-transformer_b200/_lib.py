@@ -78,6 +78,8 @@ SIGNATURES = {
     'ctx_conv2d_simt': (_I, [C.POINTER(CtxConvParams), _P]),
     'ctx_conv2d_tc_supported': (_I, [C.POINTER(CtxConvParams)]),
     'ctx_conv2d_tc_plan_create': (_I, [C.POINTER(CtxConvParams), C.POINTER(_P)]),
+    'ctx_conv2d_tc_plan_create_tuned': (_I, [C.POINTER(CtxConvParams), _I, _I, _I, C.POINTER(_P)]),
+    'ctx_conv2d_tc_plan_info': (_I, [_P, C.POINTER(_I)]),
     'ctx_conv2d_tc_plan_run': (_I, [_P, _P]),
     'ctx_conv2d_tc_plan_destroy': (None, [_P]),
     'ctx_maxpool2d_nhwc': (_I, [C.POINTER(CtxPoolParams), _P]),
@@ -95,6 +97,9 @@ SIGNATURES = {
     'ctx_prog_add_nchw_to_nhwc': (_I, [_P, _P, _P, _I, _I, _I, _I, _I]),
     'ctx_prog_add_attention': (_I, [_P, C.POINTER(CtxAttnParams)]),
     'ctx_prog_add_softmax': (_I, [_P, _P, _P, _LL, _I]),
+    'ctx_prog_set_lane': (_I, [_P, _I, C.c_uint]),
+    'ctx_prog_autotune': (_I, [_P, _P, _I]),
+    'ctx_prog_conv_config': (_I, [_P, _I, C.POINTER(_I)]),
     'ctx_prog_num_ops': (_I, [_P]),
     'ctx_prog_run': (_I, [_P, _P]),
     'ctx_prog_instantiate_graph': (_I, [_P, _P]),

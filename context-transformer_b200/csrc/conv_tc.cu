@@ -472,7 +472,7 @@ static int num_sms() {
   return cached;
 }
 
-static bool choose_patch(const CtxConvParams* p, int* tw, int* th);
+static bool choose_patch(const CtxConvParams* p, int* tw, int* th, int max_waste_pct = 10);
 
 static int tc_supported(const CtxConvParams* p) {
   if (!p) return 0;
@@ -493,8 +493,8 @@ static int tc_supported(const CtxConvParams* p) {
 
 // TMA activation mode: stride-1 conv, whole 64-channel K-steps, and a TW x TH = 128 pixel patch that tiles the
 // output map with <= 10 % waste.
-static bool choose_patch(const CtxConvParams* p, int* tw, int* th) {
-  if (p->stride != 1 || p->Cin % 64 || p->in_coffset % 64) return false;
+static bool choose_patch(const CtxConvParams* p, int* tw, int* th, int max_waste_pct) {
+  if (p->stride != 1 || p->Cin % 64 || p->in_coffset % 64 || p->in_cstride % 8) return false;
   if (p->pool2) {                       // 2 x 2 windows must sit inside one warp of the epilogue: 16 x 8 patches
     if ((p->Ho | p->Wo) & 1) return false;
     *tw = 16; *th = 8;
@@ -506,7 +506,7 @@ static bool choose_patch(const CtxConvParams* p, int* tw, int* th) {
     const long long cover = (long long)cdiv(p->Wo, w) * w * cdiv(p->Ho, h) * h;
     if (best < 0 || cover < best) { best = cover; *tw = w; *th = h; }
   }
-  return best * 10 <= (long long)p->Wo * p->Ho * 11;
+  return best * 100 <= (long long)p->Wo * p->Ho * (100 + max_waste_pct);
 }
 
 template <int S, int CL>
@@ -519,7 +519,8 @@ static int launch_tc(const TcPlan* pl, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const int pdl = [] { const char* e = getenv("CTX_CONV_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+  attr[0].val.programmaticStreamSerializationAllowed = pdl;
   attr[1].id = cudaLaunchAttributeClusterDimension;
   attr[1].val.clusterDim.x = (unsigned)pl->p.cluster;
   attr[1].val.clusterDim.y = 1;
@@ -537,7 +538,10 @@ using namespace ctx;
 
 extern "C" int ctx_conv2d_tc_supported(const CtxConvParams* p) { return tc_supported(p); }
 
-extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out) {
+// tune_n: number of N tiles (0 = ceil(Cout / 256)); tune_cluster: 1 / 2 CTAs per MMA (0 = default); tune_amode: -1 = rule
+// of thumb (TMA patches when they tile the map with <= 10 % waste), 0 = im2col gather, 1 = TMA patches whenever the
+// geometry allows them (any waste).  Results are bit-identical across all settings: only the tiling changes.
+static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int tune_amode, void** plan_out) {
   CTX_REQUIRE(p && plan_out, "ctx_conv2d_tc_plan_create: null argument");
   *plan_out = nullptr;
   if (!tc_supported(p)) { set_error("ctx_conv2d_tc: geometry / dtype not supported by the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
@@ -585,11 +589,14 @@ extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out
   }
 
   // N tile: split Cout evenly over ceil(Cout / 256) tiles, rounded up to the UMMA granularity of 16
-  t.n_tiles_n = cdiv(p->Cout, 256);
+  t.n_tiles_n = std::max(cdiv(p->Cout, 256), std::min(tune_n, cdiv(p->Cout, 16)));
   t.bn = (cdiv(p->Cout, t.n_tiles_n) + 15) / 16 * 16;
+  t.n_tiles_n = cdiv(p->Cout, t.bn);
 
   int tw = 0, th = 0;
-  t.a_mode = p->in_nchw ? A_STEM : (choose_patch(p, &tw, &th) ? A_TMA : A_GATHER);
+  if (p->in_nchw) t.a_mode = A_STEM;
+  else if (tune_amode == 0 && !p->pool2) t.a_mode = A_GATHER;
+  else t.a_mode = choose_patch(p, &tw, &th, tune_amode == 1 ? 1000 : 10) ? A_TMA : A_GATHER;
   t.TW = tw; t.TH = th;
   t.tiles_x = t.a_mode == A_TMA ? cdiv(p->Wo, tw) : 0;
   t.tiles_y = t.a_mode == A_TMA ? cdiv(p->Ho, th) : 0;
@@ -600,7 +607,8 @@ extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out
     // tile) are implemented and parity-tested, but on this network they measure within 2 % of the single-CTA path
     // (profiles/README.md), so they stay opt-in: CTX_CONV_CLUSTER=2.
     const char* e = getenv("CTX_CONV_CLUSTER");
-    t.cluster = (e && e[0] == '2' && m_tiles >= 2 && t.bn % 32 == 0 && t.bn >= 128) ? 2 : 1;
+    const bool want2 = tune_cluster ? tune_cluster == 2 : (e && e[0] == '2');
+    t.cluster = (want2 && m_tiles >= 2 && t.bn % 32 == 0 && t.bn >= 128) ? 2 : 1;
   }
   t.num_tiles = cdiv(m_tiles, t.cluster) * t.n_tiles_n;
   const int stage_bytes = TC_A_STAGE + (t.bn / t.cluster) * TC_BK * 2;
@@ -621,6 +629,19 @@ extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out
     return CTX_ERR_UNSUPPORTED;
   }
   *plan_out = pl;
+  return CTX_OK;
+}
+
+extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out) { return plan_create(p, 0, 0, -1, plan_out); }
+
+extern "C" int ctx_conv2d_tc_plan_create_tuned(const CtxConvParams* p, int n_tiles_n, int cluster, int a_mode, void** plan_out) {
+  return plan_create(p, n_tiles_n, cluster, a_mode, plan_out);
+}
+
+extern "C" int ctx_conv2d_tc_plan_info(void* plan, int* info6) {
+  CTX_REQUIRE(plan && info6, "ctx_conv2d_tc_plan_info: null argument");
+  const TcPlan* pl = (const TcPlan*)plan;
+  info6[0] = pl->p.bn; info6[1] = pl->p.n_tiles_n; info6[2] = pl->p.cluster; info6[3] = pl->p.a_mode; info6[4] = pl->stages; info6[5] = pl->grid;
   return CTX_OK;
 }
 

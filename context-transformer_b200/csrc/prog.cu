@@ -7,6 +7,7 @@
 // so that a step is a single cudaGraphLaunch (the late-pyramid layers are launch-latency bound).
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <vector>
 
 namespace ctx {
@@ -19,8 +20,12 @@ int attention_simt_launch(const CtxAttnParams* p, cudaStream_t st);
 
 enum OpKind { OP_CONV_SIMT, OP_CONV_TC, OP_POOL, OP_NCHW2NHWC, OP_PATCH27, OP_ATTN, OP_SOFTMAX };
 
+constexpr int MAX_LANES = 8;
+
 struct Op {
   OpKind kind;
+  int lane = 0;                  // stream the op is captured on (graph mode); serial replay ignores lanes
+  unsigned wait_mask = 0;        // lanes whose work issued so far must finish before this op starts
   CtxConvParams conv;
   CtxPoolParams pool;
   CtxAttnParams attn;
@@ -34,7 +39,18 @@ struct Prog {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   int launches_per_run = 0;      // kernels inside the captured graph (for ctx_launch_count)
+  int cur_lane = 0;
+  unsigned pending_wait = 0;
+  cudaStream_t lane_stream[MAX_LANES] = {};
+  std::vector<cudaEvent_t> events;
 };
+
+static void push_op(Prog* pr, Op& op) {
+  op.lane = pr->cur_lane;
+  op.wait_mask = pr->pending_wait & ~(1u << pr->cur_lane);
+  pr->pending_wait = 0;
+  pr->ops.push_back(op);
+}
 
 static int run_op(Op& op, cudaStream_t st) {
   switch (op.kind) {
@@ -70,6 +86,8 @@ extern "C" void ctx_prog_destroy(void* prog) {
   drop_graph(pr);
   for (Op& op : pr->ops)
     if (op.tc_plan) ctx_conv2d_tc_plan_destroy(op.tc_plan);
+  for (cudaEvent_t e : pr->events) cudaEventDestroy(e);
+  for (cudaStream_t s : pr->lane_stream) if (s) cudaStreamDestroy(s);
   delete pr;
 }
 
@@ -82,7 +100,7 @@ extern "C" int ctx_prog_add_conv_simt(void* prog, const CtxConvParams* p) {
   PROG_OR_FAIL(prog);
   CTX_REQUIRE(p, "ctx_prog_add_conv_simt: null params");
   Op op{}; op.kind = OP_CONV_SIMT; op.conv = *p;
-  pr->ops.push_back(op);
+  push_op(pr, op);
   return CTX_OK;
 }
 
@@ -92,7 +110,7 @@ extern "C" int ctx_prog_add_conv_tc(void* prog, const CtxConvParams* p) {
   Op op{}; op.kind = OP_CONV_TC; op.conv = *p;
   int rc = ctx_conv2d_tc_plan_create(p, &op.tc_plan);
   if (rc) return rc;
-  pr->ops.push_back(op);
+  push_op(pr, op);
   return CTX_OK;
 }
 
@@ -100,7 +118,7 @@ extern "C" int ctx_prog_add_pool(void* prog, const CtxPoolParams* p) {
   PROG_OR_FAIL(prog);
   CTX_REQUIRE(p, "ctx_prog_add_pool: null params");
   Op op{}; op.kind = OP_POOL; op.pool = *p;
-  pr->ops.push_back(op);
+  push_op(pr, op);
   return CTX_OK;
 }
 
@@ -108,7 +126,7 @@ extern "C" int ctx_prog_add_nchw_to_nhwc(void* prog, const float* in, void* out,
   PROG_OR_FAIL(prog);
   Op op{}; op.kind = OP_NCHW2NHWC;
   op.cvt.in = in; op.cvt.out = out; op.cvt.N = N; op.cvt.C = C; op.cvt.H = H; op.cvt.W = W; op.cvt.dtype = out_dtype;
-  pr->ops.push_back(op);
+  push_op(pr, op);
   return CTX_OK;
 }
 
@@ -116,7 +134,7 @@ extern "C" int ctx_prog_add_nchw_to_patch27(void* prog, const float* in, void* o
   PROG_OR_FAIL(prog);
   Op op{}; op.kind = OP_PATCH27;
   op.cvt.in = in; op.cvt.out = out; op.cvt.N = N; op.cvt.C = 3; op.cvt.H = H; op.cvt.W = W; op.cvt.dtype = out_dtype;
-  pr->ops.push_back(op);
+  push_op(pr, op);
   return CTX_OK;
 }
 
@@ -124,15 +142,105 @@ extern "C" int ctx_prog_add_attention(void* prog, const CtxAttnParams* p) {
   PROG_OR_FAIL(prog);
   CTX_REQUIRE(p, "ctx_prog_add_attention: null params");
   Op op{}; op.kind = OP_ATTN; op.attn = *p;
-  pr->ops.push_back(op);
+  push_op(pr, op);
   return CTX_OK;
 }
 
 extern "C" int ctx_prog_add_softmax(void* prog, const float* in, float* out, long long rows, int cols) {
   PROG_OR_FAIL(prog);
   Op op{}; op.kind = OP_SOFTMAX; op.sm.in = in; op.sm.out = out; op.sm.rows = rows; op.sm.cols = cols;
-  pr->ops.push_back(op);
+  push_op(pr, op);
   return CTX_OK;
+}
+
+extern "C" int ctx_prog_set_lane(void* prog, int lane, unsigned wait_mask) {
+  CTX_REQUIRE(prog, "ctx_prog_set_lane: null handle");
+  CTX_REQUIRE(lane >= 0 && lane < MAX_LANES && (wait_mask >> MAX_LANES) == 0, "ctx_prog_set_lane: lane %d / mask %u out of range", lane, wait_mask);
+  Prog* pr = (Prog*)prog;
+  pr->cur_lane = lane;
+  pr->pending_wait |= wait_mask;
+  return CTX_OK;
+}
+
+extern "C" int ctx_prog_conv_config(void* prog, int op_index, int* info6) {
+  CTX_REQUIRE(prog && info6, "ctx_prog_conv_config: null argument");
+  Prog* pr = (Prog*)prog;
+  CTX_REQUIRE(op_index >= 0 && op_index < (int)pr->ops.size(), "ctx_prog_conv_config: bad op index %d", op_index);
+  for (int i = 0; i < 6; ++i) info6[i] = 0;
+  if (pr->ops[op_index].kind != OP_CONV_TC) return CTX_OK;
+  return ctx_conv2d_tc_plan_info(pr->ops[op_index].tc_plan, info6);
+}
+
+// Per-layer tile selection by measurement: every tensor-core conv is timed in place (its real buffers; an op only ever
+// reads its inputs and rewrites its own outputs, so running it out of order is harmless) under each candidate tiling —
+// N-tile count (wave quantisation on 148 SMs vs. operand reuse), CTA pairs, TMA patches vs. im2col gather — and the
+// fastest plan is kept.  All candidates produce bit-identical outputs.
+extern "C" int ctx_prog_autotune(void* prog, void* stream, int reps) {
+  PROG_OR_FAIL(prog);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (reps < 1) reps = 3;
+  cudaEvent_t e0, e1;
+  CTX_CUDA_TRY(cudaEventCreate(&e0));
+  CTX_CUDA_TRY(cudaEventCreate(&e1));
+  int rc = CTX_OK;
+  // optional trace of every measurement (development aid): CTX_AUTOTUNE_LOG=<path>
+  const char* log_path = getenv("CTX_AUTOTUNE_LOG");
+  FILE* log = log_path && log_path[0] ? fopen(log_path, "a") : nullptr;
+  int op_index = -1;
+  auto trace = [&](const Op& op, const int* info, float ms, const char* tag) {
+    if (!log) return;
+    fprintf(log, "op %d  %dx%dx%d->%d k%dx%d s%d d%d  bn %d ntn %d cl %d amode %d stages %d grid %d  %.2f us %s\n", op_index, op.conv.H, op.conv.W,
+            op.conv.Cin, op.conv.Cout, op.conv.KH, op.conv.KW, op.conv.stride, op.conv.dil, info[0], info[1], info[2], info[3], info[4], info[5],
+            1000.f * ms / reps, tag);
+  };
+  auto time_plan = [&](void* plan, float* ms) -> int {
+    int r = ctx_conv2d_tc_plan_run(plan, st);                  // warm-up (descriptor fetch, L2)
+    if (r) return r;
+    if (cudaEventRecord(e0, st) != cudaSuccess) return CTX_ERR_CUDA;
+    for (int i = 0; i < reps && !r; ++i) r = ctx_conv2d_tc_plan_run(plan, st);
+    if (r) return r;
+    if (cudaEventRecord(e1, st) != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess) { set_error("autotune: timing failed: %s", cudaGetErrorString(cudaGetLastError())); return CTX_ERR_CUDA; }
+    cudaEventElapsedTime(ms, e0, e1);
+    return CTX_OK;
+  };
+  for (Op& op : pr->ops) {
+    ++op_index;
+    if (op.kind != OP_CONV_TC || op.conv.in_nchw) continue;
+    float best_ms = 0.f;
+    if ((rc = time_plan(op.tc_plan, &best_ms))) break;
+    int base[6];
+    ctx_conv2d_tc_plan_info(op.tc_plan, base);
+    trace(op, base, best_ms, "default");
+    const int n0 = base[1];
+    std::vector<long> seen;                                   // (tile width, cluster, A mode) already measured
+    auto key_of = [](const int* info) { return (long)info[0] * 100 + info[2] * 10 + info[3]; };
+    seen.push_back(key_of(base));
+    for (int dn = 0; dn < 6 && !rc; ++dn) {
+      const int n = dn < 4 ? n0 + dn : n0 * (dn == 4 ? 2 : 3);
+      for (int amode = -1; amode <= 1 && !rc; ++amode)
+        for (int cl = 1; cl <= 2 && !rc; ++cl) {
+          void* cand = nullptr;
+          if (ctx_conv2d_tc_plan_create_tuned(&op.conv, n, cl, amode, &cand) != CTX_OK) continue;
+          int info[6];
+          ctx_conv2d_tc_plan_info(cand, info);
+          const long key = key_of(info);
+          bool dup = info[0] < 32;
+          for (long k : seen) dup = dup || k == key;
+          if (dup) { ctx_conv2d_tc_plan_destroy(cand); continue; }
+          seen.push_back(key);
+          float ms = 0.f;
+          rc = time_plan(cand, &ms);
+          if (!rc) trace(op, info, ms, ms < best_ms * 0.97f ? "better" : "");
+          if (!rc && ms < best_ms * 0.97f) { ctx_conv2d_tc_plan_destroy(op.tc_plan); op.tc_plan = cand; best_ms = ms; }
+          else ctx_conv2d_tc_plan_destroy(cand);
+        }
+    }
+    if (rc) break;
+  }
+  if (log) fclose(log);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
 }
 
 extern "C" int ctx_prog_num_ops(void* prog) { return prog ? (int)((Prog*)prog)->ops.size() : 0; }
@@ -154,13 +262,48 @@ extern "C" int ctx_prog_instantiate_graph(void* prog, void* stream) {
   drop_graph(pr);
   cudaStream_t st = (cudaStream_t)stream;
   CTX_REQUIRE(st != nullptr, "ctx_prog_instantiate_graph: needs a non-default stream to capture on");
+  // Lanes: ops the host put on lane L > 0 (independent RFB branches, the per-level heads) are captured on their own
+  // stream, forked from / joined to lane 0 with events, so the graph is a DAG and small kernels run side by side.
+  for (Op& op : pr->ops)
+    if (op.lane > 0 && !pr->lane_stream[op.lane]) CTX_CUDA_TRY(cudaStreamCreateWithFlags(&pr->lane_stream[op.lane], cudaStreamNonBlocking));
+  size_t ev_used = 0;
+  auto next_event = [&](cudaEvent_t* ev) -> cudaError_t {
+    if (ev_used == pr->events.size()) {
+      cudaEvent_t e;
+      cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      if (rc != cudaSuccess) return rc;
+      pr->events.push_back(e);
+    }
+    *ev = pr->events[ev_used++];
+    return cudaSuccess;
+  };
   CTX_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
   const unsigned long long before = ctx_launch_count();
   int rc = CTX_OK;
-  for (Op& op : pr->ops) { rc = run_op(op, st); if (rc) break; }
+  cudaError_t ce = cudaSuccess;
+  unsigned active = 1u;                              // lanes that are part of the capture and not yet joined back
+  auto lane_st = [&](int lane) { return lane == 0 ? st : pr->lane_stream[lane]; };
+  auto make_wait = [&](int waiter, int signal) {
+    cudaEvent_t ev;
+    if (ce == cudaSuccess) ce = next_event(&ev);
+    if (ce == cudaSuccess) ce = cudaEventRecord(ev, lane_st(signal));
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(lane_st(waiter), ev, 0);
+  };
+  for (Op& op : pr->ops) {
+    unsigned mask = op.wait_mask & active;
+    if (!(active & (1u << op.lane))) { mask |= 1u; active |= 1u << op.lane; }     // a lane enters the capture by waiting on lane 0
+    for (int l = 0; l < MAX_LANES; ++l)
+      if ((mask >> l) & 1u) make_wait(op.lane, l);
+    if (ce != cudaSuccess) break;
+    rc = run_op(op, lane_st(op.lane));
+    if (rc) break;
+  }
+  for (int l = 1; l < MAX_LANES && ce == cudaSuccess && !rc; ++l)
+    if ((active >> l) & 1u) make_wait(0, l);         // every forked lane joins lane 0 before the capture ends
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(st, &g);
   if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+  if (ce != cudaSuccess) { if (g) cudaGraphDestroy(g); set_error("ctx_prog_instantiate_graph: lane fork/join failed: %s", cudaGetErrorString(ce)); return CTX_ERR_CUDA; }
   if (e != cudaSuccess) { set_error("ctx_prog_instantiate_graph: capture failed: %s", cudaGetErrorString(e)); return CTX_ERR_CUDA; }
   pr->graph = g;
   pr->launches_per_run = (int)(ctx_launch_count() - before);

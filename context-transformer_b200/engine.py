@@ -18,6 +18,7 @@ and records all of it in a ``ctx_prog`` (csrc/prog.cu), optionally captured into
 """
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -82,6 +83,9 @@ class Engine(object):
         _lib.check(self.L.ctx_prog_create(C.byref(self.prog)), 'ctx_prog_create')
         self.graph_ready = False
         self.use_graph = use_graph
+        # independent chains (RFB branches, per-level heads) on their own graph lanes; CTX_LANES=0 keeps one chain
+        self.use_lanes = os.environ.get('CTX_LANES', '1') != '0'
+        self.autotune = os.environ.get('CTX_AUTOTUNE', '1') != '0' and precision != 'fp32'
         self.stream = torch.cuda.Stream(device=self.dev)
         with torch.cuda.device(self.dev), torch.no_grad():
             self._compile(net)
@@ -106,6 +110,15 @@ class Engine(object):
         t = torch.empty(*shape, dtype=dtype or self.act_dtype, device=self.dev)
         self.keep.append(t)
         return t
+
+    def _lane(self, lane, wait=()):
+        """Ops emitted from here on belong to ``lane``; the next one first waits for the lanes in ``wait``."""
+        mask = 0
+        for l in wait:
+            mask |= 1 << l
+        if not self.use_lanes:
+            lane, mask = 0, 0
+        _lib.check(self.L.ctx_prog_set_lane(self.prog, lane, mask), 'ctx_prog_set_lane')
 
     def _new_view(self, N, H, W, C):
         return View(self._alloc(N * H * W * C), N, H, W, C)
@@ -253,8 +266,10 @@ class Engine(object):
                 entry_out[key] = fused.slice(off, bc.out_channels)
                 off += bc.out_channels
 
+        # branch bi runs on lane bi (the block input / fused entry conv was produced on lane 0)
         off = 0
         for bi, br in enumerate(branches):
+            self._lane(min(bi, 3), wait=(0,))
             t = src
             for li, layer in enumerate(br):
                 last = li == len(br) - 1
@@ -264,6 +279,7 @@ class Engine(object):
                 t = self._basic_conv('%s.branch%d.%d' % (name, bi, li), layer, t,
                                      out=cat.slice(off, layer.out_channels) if last else None)
             off += br[-1].out_channels
+        self._lane(0, wait=tuple(range(1, min(len(branches), 4))))
         short = entry_out['shortcut'] if 'shortcut' in entry_out else self._basic_conv(name + '.shortcut', m.shortcut, src)
         # relu(ConvLinear(cat) * scale + short): scale folds into the weights, the add + ReLU into the epilogue
         return self._basic_conv(name + '.ConvLinear', m.ConvLinear, cat, residual=short, relu=True, scale=float(m.scale))
@@ -320,35 +336,31 @@ class Engine(object):
                     raise _lib.CtxError('base.%d: unsupported module %s' % (k, type(m).__name__))
             return x
 
-        x = run_base(0, SOURCE_SPLIT, x)
-        sources.append(self._rfb('Norm', net.Norm, x))
-        x = run_base(SOURCE_SPLIT, len(net.base), x)
-        for k, m in enumerate(net.extras):
-            if isinstance(m, _RFBBlock):
-                x = self._rfb('extras.%d' % k, m, x)
-            elif isinstance(m, BasicConv):
-                x = self._basic_conv('extras.%d' % k, m, x)
-            else:
-                raise _lib.CtxError('extras.%d: unsupported module %s' % (k, type(m).__name__))
-            if k < net.indicator or k % 2 == 0:
-                sources.append(x)
-
-        # ---- heads: one conv per level, three output segments -----------------------------------
+        # ---- heads: one conv per level, three output segments, emitted as soon as the level's source exists and put
+        # on lane 5 so that they overlap the rest of the trunk (they only meet again at the Context-Transformer) ------
+        from .config import MBOX, VOC_300, VOC_512
+        fmaps = (VOC_512 if S == 512 else VOC_300)['feature_maps']
         Csrc = net.num_classes
         anchors = [l.out_channels // 4 for l in net.loc]
-        level_p = [s.H * s.W * a for s, a in zip(sources, anchors)]
+        assert anchors == MBOX[S], (anchors, MBOX[S])
+        level_p = [f * f * a for f, a in zip(fmaps, anchors)]
         P = sum(level_p)
         self.num_priors = P
         ours = net.ours
-        if ours and len(sources) > len(CONF_POOL):
+        if ours and len(fmaps) > len(CONF_POOL):
             raise IndexError('Context-Transformer pooling is defined for 6 pyramid levels only (size 300); size %d '
-                             'has %d (undefined upstream as well, RFB_Net_vgg.py:235-243)' % (S, len(sources)))
+                             'has %d (undefined upstream as well, RFB_Net_vgg.py:235-243)' % (S, len(fmaps)))
         self.loc = self._alloc(B, P, 4, dtype=torch.float32)
         self.conf_raw = self._alloc(B, P, Csrc, dtype=torch.float32)
         self.obj_raw = self._alloc(B, P, 2, dtype=torch.float32)
-        poff = 0
         pooled_shapes = []
-        for i, (s, a) in enumerate(zip(sources, anchors)):
+
+        def add_source(s):
+            i = len(sources)
+            sources.append(s)
+            assert (s.H, s.W) == (fmaps[i], fmaps[i]), (i, s.H, s.W, fmaps[i])
+            a = anchors[i]
+            poff = sum(level_p[:i])
             wl, bl = self._fold(net.loc[i], None)
             wc, bc = self._fold(net.conf[i], None)
             wo, bo = self._fold(net.obj[i], None)
@@ -358,11 +370,27 @@ class Engine(object):
             segs = [(self.loc.view(-1)[poff * 4:], 0, c1, P * 4, a * 4, 0),
                     (self.conf_raw.view(-1)[poff * Csrc:], c1, c2, P * Csrc, a * Csrc, 0),
                     (self.obj_raw.view(-1)[poff * 2:], c2, c3, P * 2, a * 2, 0)]
+            self._lane(5, wait=(0,))
             self._emit_conv('head.%d' % i, s, w, b, 1, (1, 1), 1, False, segs=segs)
+            self._lane(0)
             if ours:
                 k = CONF_POOL[i]
                 pooled_shapes.append((_pool_out(s.H, k, k, 0, True), _pool_out(s.W, k, k, 0, True), a))
-            poff += level_p[i]
+
+        x = run_base(0, SOURCE_SPLIT, x)
+        add_source(self._rfb('Norm', net.Norm, x))
+        x = run_base(SOURCE_SPLIT, len(net.base), x)
+        for k, m in enumerate(net.extras):
+            if isinstance(m, _RFBBlock):
+                x = self._rfb('extras.%d' % k, m, x)
+            elif isinstance(m, BasicConv):
+                x = self._basic_conv('extras.%d' % k, m, x)
+            else:
+                raise _lib.CtxError('extras.%d: unsupported module %s' % (k, type(m).__name__))
+            if k < net.indicator or k % 2 == 0:
+                add_source(x)
+        assert len(sources) == len(fmaps)
+        self._lane(0, wait=(5,))
         self.head_end_op = self.L.ctx_prog_num_ops(self.prog)
 
         # ---- Context-Transformer (phase 2, method 'ours') ----------------------------------------
@@ -413,6 +441,10 @@ class Engine(object):
                    'ctx_prog_add_softmax')
         self.layers.append(('obj.softmax', 'softmax', 0.0, (B * P, 2)))
         self.num_ops = self.L.ctx_prog_num_ops(self.prog)
+        if self.autotune:
+            # per-layer tiling picked by timing each candidate on this GPU (bit-identical outputs)
+            torch.cuda.synchronize(self.dev)
+            _lib.check(self.L.ctx_prog_autotune(self.prog, C.c_void_p(self.stream.cuda_stream), 4), 'ctx_prog_autotune')
         self.conv_flops = sum(l[2] for l in self.layers if l[1].startswith('conv'))
 
     def _hold(self, t):
@@ -448,6 +480,12 @@ class Engine(object):
             self.load_input(x)
             self.launch()
         return self.loc, self.conf, self.obj
+
+    def conv_config(self, op_index):
+        """(tile width, N tiles, cluster, A mode, stages, grid) of a tensor-core conv op, zeros otherwise."""
+        info = (C.c_int * 6)()
+        _lib.check(self.L.ctx_prog_conv_config(self.prog, op_index, info), 'ctx_prog_conv_config')
+        return list(info)
 
     def run_range(self, first, last):
         with torch.cuda.device(self.dev):

@@ -122,6 +122,12 @@ int ctx_conv2d_simt(const CtxConvParams* p, void* stream);          /* fp32-accu
 int ctx_conv2d_tc_supported(const CtxConvParams* p);                /* 1 if the tcgen05 path takes it  */
 /* tcgen05/TMA implicit-GEMM path.  The plan owns the TMA descriptors (pointers are baked in).   */
 int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out);
+/* Same, with the tiling chosen by the caller: n_tiles_n = number of output-channel tiles (0: ceil(Cout/256)), cluster = 1 | 2
+ * CTAs per MMA (0: default), a_mode = -1 rule of thumb | 0 im2col gather | 1 TMA pixel patches.  Outputs are bit-identical
+ * for every setting; ctx_prog_autotune() picks per layer by measurement.  info6 = {tile width, N tiles, cluster, A mode
+ * (0 gather, 1 TMA, 2 stem), ring stages, grid}. */
+int ctx_conv2d_tc_plan_create_tuned(const CtxConvParams* p, int n_tiles_n, int cluster, int a_mode, void** plan_out);
+int ctx_conv2d_tc_plan_info(void* plan, int* info6);
 int ctx_conv2d_tc_plan_run(void* plan, void* stream);
 void ctx_conv2d_tc_plan_destroy(void* plan);
 int ctx_maxpool2d_nhwc(const CtxPoolParams* p, void* stream);
@@ -166,6 +172,14 @@ int ctx_prog_add_nchw_to_nhwc(void* prog, const float* in, void* out, int N, int
 int ctx_prog_add_nchw_to_patch27(void* prog, const float* in, void* out, int N, int H, int W, int out_dtype);
 int ctx_prog_add_attention(void* prog, const CtxAttnParams* p);
 int ctx_prog_add_softmax(void* prog, const float* in, float* out, long long rows, int cols);
+/* Ops added after this call belong to `lane` (0..7); the next op added first waits for everything issued so far on the
+ * lanes in `wait_mask` (bit l = lane l).  Lanes are the independent chains of the forward (the branches of an RFB block,
+ * RFB_Net_vgg.py:48-54,93-101; the per-level heads, :238-248): the captured graph runs them side by side, serial replay
+ * (ctx_prog_run_range) ignores them — program order must therefore already be a valid execution order. */
+int ctx_prog_set_lane(void* prog, int lane, unsigned wait_mask);
+/* time every tensor-core conv of the program under its candidate tilings on `stream` and keep the fastest (blocking) */
+int ctx_prog_autotune(void* prog, void* stream, int reps);
+int ctx_prog_conv_config(void* prog, int op_index, int* info6);   /* zeros for ops that are not tensor-core convs */
 int ctx_prog_num_ops(void* prog);
 int ctx_prog_run(void* prog, void* stream);
 /* capture the op list into a CUDA graph on `stream` (non-default); later ctx_prog_run calls replay it */

@@ -273,6 +273,25 @@ def test_forward_other_seed_vs_torch_oracle_and_cuda_graph():
         assert (got.cpu() - w).abs().max() < 1e-4
 
 
+def test_graph_lanes_and_autotuned_tiles_are_bit_identical(monkeypatch):
+    """The captured graph runs RFB branches / heads on parallel lanes and every conv under its measured-best tiling; neither
+    may change a single bit against the serial, default-tiled program."""
+    case = NET_CASES[0]
+    x = synth.seeded_input(2, 300, seed=1).cuda()
+    outs = []
+    for lanes, tune, graph in (('0', '0', False), ('1', '1', True), ('1', '0', True), ('0', '1', False)):
+        monkeypatch.setenv('CTX_LANES', lanes)
+        monkeypatch.setenv('CTX_AUTOTUNE', tune)
+        net = _build(case, 'bf16')
+        net.use_cuda_graph = graph
+        net(x)
+        outs.append([t.clone() for t in net(x)])               # second call: graph replay
+        torch.cuda.synchronize()
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize('precision', ['bf16', 'fp16'])
 def test_full_forward_16bit_tolerance(golden, precision):
     """Throughput mode: 16-bit activations/weights, fp32 accumulate.  The reference under CPU bf16 autocast
