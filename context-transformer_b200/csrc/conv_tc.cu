@@ -52,7 +52,8 @@ struct TcParams {
   int M, cin_blocks, nk;
   int bn, n_tiles_n, num_tiles;          // num_tiles counts tile GROUPS: `cluster` M-adjacent tiles of one N tile
   int m_tiles, cluster;                  // cluster = 2: CTA pairs, one 2-CTA MMA per K-step (opt-in)
-  int a_mode, TW, TH, tiles_x, tiles_y;       // TMA mode: output patch TW x TH, tiles per image
+  int a_mode, TW, TH, tiles_x, tiles_y;       // TMA mode: output patch TW x TH (<= 128 pixels), tiles per image
+  int flat;                                   // TMA mode, 1x1 convs: the whole batch is one pixel row, tiles are 128-pixel runs
   int res_cstride, res_coffset, res_dtype;
   int is_bf16;
   int pool2;                   // fused MaxPool2d(2,2): TMA mode with TW = 16 (2x2 windows live inside one warp)
@@ -63,14 +64,15 @@ struct TcParams {
 
 // output pixel (image, linear pixel index, validity) of row r of M-tile mt
 __device__ __forceinline__ bool tile_row_pixel(const TcParams& p, int mt, int r, int& n_img, int& pix) {
-  if (p.a_mode == A_TMA) {
+  if (p.a_mode == A_TMA && !p.flat) {
     const int per_img = p.tiles_x * p.tiles_y;
     n_img = mt / per_img;
     const int t = mt - n_img * per_img;
     const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-    const int oy = ty * p.TH + r / p.TW, ox = tx * p.TW + r % p.TW;
+    const int ry = r / p.TW;
+    const int oy = ty * p.TH + ry, ox = tx * p.TW + (r - ry * p.TW);
     pix = oy * p.Wo + ox;
-    return n_img < p.N && oy < p.Ho && ox < p.Wo;
+    return n_img < p.N && ry < p.TH && oy < p.Ho && ox < p.Wo;      // rows >= TW*TH of the M tile are never loaded
   }
   const int m = mt * TC_BM + r;
   const int HoWo = p.Ho * p.Wo;
@@ -248,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     // ================= TMA producer (weights; activations too in mode TMA) =================
     uint32_t g = 0;
     // pair mode: the leader's barrier counts the bytes landing in BOTH CTAs
-    const uint32_t tx_bytes = (uint32_t)CL * ((uint32_t)B_STAGE + (p.a_mode == A_TMA ? (uint32_t)TC_A_STAGE : 0u));
+    const uint32_t tx_bytes = (uint32_t)CL * ((uint32_t)B_STAGE + (p.a_mode == A_TMA ? (uint32_t)(p.TW * p.TH * 128) : 0u));
     for (int tile = group0; tile < p.num_tiles; tile += ngroups) {
       const int mg = tile / p.n_tiles_n, n0 = (tile - mg * p.n_tiles_n) * BN, mt = mg * CL + rank;
       int n_img = 0, x0 = 0, y0 = 0;
@@ -472,7 +474,7 @@ static int num_sms() {
   return cached;
 }
 
-static bool choose_patch(const CtxConvParams* p, int* tw, int* th, int max_waste_pct = 10);
+static bool choose_patch(const CtxConvParams* p, int* tw, int* th, int max_ratio_pct = 150);
 
 static int tc_supported(const CtxConvParams* p) {
   if (!p) return 0;
@@ -486,27 +488,36 @@ static int tc_supported(const CtxConvParams* p) {
   if (((uintptr_t)p->in) % 16 || ((uintptr_t)p->weight) % 16) return 0;
   if (p->pool2) {                        // fused 2x2 pooling: TMA patch mode, one 16-bit output segment
     int tw, th;
-    if (!choose_patch(p, &tw, &th) || p->nseg != 1 || p->residual || p->seg[0].dtype != p->in_dtype || p->Cout % 8) return 0;
+    if (!choose_patch(p, &tw, &th) || p->Cin % 64 || p->nseg != 1 || p->residual || p->seg[0].dtype != p->in_dtype || p->Cout % 8) return 0;
   }
   return 1;
 }
 
-// TMA activation mode: stride-1 conv, whole 64-channel K-steps, and a TW x TH = 128 pixel patch that tiles the
-// output map with <= 10 % waste.
-static bool choose_patch(const CtxConvParams* p, int* tw, int* th, int max_waste_pct) {
-  if (p->stride != 1 || p->Cin % 64 || p->in_coffset % 64 || p->in_cstride % 8) return false;
+// TMA activation mode: stride-1 conv whose output map is tiled by TW x TH pixel patches, TW * TH <= 128 (the rows of the
+// M = 128 tile beyond TW * TH are never loaded nor stored).  The patch that needs the fewest tiles wins; `max_ratio_pct`
+// bounds the tile count against the gather mode's ceil(M / 128) (gather packs pixels across rows and images).
+static bool tma_eligible(const CtxConvParams* p) {
+  return p->stride == 1 && p->Cin % 8 == 0 && p->in_coffset % 8 == 0 && p->in_cstride % 8 == 0 && !p->in_nchw;
+}
+static bool flat_eligible(const CtxConvParams* p) {
+  return tma_eligible(p) && p->KH == 1 && p->KW == 1 && p->pad_h == 0 && p->pad_w == 0 && !p->pool2;
+}
+static bool choose_patch(const CtxConvParams* p, int* tw, int* th, int max_ratio_pct) {
+  if (!tma_eligible(p)) return false;
   if (p->pool2) {                       // 2 x 2 windows must sit inside one warp of the epilogue: 16 x 8 patches
     if ((p->Ho | p->Wo) & 1) return false;
     *tw = 16; *th = 8;
-    return (long long)cdiv(p->Wo, 16) * 16 * cdiv(p->Ho, 8) * 8 * 100 <= (long long)p->Wo * p->Ho * 112;
+    return (long long)cdiv(p->Wo, 16) * cdiv(p->Ho, 8) * p->N * 100 <= (long long)cdiv((long long)p->N * p->Ho * p->Wo, 128) * max_ratio_pct;
   }
   long long best = -1;
-  for (int w = 128; w >= 4; w >>= 1) {
-    const int h = 128 / w;
-    const long long cover = (long long)cdiv(p->Wo, w) * w * cdiv(p->Ho, h) * h;
-    if (best < 0 || cover < best) { best = cover; *tw = w; *th = h; }
+  int best_area = 0;
+  for (int w = std::min(p->Wo, 128); w >= 1; --w) {
+    const int h = std::min(128 / w, p->Ho);
+    const long long tiles = (long long)cdiv(p->Wo, w) * cdiv(p->Ho, h);
+    if (best < 0 || tiles < best || (tiles == best && w * h < best_area)) { best = tiles; best_area = w * h; *tw = w; *th = h; }
   }
-  return best * 100 <= (long long)p->Wo * p->Ho * (100 + max_waste_pct);
+  const long long gather_tiles = cdiv((long long)p->N * p->Ho * p->Wo, 128);
+  return best * p->N * 100 <= gather_tiles * max_ratio_pct;
 }
 
 template <int S, int CL>
@@ -596,11 +607,13 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
   int tw = 0, th = 0;
   if (p->in_nchw) t.a_mode = A_STEM;
   else if (tune_amode == 0 && !p->pool2) t.a_mode = A_GATHER;
-  else t.a_mode = choose_patch(p, &tw, &th, tune_amode == 1 ? 1000 : 10) ? A_TMA : A_GATHER;
+  else if (flat_eligible(p)) { t.a_mode = A_TMA; tw = 128; th = 1; }
+  else t.a_mode = choose_patch(p, &tw, &th, tune_amode == 1 ? 100000 : 150) ? A_TMA : A_GATHER;
+  t.flat = t.a_mode == A_TMA && flat_eligible(p);
   t.TW = tw; t.TH = th;
-  t.tiles_x = t.a_mode == A_TMA ? cdiv(p->Wo, tw) : 0;
-  t.tiles_y = t.a_mode == A_TMA ? cdiv(p->Ho, th) : 0;
-  const int m_tiles = t.a_mode == A_TMA ? p->N * t.tiles_x * t.tiles_y : cdiv(t.M, TC_BM);
+  t.tiles_x = t.a_mode == A_TMA ? (t.flat ? cdiv(t.M, 128) : cdiv(p->Wo, tw)) : 0;
+  t.tiles_y = t.a_mode == A_TMA ? (t.flat ? 1 : cdiv(p->Ho, th)) : 0;
+  const int m_tiles = t.a_mode == A_TMA ? (t.flat ? t.tiles_x : p->N * t.tiles_x * t.tiles_y) : cdiv(t.M, TC_BM);
   t.m_tiles = m_tiles;
   {
     // CTA pairs (one tcgen05.mma.cta_group::2 spanning both SMs of a cluster of two, each CTA staging half of the weight
@@ -621,7 +634,8 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
   const unsigned long long cout_pad = (unsigned long long)((p->Cout + 15) / 16 * 16);
   int rc = encode_2d_sw128(&pl->tmap_w, p->weight, t.is_bf16 != 0, cout_pad, ktot, (unsigned)(t.bn / t.cluster));
   if (!rc && t.a_mode == A_TMA)
-    rc = encode_nhwc_sw128(&pl->tmap_a, p->in, t.is_bf16 != 0, p->N, p->H, p->W, p->in_cstride, (unsigned)tw, (unsigned)th);
+    rc = t.flat ? encode_nhwc_sw128(&pl->tmap_a, p->in, t.is_bf16 != 0, 1, 1, t.M, p->in_cstride, p->in_coffset + p->Cin, 128u, 1u)
+                : encode_nhwc_sw128(&pl->tmap_a, p->in, t.is_bf16 != 0, p->N, p->H, p->W, p->in_cstride, p->in_coffset + p->Cin, (unsigned)tw, (unsigned)th);
   if (rc) { delete pl; return rc; }
   if (t.pool2 && !(t.a_mode == A_TMA && t.TW == 16 && t.fast_out)) {
     delete pl;

@@ -34,12 +34,13 @@ int encode_2d_sw128(CUtensorMap* out, const void* base, bool bf16, unsigned long
   return CTX_OK;
 }
 
-// NHWC activation [N][H][W][C] 16-bit as a 4-D tensor (C innermost); box = 64 channels x bw x bh pixels of one
-// image, SWIZZLE_128B.  Out-of-range pixels (conv padding) and channels read as zero.
-int encode_nhwc_sw128(CUtensorMap* out, const void* base, bool bf16, int N, int H, int W, int C, unsigned bw, unsigned bh) {
+// NHWC activation [N][H][W][C] 16-bit as a 4-D tensor (C innermost, pixels C elements apart, only channels < c_limit
+// addressable); box = 64 channels x bw x bh pixels of one image, SWIZZLE_128B.  Out-of-range pixels (conv padding) and
+// channels >= c_limit (the tail of a channel slice that is not a multiple of 64) read as zero.
+int encode_nhwc_sw128(CUtensorMap* out, const void* base, bool bf16, int N, int H, int W, int C, int c_limit, unsigned bw, unsigned bh) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return CTX_ERR_CUDA; }
-  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gdim[4] = {(cuuint64_t)c_limit, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[4] = {64u, bw, bh, 1u};
   cuuint32_t estr[4] = {1, 1, 1, 1};

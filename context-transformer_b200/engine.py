@@ -180,6 +180,7 @@ class Engine(object):
             p.seg[i].c_begin, p.seg[i].c_end = c0, c1
             p.seg[i].img_stride, p.seg[i].pix_stride, p.seg[i].ch_offset = img_stride, pix_stride, ch_off
             p.seg[i].dtype = _lib.dtype_code(t.dtype)
+        self.last_conv_params = p            # (tests re-plan the same conv under other tilings)
         flops = algo_flops if algo_flops is not None else 2.0 * src.N * Ho * Wo * Cout * Cin * KH * KW
         use_tc = self.precision != 'fp32' and self.L.ctx_conv2d_tc_supported(C.byref(p)) == 1
         if pool2 and not use_tc:

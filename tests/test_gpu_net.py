@@ -106,6 +106,50 @@ def test_conv_cta_pair_mode(case, monkeypatch):
     assert torch.allclose(got, want, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize('case', [(128, 128, 3, 1, 1, 1, 38, 38), (256, 256, 3, 1, 2, 2, 19, 19), (96, 128, (3, 1), 1, (1, 0), 1, 38, 38),
+                                  (512, 320, 1, 1, 0, 1, 19, 19), (192, 256, 3, 1, 1, 1, 10, 10), (64, 64, 3, 1, 1, 1, 75, 75),
+                                  (128, 256, 3, 1, 1, 1, 5, 5), (1024, 264, 1, 1, 0, 1, 7, 9)], ids=str)
+def test_conv_every_tiling_is_bit_identical(case):
+    """ctx_conv2d_tc_plan_create_tuned: N-tile count, CTA pairs and the A-operand mode (TMA pixel patches of any
+    TW x TH <= 128 shape, flat 128-pixel runs for 1x1 convs, im2col gather) only change the tiling, never a bit of the result."""
+    cin, cout, k, stride, pad, dil, H, W = case
+    kh, kw = (k, k) if isinstance(k, int) else k
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    g = synth._gen(11, 'tiling%s' % (case,))
+    N = 4
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, kh, kw, generator=g) * (2.0 / (cin * kh * kw)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    e = _Scratch('bf16')
+    src, _ = _nhwc_view(x, e.act_dtype, pad_c=72, coff=8)          # a channel slice that does not start at a multiple of 64
+    out = e._emit_conv('t', src, w.to(DEV), b.to(DEV), stride, (ph, pw), dil, True)
+    assert e.layers[-1][1] == 'conv_tc'
+    e.go()
+    ref = out.tensor().clone()
+    want = F.relu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, stride, (ph, pw), dil))
+    assert torch.allclose(ref.float().cpu().permute(0, 3, 1, 2), want, rtol=1e-2, atol=1e-2)
+    L = e.L
+    p = e.last_conv_params
+    seen = set()
+    for n in (0, 2, 3, 5):
+        for cl in (1, 2):
+            for amode in (-1, 0, 1):
+                plan = C.c_void_p()
+                _lib.check(L.ctx_conv2d_tc_plan_create_tuned(C.byref(p), n, cl, amode, C.byref(plan)), 'plan_create_tuned')
+                info = (C.c_int * 6)()
+                _lib.check(L.ctx_conv2d_tc_plan_info(plan, info))
+                key = tuple(info)[:4]
+                if key not in seen:
+                    seen.add(key)
+                    out.buf.zero_()
+                    _lib.check(L.ctx_conv2d_tc_plan_run(plan, _lib.current_stream_ptr(DEV)), 'plan_run %s' % (key,))
+                    torch.cuda.synchronize()
+                    assert torch.equal(out.tensor(), ref), key
+                L.ctx_conv2d_tc_plan_destroy(plan)
+    assert len(seen) >= 4
+    assert {m for (_, _, _, m) in seen} == {0, 1}                 # both A-operand modes were exercised
+
+
 @pytest.mark.parametrize('case', [(64, 64, 32, 48), (128, 128, 30, 64), (64, 96, 24, 32)], ids=str)
 def test_conv_fused_maxpool(case):
     """conv3x3 -> ReLU -> MaxPool2d(2,2) with the pooling done in the conv epilogue (vgg 'M' layers)."""
@@ -120,7 +164,7 @@ def test_conv_fused_maxpool(case):
     out = e._emit_conv('t', src, w.to(DEV), b.to(DEV), 1, (1, 1), 1, True, pool2=True)
     assert out is not None and (out.H, out.W) == (H // 2, W // 2)
     # maps that 16 x 8 patches tile badly are declined (the engine then emits conv + pool separately)
-    assert e._emit_conv('u', View(buf.view(-1)[:3 * 6 * 10 * cin], 3, 6, 10, cin), w.to(DEV), b.to(DEV), 1, (1, 1), 1, True, pool2=True) is None
+    assert e._emit_conv('u', View(buf.view(-1)[:3 * 2 * 2 * cin], 3, 2, 2, cin), w.to(DEV), b.to(DEV), 1, (1, 1), 1, True, pool2=True) is None
     e.go()
     got = out.tensor().float().cpu().permute(0, 3, 1, 2)
     want = F.max_pool2d(F.relu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, 1, 1)), 2, 2)
