@@ -1,0 +1,174 @@
+// mma_probe.cu — standalone sm_100a probe (development aid, not part of the library):
+//   (1) tcgen05.mma issue cost and issue->commit-arrival latency for M128 x N x K16 bf16 MMAs, N = 64 / 128 / 256;
+//   (2) steady-state throughput of {4 MMAs + commit} groups (the conv kernel's K-step);
+//   (3) whether a SWIZZLE_128B K-major operand descriptor may START at any 128-byte row (not only at a 1024-byte swizzle
+//       atom) and use a stride between 8-row groups that is not 1024 B: the "halo window" addressing of a 3x3 conv whose
+//       activation patch is staged once and read under nine shifted descriptors.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o mma_probe mma_probe.cu ; run: ./mma_probe
+#include "../../context-transformer_b200/csrc/tc_common.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+using namespace ctx;
+
+namespace ctx { void set_error(const char*, ...) {} void count_launch(int) {} }
+
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+// ---- (1) + (2): timing -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) timing_kernel(long long* out, int N) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + 16384, bars = base + 16384 + 32768, slot = bars + 256;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(raw + (base - smem_u32(raw)))[i] = 0u;
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) { for (int b = 0; b < 32; ++b) mbar_init(bars + 8 * b, 1); fence_barrier_init(); }
+    __syncwarp();
+    tmem_alloc(slot, 512); tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_f16(true, 128, N);
+    const uint64_t ad = desc_sw128(sA, 1024), bd = desc_sw128(sB, 1024);
+    int o = 0, bar = 0;
+    uint32_t ph[32];
+    for (int b = 0; b < 32; ++b) ph[b] = 0;
+    // (1) n MMAs + one commit: issue clocks, clocks until the commit's mbarrier arrival is visible
+    const int counts[8] = {1, 2, 4, 8, 16, 36, 72, 144};
+    for (int rep = 0; rep < 2; ++rep)
+      for (int c = 0; c < 8; ++c) {
+        const long long t0 = clock64();
+        for (int i = 0; i < counts[c]; ++i) umma_f16(tmem, ad + 2 * (i & 3), bd + 2 * (i & 3), idesc, i ? 1u : 0u);
+        umma_commit(bars + 8 * bar);
+        const long long t1 = clock64();
+        mbar_spin(bars + 8 * bar, ph[bar]); ph[bar] ^= 1u;
+        const long long t2 = clock64();
+        if (rep == 1) { out[o++] = counts[c]; out[o++] = t1 - t0; out[o++] = t2 - t0; }
+      }
+    // (2) G groups of {4 MMAs + commit} issued back to back on a ring of 8 barriers (waiting for group g - 8 before
+    //     issuing g, like the conv kernel's smem ring): clocks per group in steady state
+    for (int ring = 2; ring <= 8; ring *= 2) {
+      const int G = 64;
+      const long long t0 = clock64();
+      for (int g = 0; g < G; ++g) {
+        const int b = g % ring;
+        if (g >= ring) { mbar_spin(bars + 8 * b, ph[b]); ph[b] ^= 1u; }
+        for (int i = 0; i < 4; ++i) umma_f16(tmem, ad + 2 * i, bd + 2 * i, idesc, (g | i) ? 1u : 0u);
+        umma_commit(bars + 8 * b);
+      }
+      for (int b = 0; b < ring; ++b) { mbar_spin(bars + 8 * b, ph[b]); ph[b] ^= 1u; }
+      const long long t1 = clock64();
+      out[o++] = -ring; out[o++] = G; out[o++] = t1 - t0;
+    }
+    out[o++] = 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ---- (3) shifted / strided descriptor windows ---------------------------------------------------------
+// smem A: R rows of 64 bf16 (128 B) in the SWIZZLE_128B pattern of a 1024-B aligned buffer: A[r][k] = value(r, k).
+// B = 64 x 64 identity.  D = A_window * B^T  ->  D[m][n] = A[row(m)][n], row(m) = shift + (m / 8) * group_rows + m % 8.
+__global__ void __launch_bounds__(128, 1) window_kernel(float* out, int shift, int group_rows) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  uint8_t* gen = raw + (base - smem_u32(raw));
+  const int R = 320;
+  const uint32_t sA = base, sB = base + R * 128, bars = sB + 64 * 128, slot = bars + 64;
+  for (int i = threadIdx.x; i < R * 64; i += 128) {
+    const int r = i >> 6, k = i & 63;
+    const float v = (float)((r * 3 + k * 5) % 251) - 125.f;          // exactly representable in bf16 (|v| < 256, integer)
+    const uint32_t off = r * 128 + ((((k >> 3) ^ (r & 7)) << 4) | ((k & 7) << 1));
+    *reinterpret_cast<__nv_bfloat16*>(gen + off) = __float2bfloat16_rn(v);
+  }
+  for (int i = threadIdx.x; i < 64 * 64; i += 128) {
+    const int r = i >> 6, k = i & 63;
+    const uint32_t off = R * 128 + r * 128 + ((((k >> 3) ^ (r & 7)) << 4) | ((k & 7) << 1));
+    *reinterpret_cast<__nv_bfloat16*>(gen + off) = __float2bfloat16_rn(r == k ? 1.f : 0.f);
+  }
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) { mbar_init(bars, 1); fence_barrier_init(); }
+    __syncwarp();
+    tmem_alloc(slot, 64); tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_f16(true, 128, 64);
+    const uint64_t ad = desc_sw128(sA + shift * 128, group_rows * 128), bd = desc_sw128(sB, 1024);
+    for (int k = 0; k < 4; ++k) umma_f16(tmem, ad + 2 * k, bd + 2 * k, idesc, k ? 1u : 0u);
+    umma_commit(bars);
+    mbar_spin(bars, 0);
+  }
+  __syncthreads();
+  tc_fence_after();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int cb = 0; cb < 2; ++cb) {
+    uint32_t v[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + cb * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 64); }
+}
+
+int main() {
+  long long* d_out; float* d_f;
+  cudaMalloc(&d_out, 4096 * sizeof(long long));
+  cudaMalloc(&d_f, 128 * 64 * sizeof(float));
+  cudaFuncSetAttribute(timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  const int Ns[3] = {64, 128, 256};
+  for (int n = 0; n < 3; ++n) {
+    cudaMemset(d_out, 0, 4096 * sizeof(long long));
+    timing_kernel<<<1, 128, 64 * 1024>>>(d_out, Ns[n]);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("timing N=%d failed: %s\n", Ns[n], cudaGetErrorString(e)); return 1; }
+    std::vector<long long> h(4096);
+    cudaMemcpy(h.data(), d_out, 4096 * sizeof(long long), cudaMemcpyDeviceToHost);
+    printf("== N = %d (floor %d clk / MMA)\n", Ns[n], Ns[n] / 2);
+    for (int o = 0; h[o] != 0; o += 3) {
+      if (h[o] > 0) printf("  %3lld MMAs + commit: issue %5lld clk, issue->arrival %6lld clk (%.1f clk/MMA)\n", h[o], h[o + 1], h[o + 2], (double)h[o + 2] / h[o]);
+      else printf("  ring of %lld: %lld groups of {4 MMA + commit}: %lld clk = %.1f clk/group\n", -h[o], h[o + 1], h[o + 2], (double)h[o + 2] / h[o + 1]);
+    }
+  }
+  // (3)
+  const int shifts[8] = {0, 1, 2, 3, 7, 8, 9, 11};
+  const int groups[3] = {8, 10, 18};
+  std::vector<float> hf(128 * 64);
+  for (int gi = 0; gi < 3; ++gi)
+    for (int si = 0; si < 8; ++si) {
+      cudaMemset(d_f, 0, 128 * 64 * sizeof(float));
+      window_kernel<<<1, 128, 64 * 1024>>>(d_f, shifts[si], groups[gi]);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("window shift %d group %d failed: %s\n", shifts[si], groups[gi], cudaGetErrorString(e)); return 1; }
+      cudaMemcpy(hf.data(), d_f, hf.size() * sizeof(float), cudaMemcpyDeviceToHost);
+      int bad = 0, first = -1;
+      for (int m = 0; m < 128; ++m)
+        for (int nn = 0; nn < 64; ++nn) {
+          const int r = shifts[si] + (m / 8) * groups[gi] + m % 8;
+          const float want = (float)((r * 3 + nn * 5) % 251) - 125.f;
+          if (hf[m * 64 + nn] != want) { if (first < 0) first = m * 64 + nn; ++bad; }
+        }
+      printf("window: start row %2d, 8-row groups %2d rows apart: %s (%d mismatches%s)\n", shifts[si], groups[gi], bad ? "WRONG" : "exact", bad,
+             bad ? "" : "");
+      if (bad && first >= 0) printf("    first mismatch at m=%d n=%d: got %g\n", first / 64, first % 64, hf[first]);
+    }
+  return 0;
+}
