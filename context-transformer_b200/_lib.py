@@ -78,7 +78,7 @@ SIGNATURES = {
     'ctx_conv2d_simt': (_I, [C.POINTER(CtxConvParams), _P]),
     'ctx_conv2d_tc_supported': (_I, [C.POINTER(CtxConvParams)]),
     'ctx_conv2d_tc_plan_create': (_I, [C.POINTER(CtxConvParams), C.POINTER(_P)]),
-    'ctx_conv2d_tc_plan_create_tuned': (_I, [C.POINTER(CtxConvParams), _I, _I, _I, C.POINTER(_P)]),
+    'ctx_conv2d_tc_plan_create_tuned': (_I, [C.POINTER(CtxConvParams), _I, _I, _I, _I, C.POINTER(_P)]),
     'ctx_conv2d_tc_plan_info': (_I, [_P, C.POINTER(_I)]),
     'ctx_conv2d_tc_plan_run': (_I, [_P, _P]),
     'ctx_conv2d_tc_plan_destroy': (None, [_P]),

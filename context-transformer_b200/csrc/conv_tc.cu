@@ -57,6 +57,7 @@ struct TcParams {
   int res_cstride, res_coffset, res_dtype;
   int is_bf16;
   int pool2;                   // fused MaxPool2d(2,2): TMA mode with TW = 16 (2x2 windows live inside one warp)
+  int clog;                    // log2 of the commit group: ring slots are handed back to the producers 1 << clog at a time
   int fast_out;                // single 16-bit segment, 8-channel aligned: 128-bit stores
   int vec_f32;                 // fp32 segments, 4-channel aligned: 128-bit stores
   SegTable segs;
@@ -99,6 +100,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = p.nk;
+  // A tcgen05.commit costs the issuing thread ~350 clk in steady state ({4 MMA + commit} = 546 clk whatever N,
+  // profiles/r1_mma_probe.txt): with narrow N tiles one commit per K-step would bound the kernel, so ring slots are
+  // released in groups of 1 << clog K-steps (one commit, one EMPTY barrier per group).
+  const uint32_t cmask = (1u << p.clog) - 1u;
   const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
   const int group0 = blockIdx.x / CL, ngroups = gridDim.x / CL;   // persistent walk over tile groups
 
@@ -167,7 +172,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         int tap = 0, cc = 0, ky = 0, kx = 0;
         for (int it = 0; it < nk; ++it, ++g) {
           const uint32_t s = g % S;
-          mbar_wait(empty0 + 8 * s, ((g / S) & 1) ^ 1);
+          if ((s & cmask) == 0) mbar_wait(empty0 + 8 * (s >> p.clog), ((g / S) & 1) ^ 1);
           const long long tap_off = (long long)((ky * p.dil) * p.W + kx * p.dil) * p.in_cstride + cc * TC_BK;
           const bool ch_ok = (cc * TC_BK + chunk * 8) < p.Cin;
           const uint32_t dst_stage = sA + s * TC_A_STAGE;
@@ -230,7 +235,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         for (int e = 0; e < 28; ++e) v[e] = vnext[e];
         load_patch(tile + ngroups, vnext);
         const uint32_t s = g % S;
-        mbar_wait(empty0 + 8 * s, ((g / S) & 1) ^ 1);
+        if ((s & cmask) == 0) mbar_wait(empty0 + 8 * (s >> p.clog), ((g / S) & 1) ^ 1);
         const uint32_t row = sA + s * TC_A_STAGE + r * 128;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
@@ -264,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       int cc = 0, ky = 0, kx = 0;
       for (int it = 0; it < nk; ++it, ++g) {
         const uint32_t s = g % S;
-        mbar_wait(empty0 + 8 * s, ((g / S) & 1) ^ 1);
+        if ((s & cmask) == 0) mbar_wait(empty0 + 8 * (s >> p.clog), ((g / S) & 1) ^ 1);
         if (elect_one()) {
           // this CTA stages rows [rank * BN/CL, +BN/CL) of the weight tile (a 2-CTA MMA reads both halves)
           if (CL == 2 && rank == 1) {
@@ -307,11 +312,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             if (CL == 2) {
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) umma_f16_2cta(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (it | k) ? 1u : 0u);
-              umma_commit_2cta(empty0 + 8 * s, (uint16_t)3);
+              if ((s & cmask) == cmask) umma_commit_2cta(empty0 + 8 * (s >> p.clog), (uint16_t)3);
             } else {
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k) umma_f16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (it | k) ? 1u : 0u);
-              umma_commit(empty0 + 8 * s);
+              if ((s & cmask) == cmask) umma_commit(empty0 + 8 * (s >> p.clog));
             }
           }
           __syncwarp();
@@ -552,7 +557,7 @@ extern "C" int ctx_conv2d_tc_supported(const CtxConvParams* p) { return tc_suppo
 // tune_n: number of N tiles (0 = ceil(Cout / 256)); tune_cluster: 1 / 2 CTAs per MMA (0 = default); tune_amode: -1 = rule
 // of thumb (TMA patches when they tile the map with <= 10 % waste), 0 = im2col gather, 1 = TMA patches whenever the
 // geometry allows them (any waste).  Results are bit-identical across all settings: only the tiling changes.
-static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int tune_amode, void** plan_out) {
+static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int tune_amode, int tune_commit, void** plan_out) {
   CTX_REQUIRE(p && plan_out, "ctx_conv2d_tc_plan_create: null argument");
   *plan_out = nullptr;
   if (!tc_supported(p)) { set_error("ctx_conv2d_tc: geometry / dtype not supported by the tcgen05 path"); return CTX_ERR_UNSUPPORTED; }
@@ -626,6 +631,16 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
   t.num_tiles = cdiv(m_tiles, t.cluster) * t.n_tiles_n;
   const int stage_bytes = TC_A_STAGE + (t.bn / t.cluster) * TC_BK * 2;
   pl->stages = stage_bytes <= 24 * 1024 ? 8 : (stage_bytes <= 32 * 1024 ? 6 : 4);
+  {
+    // commit group: enough MMA work per commit to hide its ~550 clk (4 MMAs of M128 x N x K16 take 2 N clk); must divide the ring
+    int c = tune_commit > 0 ? tune_commit : (t.bn >= 192 ? 1 : (t.bn >= 96 ? 2 : 4));
+    if (t.nk == 1) c = 1;                               // stem: one K-step per tile, latency matters more
+    // gather mode signals K-step j only when it issues K-step j + S - 2 (cp.async look-ahead): the producers must be
+    // able to run S - 2 slots ahead of the oldest unreleased group, i.e. look-ahead + group <= S
+    if (t.a_mode == A_GATHER && c > 2) c = 2;
+    while (c > 1 && (pl->stages % c || c > pl->stages / 2)) c >>= 1;
+    t.clog = c >= 4 ? 2 : (c >= 2 ? 1 : 0);
+  }
   pl->smem = (size_t)pl->stages * stage_bytes + 24 * pl->stages + 64 + 4 * (((size_t)p->Cout + 31) / 32 * 32 + 32) + 1024;
   pl->grid = std::min(t.num_tiles, num_sms() / t.cluster) * t.cluster;
 
@@ -646,15 +661,17 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
   return CTX_OK;
 }
 
-extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out) { return plan_create(p, 0, 0, -1, plan_out); }
+extern "C" int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out) { return plan_create(p, 0, 0, -1, 0, plan_out); }
 
-extern "C" int ctx_conv2d_tc_plan_create_tuned(const CtxConvParams* p, int n_tiles_n, int cluster, int a_mode, void** plan_out) {
-  return plan_create(p, n_tiles_n, cluster, a_mode, plan_out);
+extern "C" int ctx_conv2d_tc_plan_create_tuned(const CtxConvParams* p, int n_tiles_n, int cluster, int a_mode, int commit_group, void** plan_out) {
+  return plan_create(p, n_tiles_n, cluster, a_mode, commit_group, plan_out);
 }
 
-extern "C" int ctx_conv2d_tc_plan_info(void* plan, int* info6) {
-  CTX_REQUIRE(plan && info6, "ctx_conv2d_tc_plan_info: null argument");
+extern "C" int ctx_conv2d_tc_plan_info(void* plan, int* info8) {
+  CTX_REQUIRE(plan && info8, "ctx_conv2d_tc_plan_info: null argument");
   const TcPlan* pl = (const TcPlan*)plan;
+  int* info6 = info8;
+  info8[6] = 1 << pl->p.clog; info8[7] = pl->p.TW * 1000 + pl->p.TH;
   info6[0] = pl->p.bn; info6[1] = pl->p.n_tiles_n; info6[2] = pl->p.cluster; info6[3] = pl->p.a_mode; info6[4] = pl->stages; info6[5] = pl->grid;
   return CTX_OK;
 }

@@ -162,11 +162,11 @@ extern "C" int ctx_prog_set_lane(void* prog, int lane, unsigned wait_mask) {
   return CTX_OK;
 }
 
-extern "C" int ctx_prog_conv_config(void* prog, int op_index, int* info6) {
+extern "C" int ctx_prog_conv_config(void* prog, int op_index, int* info6) {          // info6: 8 ints (ctx_conv2d_tc_plan_info)
   CTX_REQUIRE(prog && info6, "ctx_prog_conv_config: null argument");
   Prog* pr = (Prog*)prog;
   CTX_REQUIRE(op_index >= 0 && op_index < (int)pr->ops.size(), "ctx_prog_conv_config: bad op index %d", op_index);
-  for (int i = 0; i < 6; ++i) info6[i] = 0;
+  for (int i = 0; i < 8; ++i) info6[i] = 0;
   if (pr->ops[op_index].kind != OP_CONV_TC) return CTX_OK;
   return ctx_conv2d_tc_plan_info(pr->ops[op_index].tc_plan, info6);
 }
@@ -189,9 +189,9 @@ extern "C" int ctx_prog_autotune(void* prog, void* stream, int reps) {
   int op_index = -1;
   auto trace = [&](const Op& op, const int* info, float ms, const char* tag) {
     if (!log) return;
-    fprintf(log, "op %d  %dx%dx%d->%d k%dx%d s%d d%d  bn %d ntn %d cl %d amode %d stages %d grid %d  %.2f us %s\n", op_index, op.conv.H, op.conv.W,
-            op.conv.Cin, op.conv.Cout, op.conv.KH, op.conv.KW, op.conv.stride, op.conv.dil, info[0], info[1], info[2], info[3], info[4], info[5],
-            1000.f * ms / reps, tag);
+    fprintf(log, "op %d  %dx%dx%d->%d k%dx%d s%d d%d  bn %d ntn %d cl %d amode %d stages %d grid %d commit %d patch %dx%d  %.2f us %s\n", op_index,
+            op.conv.H, op.conv.W, op.conv.Cin, op.conv.Cout, op.conv.KH, op.conv.KW, op.conv.stride, op.conv.dil, info[0], info[1], info[2],
+            info[3], info[4], info[5], info[6], info[7] / 1000, info[7] % 1000, 1000.f * ms / reps, tag);
   };
   auto time_plan = [&](void* plan, float* ms) -> int {
     int r = ctx_conv2d_tc_plan_run(plan, st);                  // warm-up (descriptor fetch, L2)
@@ -208,33 +208,40 @@ extern "C" int ctx_prog_autotune(void* prog, void* stream, int reps) {
     if (op.kind != OP_CONV_TC || op.conv.in_nchw) continue;
     float best_ms = 0.f;
     if ((rc = time_plan(op.tc_plan, &best_ms))) break;
-    int base[6];
+    int base[8];
     ctx_conv2d_tc_plan_info(op.tc_plan, base);
     trace(op, base, best_ms, "default");
     const int n0 = base[1];
-    std::vector<long> seen;                                   // (tile width, cluster, A mode) already measured
-    auto key_of = [](const int* info) { return (long)info[0] * 100 + info[2] * 10 + info[3]; };
+    int best_n = 0, best_cl = 0, best_amode = -1;             // arguments that produced the current best plan
+    std::vector<long> seen;                                   // (tile width, cluster, A mode, commit group) already measured
+    auto key_of = [](const int* info) { return ((long)info[0] * 100 + info[2] * 10 + info[3]) * 10 + info[6]; };
     seen.push_back(key_of(base));
+    auto consider = [&](int n, int cl, int amode, int cg) -> bool {          // true if the candidate became the best plan
+      void* cand = nullptr;
+      if (ctx_conv2d_tc_plan_create_tuned(&op.conv, n, cl, amode, cg, &cand) != CTX_OK) return false;
+      int info[8];
+      ctx_conv2d_tc_plan_info(cand, info);
+      const long key = key_of(info);
+      bool dup = info[0] < 32;
+      for (long k : seen) dup = dup || k == key;
+      if (dup) { ctx_conv2d_tc_plan_destroy(cand); return false; }
+      seen.push_back(key);
+      float ms = 0.f;
+      rc = time_plan(cand, &ms);
+      const bool better = !rc && ms < best_ms * 0.97f;
+      if (!rc) trace(op, info, ms, better ? "better" : "");
+      if (better) { ctx_conv2d_tc_plan_destroy(op.tc_plan); op.tc_plan = cand; best_ms = ms; }
+      else ctx_conv2d_tc_plan_destroy(cand);
+      return better;
+    };
+    // pass 1: tile width x CTA pairs x A-operand mode, commit group by rule; pass 2: commit group on the winner
     for (int dn = 0; dn < 6 && !rc; ++dn) {
       const int n = dn < 4 ? n0 + dn : n0 * (dn == 4 ? 2 : 3);
       for (int amode = -1; amode <= 1 && !rc; ++amode)
-        for (int cl = 1; cl <= 2 && !rc; ++cl) {
-          void* cand = nullptr;
-          if (ctx_conv2d_tc_plan_create_tuned(&op.conv, n, cl, amode, &cand) != CTX_OK) continue;
-          int info[6];
-          ctx_conv2d_tc_plan_info(cand, info);
-          const long key = key_of(info);
-          bool dup = info[0] < 32;
-          for (long k : seen) dup = dup || k == key;
-          if (dup) { ctx_conv2d_tc_plan_destroy(cand); continue; }
-          seen.push_back(key);
-          float ms = 0.f;
-          rc = time_plan(cand, &ms);
-          if (!rc) trace(op, info, ms, ms < best_ms * 0.97f ? "better" : "");
-          if (!rc && ms < best_ms * 0.97f) { ctx_conv2d_tc_plan_destroy(op.tc_plan); op.tc_plan = cand; best_ms = ms; }
-          else ctx_conv2d_tc_plan_destroy(cand);
-        }
+        for (int cl = 1; cl <= 2 && !rc; ++cl)
+          if (consider(n, cl, amode, 0)) { best_n = n; best_cl = cl; best_amode = amode; }
     }
+    for (int cg = 1; cg <= 4 && !rc; cg *= 2) consider(best_n, best_cl, best_amode, cg);
     if (rc) break;
   }
   if (log) fclose(log);

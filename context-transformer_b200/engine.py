@@ -483,8 +483,8 @@ class Engine(object):
         return self.loc, self.conf, self.obj
 
     def conv_config(self, op_index):
-        """(tile width, N tiles, cluster, A mode, stages, grid) of a tensor-core conv op, zeros otherwise."""
-        info = (C.c_int * 6)()
+        """(tile width, N tiles, cluster, A mode, stages, grid, commit group, patch) of a tensor-core conv op, zeros otherwise."""
+        info = (C.c_int * 8)()
         _lib.check(self.L.ctx_prog_conv_config(self.prog, op_index, info), 'ctx_prog_conv_config')
         return list(info)
 

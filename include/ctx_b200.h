@@ -123,11 +123,12 @@ int ctx_conv2d_tc_supported(const CtxConvParams* p);                /* 1 if the 
 /* tcgen05/TMA implicit-GEMM path.  The plan owns the TMA descriptors (pointers are baked in).   */
 int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out);
 /* Same, with the tiling chosen by the caller: n_tiles_n = number of output-channel tiles (0: ceil(Cout/256)), cluster = 1 | 2
- * CTAs per MMA (0: default), a_mode = -1 rule of thumb | 0 im2col gather | 1 TMA pixel patches.  Outputs are bit-identical
- * for every setting; ctx_prog_autotune() picks per layer by measurement.  info6 = {tile width, N tiles, cluster, A mode
- * (0 gather, 1 TMA, 2 stem), ring stages, grid}. */
-int ctx_conv2d_tc_plan_create_tuned(const CtxConvParams* p, int n_tiles_n, int cluster, int a_mode, void** plan_out);
-int ctx_conv2d_tc_plan_info(void* plan, int* info6);
+ * CTAs per MMA (0: default), a_mode = -1 rule of thumb | 0 im2col gather | 1 TMA pixel patches, commit_group = K-steps per
+ * tcgen05.commit (0: by tile width | 1 | 2 | 4).  Outputs are bit-identical for every setting; ctx_prog_autotune() picks per
+ * layer by measurement.  info8 = {tile width, N tiles, cluster, A mode (0 gather, 1 TMA, 2 stem), ring stages, grid,
+ * commit group, TMA patch TW * 1000 + TH}. */
+int ctx_conv2d_tc_plan_create_tuned(const CtxConvParams* p, int n_tiles_n, int cluster, int a_mode, int commit_group, void** plan_out);
+int ctx_conv2d_tc_plan_info(void* plan, int* info8);
 int ctx_conv2d_tc_plan_run(void* plan, void* stream);
 void ctx_conv2d_tc_plan_destroy(void* plan);
 int ctx_maxpool2d_nhwc(const CtxPoolParams* p, void* stream);
@@ -179,7 +180,7 @@ int ctx_prog_add_softmax(void* prog, const float* in, float* out, long long rows
 int ctx_prog_set_lane(void* prog, int lane, unsigned wait_mask);
 /* time every tensor-core conv of the program under its candidate tilings on `stream` and keep the fastest (blocking) */
 int ctx_prog_autotune(void* prog, void* stream, int reps);
-int ctx_prog_conv_config(void* prog, int op_index, int* info6);   /* zeros for ops that are not tensor-core convs */
+int ctx_prog_conv_config(void* prog, int op_index, int* info8);   /* zeros for ops that are not tensor-core convs */
 int ctx_prog_num_ops(void* prog);
 int ctx_prog_run(void* prog, void* stream);
 /* capture the op list into a CUDA graph on `stream` (non-default); later ctx_prog_run calls replay it */

@@ -131,14 +131,14 @@ def test_conv_every_tiling_is_bit_identical(case):
     L = e.L
     p = e.last_conv_params
     seen = set()
-    for n in (0, 2, 3, 5):
+    for n, cg in ((0, 0), (2, 1), (3, 2), (5, 4), (0, 4), (0, 1)):
         for cl in (1, 2):
             for amode in (-1, 0, 1):
                 plan = C.c_void_p()
-                _lib.check(L.ctx_conv2d_tc_plan_create_tuned(C.byref(p), n, cl, amode, C.byref(plan)), 'plan_create_tuned')
-                info = (C.c_int * 6)()
+                _lib.check(L.ctx_conv2d_tc_plan_create_tuned(C.byref(p), n, cl, amode, cg, C.byref(plan)), 'plan_create_tuned')
+                info = (C.c_int * 8)()
                 _lib.check(L.ctx_conv2d_tc_plan_info(plan, info))
-                key = tuple(info)[:4]
+                key = (info[0], info[1], info[2], info[3], info[6])
                 if key not in seen:
                     seen.add(key)
                     out.buf.zero_()
@@ -147,7 +147,8 @@ def test_conv_every_tiling_is_bit_identical(case):
                     assert torch.equal(out.tensor(), ref), key
                 L.ctx_conv2d_tc_plan_destroy(plan)
     assert len(seen) >= 4
-    assert {m for (_, _, _, m) in seen} == {0, 1}                 # both A-operand modes were exercised
+    assert {k[3] for k in seen} == {0, 1}                         # both A-operand modes were exercised
+    assert len({k[4] for k in seen}) >= 2                         # ... and more than one commit-group size
 
 
 @pytest.mark.parametrize('case', [(64, 64, 32, 48), (128, 128, 30, 64), (64, 96, 24, 32)], ids=str)
