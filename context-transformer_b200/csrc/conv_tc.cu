@@ -41,7 +41,8 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_THREADS = 448;        // 4 producer + TMA + MMA + 2 x 4 epilogue warps
 constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;     // 16 KB
-constexpr int A_GATHER = 0, A_TMA = 1, A_STEM = 2;
+constexpr int A_GATHER = 0, A_TMA = 1, A_STEM = 2, A_HALO = 3;
+constexpr int HALO_THREADS = 352;      // patch TMA + weight TMA + MMA + 2 x 4 epilogue warps
 
 struct TcParams {
   const void* in;
@@ -51,8 +52,10 @@ struct TcParams {
   int Cout, KH, KW, stride, pad_h, pad_w, dil, Ho, Wo, relu, relu_cend;
   int M, cin_blocks, nk;
   int bn, n_tiles_n, num_tiles;          // num_tiles counts tile GROUPS: `cluster` M-adjacent tiles of one N tile
+  int cluster_req;
   int m_tiles, cluster;                  // cluster = 2: CTA pairs, one 2-CTA MMA per K-step (opt-in)
   int a_mode, TW, TH, tiles_x, tiles_y;       // TMA mode: output patch TW x TH (<= 128 pixels), tiles per image
+  int PW, PH, a_slot, sa, sb;                 // HALO mode: staged patch (TW + 2 dil) x (TH + 2 dil) pixels, slot bytes, A / B ring depths
   int flat;                                   // TMA mode, 1x1 convs: the whole batch is one pixel row, tiles are 128-pixel runs
   int res_cstride, res_coffset, res_dtype;
   int is_bf16;
@@ -65,7 +68,7 @@ struct TcParams {
 
 // output pixel (image, linear pixel index, validity) of row r of M-tile mt
 __device__ __forceinline__ bool tile_row_pixel(const TcParams& p, int mt, int r, int& n_img, int& pix) {
-  if (p.a_mode == A_TMA && !p.flat) {
+  if ((p.a_mode == A_TMA && !p.flat) || p.a_mode == A_HALO) {
     const int per_img = p.tiles_x * p.tiles_y;
     n_img = mt / per_img;
     const int t = mt - n_img * per_img;
@@ -80,6 +83,132 @@ __device__ __forceinline__ bool tile_row_pixel(const TcParams& p, int mt, int r,
   n_img = m / HoWo;
   pix = m - n_img * HoWo;
   return m < p.M;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Epilogue role (shared by the kernels below): epilogue set `eset` (four warps, one per TMEM lane quarter) drains
+// accumulator `eset` = local tiles eset, eset + 2, ...: tcgen05.ld, + bias (BatchNorm folded) [+ residual] [ReLU]
+// [2x2 max-pool], convert, vectorised NHWC store(s).
+template <int CL>
+__device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_bias, uint32_t tmem_base, uint32_t accf0, uint32_t acce0,
+                                              int warp, int lane, uint32_t eset, int rank, int group0, int ngroups) {
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int BN = p.bn;
+    const int r = q * 32 + lane;
+    const bool bf16 = p.is_bf16 != 0;
+    uint32_t lt = eset;
+    for (int tile = group0 + (int)eset * ngroups; tile < p.num_tiles; tile += 2 * ngroups, lt += 2) {
+      const uint32_t buf = lt & 1;
+      const int mg = tile / p.n_tiles_n, n0 = (tile - mg * p.n_tiles_n) * BN, mt = mg * CL + rank;
+      int n_img, pix;
+      const bool row_ok = tile_row_pixel(p, mt, r, n_img, pix);
+      const long long m_lin = (long long)n_img * p.Ho * p.Wo + pix;
+      mbar_wait(accf0 + 8 * buf, (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int cb = 0; cb * 32 < BN; ++cb) {
+        const int c0 = n0 + cb * 32;
+        if (c0 >= p.Cout) break;                                   // warp-uniform
+        const int lim = BN - cb * 32;                              // columns of this chunk that belong to the tile
+        uint32_t v[32];
+        tmem_ld32(tmem_d + (uint32_t)(cb * 32), v);
+        tmem_ld_wait();
+        if (!row_ok && !p.pool2) continue;
+        if (p.fast_out) {
+          const CtxOutSeg& sg = p.segs.seg[0];
+          // pool2: row r of the tile is pixel (r / TW, r % TW) of a TW x 128/TW patch, TW = 16 or 8, so the 2 x 2 window
+          // partners are lanes ^1 (x) and ^TW (y) of the same warp; the even/even lane stores the pooled pixel
+          long long opix = pix;
+          bool store = row_ok;
+          if (p.pool2) {
+            const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
+            opix = (long long)(oy >> 1) * (p.Wo >> 1) + (ox >> 1);
+            store = row_ok && !(lane & (1 | p.TW));
+          }
+          uint16_t* out = reinterpret_cast<uint16_t*>(sg.ptr) + (long long)n_img * sg.img_stride + opix * sg.pix_stride + sg.ch_offset;
+          const uint16_t* res = (p.residual && row_ok) ? reinterpret_cast<const uint16_t*>(p.residual) + m_lin * p.res_cstride + p.res_coffset : nullptr;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            const int c = c0 + gq * 8;
+            if (c < p.Cout && gq * 8 < lim) {
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
+              float f[8] = {__uint_as_float(v[gq * 8 + 0]) + b0.x, __uint_as_float(v[gq * 8 + 1]) + b0.y,
+                            __uint_as_float(v[gq * 8 + 2]) + b0.z, __uint_as_float(v[gq * 8 + 3]) + b0.w,
+                            __uint_as_float(v[gq * 8 + 4]) + b1.x, __uint_as_float(v[gq * 8 + 5]) + b1.y,
+                            __uint_as_float(v[gq * 8 + 6]) + b1.z, __uint_as_float(v[gq * 8 + 7]) + b1.w};
+              if (res) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(res + c);
+                const float2 r0 = unpack2(rv.x, bf16), r1 = unpack2(rv.y, bf16), r2 = unpack2(rv.z, bf16), r3 = unpack2(rv.w, bf16);
+                f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y; f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+              }
+              if (p.relu && c < p.relu_cend) {           // relu_cend is a multiple of 8 on this path
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+              }
+              if (p.pool2) {                             // max is exact in any precision: pool the fp32 values
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 1));
+                  f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], p.TW));
+                }
+              }
+              if (store) {
+                uint4 o;
+                o.x = pack2(f[0], f[1], bf16); o.y = pack2(f[2], f[3], bf16); o.z = pack2(f[4], f[5], bf16); o.w = pack2(f[6], f[7], bf16);
+                *reinterpret_cast<uint4*>(out + c) = o;
+              }
+            }
+          }
+        } else if (!row_ok) {
+          continue;
+        } else if (p.vec_f32) {
+          // fp32 segments whose boundaries, strides and offsets are multiples of 4 channels (the fused heads)
+#pragma unroll
+          for (int gq = 0; gq < 8; ++gq) {
+            const int c = c0 + gq * 4;
+            if (c < p.Cout && gq * 4 < lim) {
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
+              float4 f = make_float4(__uint_as_float(v[gq * 4 + 0]) + b0.x, __uint_as_float(v[gq * 4 + 1]) + b0.y,
+                                     __uint_as_float(v[gq * 4 + 2]) + b0.z, __uint_as_float(v[gq * 4 + 3]) + b0.w);
+              if (p.relu && c < p.relu_cend) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+              int sgi = 0;
+              if (p.segs.nseg > 1 && c >= p.segs.seg[1].c_begin) sgi = 1;
+              if (p.segs.nseg > 2 && c >= p.segs.seg[2].c_begin) sgi = 2;
+              const CtxOutSeg& sg = p.segs.seg[sgi];
+              float* out = reinterpret_cast<float*>(sg.ptr) + (long long)n_img * sg.img_stride + (long long)pix * sg.pix_stride +
+                           sg.ch_offset + (c - sg.c_begin);
+              *reinterpret_cast<float4*>(out) = f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = c0 + j;
+            if (c < p.Cout && j < lim) {
+              float f = __uint_as_float(v[j]) + s_bias[c];
+              if (p.residual) f += load_as(p.residual, m_lin * p.res_cstride + p.res_coffset + c, p.res_dtype);
+              if (p.relu && c < p.relu_cend) f = fmaxf(f, 0.f);
+#pragma unroll
+              for (int sgi = 0; sgi < 3; ++sgi) {
+                if (sgi < p.segs.nseg && c >= p.segs.seg[sgi].c_begin && c < p.segs.seg[sgi].c_end) {
+                  const CtxOutSeg& sg = p.segs.seg[sgi];
+                  store_as(sg.ptr, (long long)n_img * sg.img_stride + (long long)pix * sg.pix_stride + sg.ch_offset + (c - sg.c_begin),
+                           sg.dtype, f);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CL == 2 && rank == 1) mbar_arrive_remote(acce0 + 8 * buf, 0);     // the leader's MMA owns the accumulator hand-off
+        else mbar_arrive(acce0 + 8 * buf);
+      }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -190,7 +319,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             __syncwarp();
             if (lane == 0) arrive_full(full0 + 8 * ((g - LOOKAHEAD) % S));
           }
-          if (++cc == p.cin_blocks) { cc = 0; ++tap; if (++kx == p.KW) { kx = 0; ++ky; } }
+          ++tap; if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; tap = 0; ++cc; } }      // taps innermost, then channel blocks
         }
       }
       cp_async_wait<0>();
@@ -273,20 +402,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         if (elect_one()) {
           // this CTA stages rows [rank * BN/CL, +BN/CL) of the weight tile (a 2-CTA MMA reads both halves)
           if (CL == 2 && rank == 1) {
-            tma_load_2d_2cta(sB + s * B_STAGE, &tmap_w, it * TC_BK, n0 + (BN / CL), full0 + 8 * s);
+            tma_load_2d_2cta(sB + s * B_STAGE, &tmap_w, ((ky * p.KW + kx) * p.cin_blocks + cc) * TC_BK, n0 + (BN / CL), full0 + 8 * s);
             if (p.a_mode == A_TMA)
               tma_load_4d_2cta(sA + s * TC_A_STAGE, &tmap_a, p.in_coffset + cc * TC_BK, x0 + kx * p.dil, y0 + ky * p.dil, n_img,
                                full0 + 8 * s);
           } else {
             mbar_arrive_expect_tx(full0 + 8 * s, tx_bytes);
-            tma_load_2d(sB + s * B_STAGE, &tmap_w, it * TC_BK, n0, full0 + 8 * s);
+            tma_load_2d(sB + s * B_STAGE, &tmap_w, ((ky * p.KW + kx) * p.cin_blocks + cc) * TC_BK, n0, full0 + 8 * s);
             if (p.a_mode == A_TMA)
               tma_load_4d(sA + s * TC_A_STAGE, &tmap_a, p.in_coffset + cc * TC_BK, x0 + kx * p.dil, y0 + ky * p.dil, n_img,
                           full0 + 8 * s);
           }
         }
         __syncwarp();
-        if (++cc == p.cin_blocks) { cc = 0; if (++kx == p.KW) { kx = 0; ++ky; } }
+        if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++cc; } }
       }
     }
   } else if (warp == 5) {
@@ -329,124 +458,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       }
     }
   } else {
-    // ================= epilogue =================
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;
-    const bool bf16 = p.is_bf16 != 0;
-    const uint32_t eset = (warp - 6) >> 2;        // epilogue set: drains accumulator `eset`, i.e. local tiles eset, eset+2, ...
-    uint32_t lt = eset;
-    for (int tile = group0 + (int)eset * ngroups; tile < p.num_tiles; tile += 2 * ngroups, lt += 2) {
-      const uint32_t buf = lt & 1;
-      const int mg = tile / p.n_tiles_n, n0 = (tile - mg * p.n_tiles_n) * BN, mt = mg * CL + rank;
-      int n_img, pix;
-      const bool row_ok = tile_row_pixel(p, mt, r, n_img, pix);
-      const long long m_lin = (long long)n_img * p.Ho * p.Wo + pix;
-      mbar_wait(accf0 + 8 * buf, (lt >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int cb = 0; cb * 32 < BN; ++cb) {
-        const int c0 = n0 + cb * 32;
-        if (c0 >= p.Cout) break;                                   // warp-uniform
-        const int lim = BN - cb * 32;                              // columns of this chunk that belong to the tile
-        uint32_t v[32];
-        tmem_ld32(tmem_d + (uint32_t)(cb * 32), v);
-        tmem_ld_wait();
-        if (!row_ok && !p.pool2) continue;
-        if (p.fast_out) {
-          const CtxOutSeg& sg = p.segs.seg[0];
-          // pool2: row r of the tile is pixel (r / 16, r % 16) of a 16 x 8 patch, so the 2 x 2 window partners are lanes
-          // ^1 (x) and ^16 (y) of the same warp; the even/even lane stores the pooled pixel
-          long long opix = pix;
-          bool store = row_ok;
-          if (p.pool2) {
-            const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
-            opix = (long long)(oy >> 1) * (p.Wo >> 1) + (ox >> 1);
-            store = row_ok && !(lane & 17);
-          }
-          uint16_t* out = reinterpret_cast<uint16_t*>(sg.ptr) + (long long)n_img * sg.img_stride + opix * sg.pix_stride + sg.ch_offset;
-          const uint16_t* res = (p.residual && row_ok) ? reinterpret_cast<const uint16_t*>(p.residual) + m_lin * p.res_cstride + p.res_coffset : nullptr;
-#pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
-            const int c = c0 + gq * 8;
-            if (c < p.Cout && gq * 8 < lim) {
-              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
-              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
-              float f[8] = {__uint_as_float(v[gq * 8 + 0]) + b0.x, __uint_as_float(v[gq * 8 + 1]) + b0.y,
-                            __uint_as_float(v[gq * 8 + 2]) + b0.z, __uint_as_float(v[gq * 8 + 3]) + b0.w,
-                            __uint_as_float(v[gq * 8 + 4]) + b1.x, __uint_as_float(v[gq * 8 + 5]) + b1.y,
-                            __uint_as_float(v[gq * 8 + 6]) + b1.z, __uint_as_float(v[gq * 8 + 7]) + b1.w};
-              if (res) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(res + c);
-                const float2 r0 = unpack2(rv.x, bf16), r1 = unpack2(rv.y, bf16), r2 = unpack2(rv.z, bf16), r3 = unpack2(rv.w, bf16);
-                f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y; f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
-              }
-              if (p.relu && c < p.relu_cend) {           // relu_cend is a multiple of 8 on this path
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-              }
-              if (p.pool2) {                             // max is exact in any precision: pool the fp32 values
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 1));
-                  f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 16));
-                }
-              }
-              if (store) {
-                uint4 o;
-                o.x = pack2(f[0], f[1], bf16); o.y = pack2(f[2], f[3], bf16); o.z = pack2(f[4], f[5], bf16); o.w = pack2(f[6], f[7], bf16);
-                *reinterpret_cast<uint4*>(out + c) = o;
-              }
-            }
-          }
-        } else if (!row_ok) {
-          continue;
-        } else if (p.vec_f32) {
-          // fp32 segments whose boundaries, strides and offsets are multiples of 4 channels (the fused heads)
-#pragma unroll
-          for (int gq = 0; gq < 8; ++gq) {
-            const int c = c0 + gq * 4;
-            if (c < p.Cout && gq * 4 < lim) {
-              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
-              float4 f = make_float4(__uint_as_float(v[gq * 4 + 0]) + b0.x, __uint_as_float(v[gq * 4 + 1]) + b0.y,
-                                     __uint_as_float(v[gq * 4 + 2]) + b0.z, __uint_as_float(v[gq * 4 + 3]) + b0.w);
-              if (p.relu && c < p.relu_cend) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
-              int sgi = 0;
-              if (p.segs.nseg > 1 && c >= p.segs.seg[1].c_begin) sgi = 1;
-              if (p.segs.nseg > 2 && c >= p.segs.seg[2].c_begin) sgi = 2;
-              const CtxOutSeg& sg = p.segs.seg[sgi];
-              float* out = reinterpret_cast<float*>(sg.ptr) + (long long)n_img * sg.img_stride + (long long)pix * sg.pix_stride +
-                           sg.ch_offset + (c - sg.c_begin);
-              *reinterpret_cast<float4*>(out) = f;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = c0 + j;
-            if (c < p.Cout && j < lim) {
-              float f = __uint_as_float(v[j]) + s_bias[c];
-              if (p.residual) f += load_as(p.residual, m_lin * p.res_cstride + p.res_coffset + c, p.res_dtype);
-              if (p.relu && c < p.relu_cend) f = fmaxf(f, 0.f);
-#pragma unroll
-              for (int sgi = 0; sgi < 3; ++sgi) {
-                if (sgi < p.segs.nseg && c >= p.segs.seg[sgi].c_begin && c < p.segs.seg[sgi].c_end) {
-                  const CtxOutSeg& sg = p.segs.seg[sgi];
-                  store_as(sg.ptr, (long long)n_img * sg.img_stride + (long long)pix * sg.pix_stride + sg.ch_offset + (c - sg.c_begin),
-                           sg.dtype, f);
-                }
-              }
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CL == 2 && rank == 1) mbar_arrive_remote(acce0 + 8 * buf, 0);     // the leader's MMA owns the accumulator hand-off
-        else mbar_arrive(acce0 + 8 * buf);
-      }
-    }
+    epilogue_role<CL>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 6) >> 2, rank, group0, ngroups);
   }
 
   tc_fence_before();
@@ -456,6 +468,134 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     tc_fence_after();
     if (CL == 2) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// HALO mode: 3x3 (dilated) stride-1 convs.  The output tile is an 8 x 16 pixel patch; its (8 + 2 dil) x (16 + 2 dil)
+// input neighbourhood of one 64-channel block is staged ONCE (one 4-D TMA box, zero-filled outside the image) and
+// the nine taps read it through nine shifted UMMA descriptors: with 8-pixel tile rows every 8-row group of the
+// M = 128 operand is one patch row, so tap (ky, kx) is the same SWIZZLE_128B K-major matrix started
+// (ky dil PW + kx dil) rows later with PW rows between groups (profiles/r1_mma_probe.txt: exact for any start row and
+// group stride).  Against the per-tap patches of mode TMA this cuts the activation traffic L2 -> shared memory about
+// 6x — those layers sit at the L2 bandwidth — and needs one A barrier per channel block instead of one per tap.
+// Weights stream through their own ring, one BN x 64 tile per (channel block, tap), released in commit groups.
+// Warp roles (352 threads): warp 0 patch producer (runs a full patch ring ahead: a patch load has several channel blocks
+// of MMA work to hide behind), warp 1 weight producer, warp 2 MMA issuer, warps 3-10 two epilogue sets.
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int BN = p.bn, SA = p.sa, SB = p.sb;
+  const uint32_t B_STAGE = (uint32_t)BN * TC_BK * 2;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base, sB = smem_base + (uint32_t)(SA * p.a_slot);
+  const uint32_t bars = sB + (uint32_t)SB * B_STAGE;
+  const uint32_t fullA0 = bars, emptyA0 = bars + 8 * SA, fullB0 = bars + 16 * SA, emptyB0 = fullB0 + 8 * SB, accf0 = emptyB0 + 8 * SB,
+                 acce0 = accf0 + 16, tmem_slot = acce0 + 16;
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group0 = blockIdx.x, ngroups = gridDim.x;
+  const uint32_t cmask = (1u << p.clog) - 1u;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_a);
+  if (warp == 1 && lane == 0) tma_prefetch_desc(&tmap_w);
+  if (warp == 2) {
+    if (lane == 0) {
+      for (int s = 0; s < SA; ++s) { mbar_init(fullA0 + 8 * s, 1); mbar_init(emptyA0 + 8 * s, 1); }
+      for (int s = 0; s < SB; ++s) { mbar_init(fullB0 + 8 * s, 1); mbar_init(emptyB0 + 8 * s, 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512); tmem_relinquish();
+  }
+  for (int c = threadIdx.x; c < ((p.Cout + 31) & ~31) + 32; c += HALO_THREADS) s_bias[c] = c < p.Cout ? p.bias[c] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  asm volatile("griddepcontrol.wait;" ::: "memory");          // programmatic dependent launch (see conv_tc_kernel)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int per_img = p.tiles_x * p.tiles_y;
+  if (warp == 0) {
+    // ================= patch producer =================
+    const uint32_t a_bytes = (uint32_t)(p.PW * p.PH * 128);
+    uint32_t qa = 0;
+    for (int tile = group0; tile < p.num_tiles; tile += ngroups) {
+      const int mt = tile / p.n_tiles_n;
+      const int n_img = mt / per_img, t = mt - n_img * per_img;
+      const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+      for (int cc = 0; cc < p.cin_blocks; ++cc, ++qa) {
+        const uint32_t slot = qa % (uint32_t)SA;
+        mbar_wait(emptyA0 + 8 * slot, ((qa / (uint32_t)SA) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(fullA0 + 8 * slot, a_bytes);
+          tma_load_4d(sA + slot * (uint32_t)p.a_slot, &tmap_a, p.in_coffset + cc * TC_BK, tx * p.TW - p.pad_w, ty * p.TH - p.pad_h, n_img,
+                      fullA0 + 8 * slot);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ================= weight producer =================
+    uint32_t gb = 0;
+    for (int tile = group0; tile < p.num_tiles; tile += ngroups) {
+      const int n0 = (tile % p.n_tiles_n) * BN;
+      for (int cc = 0; cc < p.cin_blocks; ++cc)
+        for (int tap = 0; tap < 9; ++tap, ++gb) {
+          const uint32_t s = gb % (uint32_t)SB;
+          if ((s & cmask) == 0) mbar_wait(emptyB0 + 8 * (s >> p.clog), ((gb / (uint32_t)SB) & 1u) ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(fullB0 + 8 * s, B_STAGE);
+            tma_load_2d(sB + s * B_STAGE, &tmap_w, (tap * p.cin_blocks + cc) * TC_BK, n0, fullB0 + 8 * s);
+          }
+          __syncwarp();
+        }
+    }
+  } else if (warp == 2) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = make_idesc_f16(p.is_bf16 != 0, TC_BM, BN);
+    const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)((uint32_t)(p.PW * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    const uint64_t bdesc0 = make_sw128_desc(sB);
+    uint32_t qa = 0, gb = 0, lt = 0;
+    for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++lt) {
+      const uint32_t buf = lt & 1;
+      mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * 256;
+      for (int cc = 0; cc < p.cin_blocks; ++cc, ++qa) {
+        const uint32_t slot = qa % (uint32_t)SA;
+        mbar_wait(fullA0 + 8 * slot, (qa / (uint32_t)SA) & 1u);
+        const uint32_t a_addr = sA + slot * (uint32_t)p.a_slot;
+        int ky = 0, kx = 0;
+        for (int tap = 0; tap < 9; ++tap, ++gb) {
+          const uint32_t s = gb % (uint32_t)SB;
+          mbar_wait(fullB0 + 8 * s, (gb / (uint32_t)SB) & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = desc_hi | (uint64_t)(((a_addr + (uint32_t)((ky * p.PW + kx) * p.dil * 128)) >> 4) & 0x3FFFu);
+            const uint64_t bd = bdesc0 + (uint64_t)((s * B_STAGE) >> 4);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) umma_f16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (cc | tap | k) ? 1u : 0u);
+            if ((s & cmask) == cmask) umma_commit(emptyB0 + 8 * (s >> p.clog));
+            if (tap == 8) umma_commit(emptyA0 + 8 * slot);
+          }
+          __syncwarp();
+          if (++kx == 3) { kx = 0; ++ky; }
+        }
+      }
+      if (elect_one()) umma_commit(accf0 + 8 * buf);
+      __syncwarp();
+    }
+  } else {
+    epilogue_role<1>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 3) >> 2, 0, group0, ngroups);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -548,6 +688,24 @@ static int launch_tc(const TcPlan* pl, cudaStream_t st) {
   return CTX_OK;
 }
 
+static int launch_halo(const TcPlan* pl, cudaStream_t st) {
+  CTX_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)pl->grid);
+  cfg.blockDim = dim3(HALO_THREADS);
+  cfg.dynamicSmemBytes = pl->smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  static const int pdl = [] { const char* e = getenv("CTX_CONV_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+  attr[0].val.programmaticStreamSerializationAllowed = pdl;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CTX_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_halo_kernel, pl->tmap_w, pl->tmap_a, pl->p));
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
 }  // namespace ctx
 
 using namespace ctx;
@@ -605,20 +763,25 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
   }
 
   // N tile: split Cout evenly over ceil(Cout / 256) tiles, rounded up to the UMMA granularity of 16
+  t.cluster_req = tune_cluster;
   t.n_tiles_n = std::max(cdiv(p->Cout, 256), std::min(tune_n, cdiv(p->Cout, 16)));
   t.bn = (cdiv(p->Cout, t.n_tiles_n) + 15) / 16 * 16;
   t.n_tiles_n = cdiv(p->Cout, t.bn);
 
   int tw = 0, th = 0;
-  if (p->in_nchw) t.a_mode = A_STEM;
+  const bool halo_ok = tma_eligible(p) && p->KH == 3 && p->KW == 3 && p->pad_h == p->pad_w && t.cluster_req != 2 &&
+                       (!p->pool2 || (((p->Ho | p->Wo) & 1) == 0 && p->Cin % 64 == 0));
+  if (tune_amode == 2 && halo_ok) { t.a_mode = A_HALO; tw = 8; th = 16; }
+  else if (p->in_nchw) t.a_mode = A_STEM;
   else if (tune_amode == 0 && !p->pool2) t.a_mode = A_GATHER;
   else if (flat_eligible(p)) { t.a_mode = A_TMA; tw = 128; th = 1; }
   else t.a_mode = choose_patch(p, &tw, &th, tune_amode == 1 ? 100000 : 150) ? A_TMA : A_GATHER;
   t.flat = t.a_mode == A_TMA && flat_eligible(p);
   t.TW = tw; t.TH = th;
-  t.tiles_x = t.a_mode == A_TMA ? (t.flat ? cdiv(t.M, 128) : cdiv(p->Wo, tw)) : 0;
-  t.tiles_y = t.a_mode == A_TMA ? (t.flat ? 1 : cdiv(p->Ho, th)) : 0;
-  const int m_tiles = t.a_mode == A_TMA ? (t.flat ? t.tiles_x : p->N * t.tiles_x * t.tiles_y) : cdiv(t.M, TC_BM);
+  const bool patches = t.a_mode == A_TMA || t.a_mode == A_HALO;
+  t.tiles_x = patches ? (t.flat ? cdiv(t.M, 128) : cdiv(p->Wo, tw)) : 0;
+  t.tiles_y = patches ? (t.flat ? 1 : cdiv(p->Ho, th)) : 0;
+  const int m_tiles = patches ? (t.flat ? t.tiles_x : p->N * t.tiles_x * t.tiles_y) : cdiv(t.M, TC_BM);
   t.m_tiles = m_tiles;
   {
     // CTA pairs (one tcgen05.mma.cta_group::2 spanning both SMs of a cluster of two, each CTA staging half of the weight
@@ -626,7 +789,7 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
     // (profiles/README.md), so they stay opt-in: CTX_CONV_CLUSTER=2.
     const char* e = getenv("CTX_CONV_CLUSTER");
     const bool want2 = tune_cluster ? tune_cluster == 2 : (e && e[0] == '2');
-    t.cluster = (want2 && m_tiles >= 2 && t.bn % 32 == 0 && t.bn >= 128) ? 2 : 1;
+    t.cluster = (want2 && m_tiles >= 2 && t.bn % 32 == 0 && t.bn >= 128 && t.a_mode != A_HALO) ? 2 : 1;
   }
   t.num_tiles = cdiv(m_tiles, t.cluster) * t.n_tiles_n;
   const int stage_bytes = TC_A_STAGE + (t.bn / t.cluster) * TC_BK * 2;
@@ -641,18 +804,38 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
     while (c > 1 && (pl->stages % c || c > pl->stages / 2)) c >>= 1;
     t.clog = c >= 4 ? 2 : (c >= 2 ? 1 : 0);
   }
-  pl->smem = (size_t)pl->stages * stage_bytes + 24 * pl->stages + 64 + 4 * (((size_t)p->Cout + 31) / 32 * 32 + 32) + 1024;
+  const size_t bias_bytes = 4 * (((size_t)p->Cout + 31) / 32 * 32 + 32);
+  if (t.a_mode == A_HALO) {
+    // weight ring first (8 slots if they fit in ~half of shared memory, a multiple of the commit group), the rest — up to
+    // 6 slots — is the patch ring: patch loads are the long-latency ones
+    t.PW = 8 + 2 * p->dil; t.PH = 16 + 2 * p->dil;
+    t.a_slot = (int)align_up((size_t)t.PW * t.PH * 128, 1024);
+    const size_t b_stage = (size_t)t.bn * TC_BK * 2, budget = 232448 - 1024 - bias_bytes - 8 * (2 * 6 + 2 * 8 + 4) - 64;
+    const int c = 1 << t.clog;
+    t.sa = 0;
+    for (int sb = 8; sb >= 3 && !t.sa; --sb) {
+      if (sb % c || sb < 2 * c || (size_t)sb * b_stage + 2 * (size_t)t.a_slot > budget) continue;
+      const int sa = (int)std::min<size_t>(6, (budget - (size_t)sb * b_stage) / t.a_slot);
+      if (sa >= 3 || sb <= 4) { t.sa = sa; t.sb = sb; }            // shrink the weight ring before going below 3 patches
+    }
+    if (!t.sa) { delete pl; set_error("conv_tc: HALO mode does not fit shared memory (dilation %d, tile width %d)", p->dil, t.bn); return CTX_ERR_UNSUPPORTED; }
+    pl->stages = t.sb;
+  }
+  pl->smem = t.a_mode == A_HALO ? (size_t)t.sa * t.a_slot + (size_t)t.sb * t.bn * TC_BK * 2 + 8 * (2 * t.sa + 2 * t.sb + 4) + 64 + bias_bytes + 1024 :
+             (size_t)pl->stages * stage_bytes + 24 * pl->stages + 64 + 4 * (((size_t)p->Cout + 31) / 32 * 32 + 32) + 1024;
   pl->grid = std::min(t.num_tiles, num_sms() / t.cluster) * t.cluster;
 
   // weights: [Cout_pad][KH*KW*Cin_pad] 16-bit, K-major; box = 64 (K) x BN (Cout), SWIZZLE_128B, OOB rows read as zero
   const unsigned long long ktot = (unsigned long long)t.nk * TC_BK;
   const unsigned long long cout_pad = (unsigned long long)((p->Cout + 15) / 16 * 16);
   int rc = encode_2d_sw128(&pl->tmap_w, p->weight, t.is_bf16 != 0, cout_pad, ktot, (unsigned)(t.bn / t.cluster));
+  if (!rc && t.a_mode == A_HALO)
+    rc = encode_nhwc_sw128(&pl->tmap_a, p->in, t.is_bf16 != 0, p->N, p->H, p->W, p->in_cstride, p->in_coffset + p->Cin, (unsigned)t.PW, (unsigned)t.PH);
   if (!rc && t.a_mode == A_TMA)
     rc = t.flat ? encode_nhwc_sw128(&pl->tmap_a, p->in, t.is_bf16 != 0, 1, 1, t.M, p->in_cstride, p->in_coffset + p->Cin, 128u, 1u)
                 : encode_nhwc_sw128(&pl->tmap_a, p->in, t.is_bf16 != 0, p->N, p->H, p->W, p->in_cstride, p->in_coffset + p->Cin, (unsigned)tw, (unsigned)th);
   if (rc) { delete pl; return rc; }
-  if (t.pool2 && !(t.a_mode == A_TMA && t.TW == 16 && t.fast_out)) {
+  if (t.pool2 && !(((t.a_mode == A_TMA && t.TW == 16) || t.a_mode == A_HALO) && t.fast_out)) {
     delete pl;
     set_error("conv_tc: fused pooling needs the TMA patch mode and a single 16-bit output segment");
     return CTX_ERR_UNSUPPORTED;
@@ -680,6 +863,7 @@ extern "C" int ctx_conv2d_tc_plan_run(void* plan, void* stream) {
   CTX_REQUIRE(plan, "ctx_conv2d_tc_plan_run: null plan");
   const TcPlan* pl = (const TcPlan*)plan;
   cudaStream_t st = (cudaStream_t)stream;
+  if (pl->p.a_mode == A_HALO) return launch_halo(pl, st);
   if (pl->p.cluster == 2) {
     if (pl->stages == 8) return launch_tc<8, 2>(pl, st);
     if (pl->stages == 6) return launch_tc<6, 2>(pl, st);

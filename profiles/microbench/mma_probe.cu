@@ -15,16 +15,24 @@ using namespace ctx;
 
 namespace ctx { void set_error(const char*, ...) {} void count_launch(int) {} }
 
+// busy poll (mbarrier.test_wait never suspends the thread): the probe measures arrival latency itself
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
 // ---- (1) + (2): timing -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) timing_kernel(long long* out, int N) {
+__global__ void __launch_bounds__(128, 1) timing_kernel(long long* out, int N, int shift_rows, int group_rows) {
   extern __shared__ uint8_t raw[];
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
-  const uint32_t sA = base, sB = base + 16384, bars = base + 16384 + 32768, slot = bars + 256;
-  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(raw + (base - smem_u32(raw)))[i] = 0u;
+  const uint32_t sA = base, sB = base + 49152, bars = base + 49152 + 32768, slot = bars + 256;
+  for (int i = threadIdx.x; i < (49152 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(raw + (base - smem_u32(raw)))[i] = 0u;
   if (threadIdx.x < 32) {
     if (threadIdx.x == 0) { for (int b = 0; b < 32; ++b) mbar_init(bars + 8 * b, 1); fence_barrier_init(); }
     __syncwarp();
@@ -38,7 +46,7 @@ __global__ void __launch_bounds__(128, 1) timing_kernel(long long* out, int N) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(slot));
   if (threadIdx.x == 0) {
     const uint32_t idesc = make_idesc_f16(true, 128, N);
-    const uint64_t ad = desc_sw128(sA, 1024), bd = desc_sw128(sB, 1024);
+    const uint64_t ad = desc_sw128(sA + shift_rows * 128, group_rows * 128), bd = desc_sw128(sB, 1024);
     int o = 0, bar = 0;
     uint32_t ph[32];
     for (int b = 0; b < 32; ++b) ph[b] = 0;
@@ -132,18 +140,21 @@ int main() {
   long long* d_out; float* d_f;
   cudaMalloc(&d_out, 4096 * sizeof(long long));
   cudaMalloc(&d_f, 128 * 64 * sizeof(float));
-  cudaFuncSetAttribute(timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   cudaFuncSetAttribute(window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int Ns[3] = {64, 128, 256};
+  const int variants[6][2] = {{0, 8}, {1, 8}, {8, 8}, {0, 10}, {11, 10}, {0, 16}};      // {start row, rows between 8-row groups}
+  for (int v = 0; v < 6; ++v)
   for (int n = 0; n < 3; ++n) {
     cudaMemset(d_out, 0, 4096 * sizeof(long long));
-    timing_kernel<<<1, 128, 64 * 1024>>>(d_out, Ns[n]);
+    timing_kernel<<<1, 128, 96 * 1024>>>(d_out, Ns[n], variants[v][0], variants[v][1]);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("timing N=%d failed: %s\n", Ns[n], cudaGetErrorString(e)); return 1; }
     std::vector<long long> h(4096);
     cudaMemcpy(h.data(), d_out, 4096 * sizeof(long long), cudaMemcpyDeviceToHost);
-    printf("== N = %d (floor %d clk / MMA)\n", Ns[n], Ns[n] / 2);
+    printf("== N = %d (floor %d clk / MMA), A window: start row %d, 8-row groups %d rows apart\n", Ns[n], Ns[n] / 2, variants[v][0], variants[v][1]);
     for (int o = 0; h[o] != 0; o += 3) {
+      if (v > 0 && !(h[o] == 144 || h[o] == -8)) continue;
       if (h[o] > 0) printf("  %3lld MMAs + commit: issue %5lld clk, issue->arrival %6lld clk (%.1f clk/MMA)\n", h[o], h[o + 1], h[o + 2], (double)h[o + 2] / h[o]);
       else printf("  ring of %lld: %lld groups of {4 MMA + commit}: %lld clk = %.1f clk/group\n", -h[o], h[o + 1], h[o + 2], (double)h[o + 2] / h[o + 1]);
     }

@@ -108,7 +108,8 @@ def test_conv_cta_pair_mode(case, monkeypatch):
 
 @pytest.mark.parametrize('case', [(128, 128, 3, 1, 1, 1, 38, 38), (256, 256, 3, 1, 2, 2, 19, 19), (96, 128, (3, 1), 1, (1, 0), 1, 38, 38),
                                   (512, 320, 1, 1, 0, 1, 19, 19), (192, 256, 3, 1, 1, 1, 10, 10), (64, 64, 3, 1, 1, 1, 75, 75),
-                                  (128, 256, 3, 1, 1, 1, 5, 5), (1024, 264, 1, 1, 0, 1, 7, 9)], ids=str)
+                                  (128, 256, 3, 1, 1, 1, 5, 5), (1024, 264, 1, 1, 0, 1, 7, 9), (128, 128, 3, 1, 3, 3, 38, 38),
+                                  (64, 128, 3, 1, 1, 1, 40, 24)], ids=str)
 def test_conv_every_tiling_is_bit_identical(case):
     """ctx_conv2d_tc_plan_create_tuned: N-tile count, CTA pairs and the A-operand mode (TMA pixel patches of any
     TW x TH <= 128 shape, flat 128-pixel runs for 1x1 convs, im2col gather) only change the tiling, never a bit of the result."""
@@ -133,7 +134,7 @@ def test_conv_every_tiling_is_bit_identical(case):
     seen = set()
     for n, cg in ((0, 0), (2, 1), (3, 2), (5, 4), (0, 4), (0, 1)):
         for cl in (1, 2):
-            for amode in (-1, 0, 1):
+            for amode in (-1, 0, 1, 2):
                 plan = C.c_void_p()
                 _lib.check(L.ctx_conv2d_tc_plan_create_tuned(C.byref(p), n, cl, amode, cg, C.byref(plan)), 'plan_create_tuned')
                 info = (C.c_int * 8)()
@@ -147,7 +148,8 @@ def test_conv_every_tiling_is_bit_identical(case):
                     assert torch.equal(out.tensor(), ref), key
                 L.ctx_conv2d_tc_plan_destroy(plan)
     assert len(seen) >= 4
-    assert {k[3] for k in seen} == {0, 1}                         # both A-operand modes were exercised
+    assert {k[3] for k in seen} >= {0, 1}                         # gather and TMA-patch A-operand modes were exercised
+    assert (3 in {k[3] for k in seen}) == (kh == 3 and kw == 3)   # ... and the halo mode for every 3x3 case
     assert len({k[4] for k in seen}) >= 2                         # ... and more than one commit-group size
 
 
