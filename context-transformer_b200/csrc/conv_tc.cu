@@ -55,6 +55,7 @@ struct TcParams {
   int cluster_req;
   int m_tiles, cluster;                  // cluster = 2: CTA pairs, one 2-CTA MMA per K-step (opt-in)
   int a_mode, TW, TH, tiles_x, tiles_y;       // TMA mode: output patch TW x TH (<= 128 pixels), tiles per image
+  int tps;                                    // HALO mode: filter taps per weight-ring slot (1 or 3)
   int PW, PH, a_slot, sa, sb;                 // HALO mode: staged patch (TW + 2 dil) x (TH + 2 dil) pixels, slot bytes, A / B ring depths
   int flat;                                   // TMA mode, 1x1 convs: the whole batch is one pixel row, tiles are 128-pixel runs
   int res_cstride, res_coffset, res_dtype;
@@ -420,43 +421,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
   } else if (warp == 5) {
     // ================= MMA issuer =================
-    // whole warp converged; one elected lane issues (see elect_one).  Pair mode: only the leader CTA (rank 0) issues —
+    // Pair mode: only the leader CTA (rank 0) issues —
     // one tcgen05.mma.cta_group::2 drives both SMs' tensor cores (M = 256: 128 rows from each CTA, B halves from each
     // CTA's shared memory); the peer's producers and TMA loads signal the leader's full barriers directly.
-    if (!(CL == 2 && rank == 1)) {
+    // The issue rate of this one thread bounds the kernel whenever a K-step holds little math (narrow N tiles: a
+    // tcgen05.mma occupies the issuing thread ~48 clk, every other instruction of the loop adds to that —
+    // profiles/r1_mma_probe.txt), so a single elected lane runs the whole role with ring slot, phase and descriptors
+    // tracked incrementally.
+    if (!(CL == 2 && rank == 1) && elect_one()) {
       const uint32_t idesc = make_idesc_f16(p.is_bf16 != 0, TC_BM * CL, BN);
       const uint64_t adesc0 = make_sw128_desc(sA), bdesc0 = make_sw128_desc(sB);
-      uint32_t g = 0, lt = 0;
+      const uint64_t a_step = (uint64_t)(TC_A_STAGE >> 4), b_step = (uint64_t)(B_STAGE >> 4);
+      uint64_t ad = adesc0, bd = bdesc0;
+      uint32_t s = 0, ph = 0, lt = 0;
       for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++lt) {
         const uint32_t buf = lt & 1;
         mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);            // (pair mode: both CTAs' epilogues) have drained it
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * 256;
-        for (int it = 0; it < nk; ++it, ++g) {
-          const uint32_t s = g % S;
-          mbar_wait(full0 + 8 * s, (g / S) & 1);                   // pair mode: arrivals come from both CTAs
+        for (int it = 0; it < nk; ++it) {
+          mbar_wait(full0 + 8 * s, ph);                            // pair mode: arrivals come from both CTAs
           tc_fence_after();
-          if (elect_one()) {
-            const uint64_t ad = adesc0 + (uint64_t)((s * TC_A_STAGE) >> 4), bd = bdesc0 + (uint64_t)((s * B_STAGE) >> 4);
-            if (CL == 2) {
+          if (CL == 2) {
 #pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k) umma_f16_2cta(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (it | k) ? 1u : 0u);
-              if ((s & cmask) == cmask) umma_commit_2cta(empty0 + 8 * (s >> p.clog), (uint16_t)3);
-            } else {
+            for (int k = 0; k < TC_BK / 16; ++k) umma_f16_2cta(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (it | k) ? 1u : 0u);
+            if ((s & cmask) == cmask) umma_commit_2cta(empty0 + 8 * (s >> p.clog), (uint16_t)3);
+          } else {
 #pragma unroll
-              for (int k = 0; k < TC_BK / 16; ++k) umma_f16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (it | k) ? 1u : 0u);
-              if ((s & cmask) == cmask) umma_commit(empty0 + 8 * (s >> p.clog));
-            }
+            for (int k = 0; k < TC_BK / 16; ++k) umma_f16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (it | k) ? 1u : 0u);
+            if ((s & cmask) == cmask) umma_commit(empty0 + 8 * (s >> p.clog));
           }
-          __syncwarp();
+          ad += a_step; bd += b_step;
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; ad = adesc0; bd = bdesc0; }
         }
-        if (elect_one()) {
-          if (CL == 2) umma_commit_2cta(accf0 + 8 * buf, (uint16_t)3);
-          else umma_commit(accf0 + 8 * buf);
-        }
-        __syncwarp();
+        if (CL == 2) umma_commit_2cta(accf0 + 8 * buf, (uint16_t)3);
+        else umma_commit(accf0 + 8 * buf);
       }
     }
+    __syncwarp();
   } else {
     epilogue_role<CL>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 6) >> 2, rank, group0, ngroups);
   }
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int BN = p.bn, SA = p.sa, SB = p.sb;
-  const uint32_t B_STAGE = (uint32_t)BN * TC_BK * 2;
+  const uint32_t B_TAP = (uint32_t)BN * TC_BK * 2, B_STAGE = B_TAP * (uint32_t)p.tps;     // a slot holds the weight tiles of `tps` taps
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base, sB = smem_base + (uint32_t)(SA * p.a_slot);
   const uint32_t bars = sB + (uint32_t)SB * B_STAGE;
@@ -518,77 +520,88 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // Each of the three issue roles is one elected lane; ring slots and phases are tracked incrementally (no division in
+  // the loops: the issue rate of these threads is the kernel's pace).
   const int per_img = p.tiles_x * p.tiles_y;
   if (warp == 0) {
     // ================= patch producer =================
-    const uint32_t a_bytes = (uint32_t)(p.PW * p.PH * 128);
-    uint32_t qa = 0;
-    for (int tile = group0; tile < p.num_tiles; tile += ngroups) {
-      const int mt = tile / p.n_tiles_n;
-      const int n_img = mt / per_img, t = mt - n_img * per_img;
-      const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-      for (int cc = 0; cc < p.cin_blocks; ++cc, ++qa) {
-        const uint32_t slot = qa % (uint32_t)SA;
-        mbar_wait(emptyA0 + 8 * slot, ((qa / (uint32_t)SA) & 1u) ^ 1u);
-        if (elect_one()) {
+    if (elect_one()) {
+      const uint32_t a_bytes = (uint32_t)(p.PW * p.PH * 128);
+      uint32_t slot = 0, ph = 1, dst = sA;
+      for (int tile = group0; tile < p.num_tiles; tile += ngroups) {
+        const int mt = tile / p.n_tiles_n;
+        const int n_img = mt / per_img, t = mt - n_img * per_img;
+        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+        const int x0 = tx * p.TW - p.pad_w, y0 = ty * p.TH - p.pad_h;
+        for (int cc = 0; cc < p.cin_blocks; ++cc) {
+          mbar_wait(emptyA0 + 8 * slot, ph);
           mbar_arrive_expect_tx(fullA0 + 8 * slot, a_bytes);
-          tma_load_4d(sA + slot * (uint32_t)p.a_slot, &tmap_a, p.in_coffset + cc * TC_BK, tx * p.TW - p.pad_w, ty * p.TH - p.pad_h, n_img,
-                      fullA0 + 8 * slot);
+          tma_load_4d(dst, &tmap_a, p.in_coffset + cc * TC_BK, x0, y0, n_img, fullA0 + 8 * slot);
+          dst += (uint32_t)p.a_slot;
+          if (++slot == (uint32_t)SA) { slot = 0; ph ^= 1u; dst = sA; }
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ================= weight producer =================
-    uint32_t gb = 0;
-    for (int tile = group0; tile < p.num_tiles; tile += ngroups) {
-      const int n0 = (tile % p.n_tiles_n) * BN;
-      for (int cc = 0; cc < p.cin_blocks; ++cc)
-        for (int tap = 0; tap < 9; ++tap, ++gb) {
-          const uint32_t s = gb % (uint32_t)SB;
-          if ((s & cmask) == 0) mbar_wait(emptyB0 + 8 * (s >> p.clog), ((gb / (uint32_t)SB) & 1u) ^ 1u);
-          if (elect_one()) {
+    if (elect_one()) {
+      uint32_t s = 0, ph = 1, dst = sB;
+      for (int tile = group0; tile < p.num_tiles; tile += ngroups) {
+        const int n0 = (tile % p.n_tiles_n) * BN;
+        for (int cc = 0; cc < p.cin_blocks; ++cc) {
+          int kcoord = cc * TC_BK;                              // weight K index of (tap, cc) = (tap * cin_blocks + cc) * 64
+          for (int tap0 = 0; tap0 < 9; tap0 += p.tps) {
+            if ((s & cmask) == 0) mbar_wait(emptyB0 + 8 * (s >> p.clog), ph);
             mbar_arrive_expect_tx(fullB0 + 8 * s, B_STAGE);
-            tma_load_2d(sB + s * B_STAGE, &tmap_w, (tap * p.cin_blocks + cc) * TC_BK, n0, fullB0 + 8 * s);
+            for (int t = 0; t < p.tps; ++t, kcoord += p.cin_blocks * TC_BK) tma_load_2d(dst + t * B_TAP, &tmap_w, kcoord, n0, fullB0 + 8 * s);
+            dst += B_STAGE;
+            if (++s == (uint32_t)SB) { s = 0; ph ^= 1u; dst = sB; }
           }
-          __syncwarp();
-        }
-    }
-  } else if (warp == 2) {
-    // ================= MMA issuer =================
-    const uint32_t idesc = make_idesc_f16(p.is_bf16 != 0, TC_BM, BN);
-    const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)((uint32_t)(p.PW * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-    const uint64_t bdesc0 = make_sw128_desc(sB);
-    uint32_t qa = 0, gb = 0, lt = 0;
-    for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++lt) {
-      const uint32_t buf = lt & 1;
-      mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + buf * 256;
-      for (int cc = 0; cc < p.cin_blocks; ++cc, ++qa) {
-        const uint32_t slot = qa % (uint32_t)SA;
-        mbar_wait(fullA0 + 8 * slot, (qa / (uint32_t)SA) & 1u);
-        const uint32_t a_addr = sA + slot * (uint32_t)p.a_slot;
-        int ky = 0, kx = 0;
-        for (int tap = 0; tap < 9; ++tap, ++gb) {
-          const uint32_t s = gb % (uint32_t)SB;
-          mbar_wait(fullB0 + 8 * s, (gb / (uint32_t)SB) & 1u);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t ad = desc_hi | (uint64_t)(((a_addr + (uint32_t)((ky * p.PW + kx) * p.dil * 128)) >> 4) & 0x3FFFu);
-            const uint64_t bd = bdesc0 + (uint64_t)((s * B_STAGE) >> 4);
-#pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) umma_f16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (cc | tap | k) ? 1u : 0u);
-            if ((s & cmask) == cmask) umma_commit(emptyB0 + 8 * (s >> p.clog));
-            if (tap == 8) umma_commit(emptyA0 + 8 * slot);
-          }
-          __syncwarp();
-          if (++kx == 3) { kx = 0; ++ky; }
         }
       }
-      if (elect_one()) umma_commit(accf0 + 8 * buf);
-      __syncwarp();
     }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ================= MMA issuer =================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(p.is_bf16 != 0, TC_BM, BN);
+      const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)((uint32_t)(p.PW * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint64_t bdesc0 = make_sw128_desc(sB), b_step = (uint64_t)(B_STAGE >> 4), b_tap = (uint64_t)(B_TAP >> 4);
+      const uint32_t row_step = (uint32_t)(p.dil * 128) >> 4, line_step = (uint32_t)((p.PW - 2) * p.dil * 128) >> 4;   // descriptor units (16 B)
+      uint32_t slot = 0, pha = 0, s = 0, phb = 0, lt = 0, a_lo = (sA >> 4) & 0x3FFFu;
+      uint64_t bd = bdesc0;
+      for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++lt) {
+        const uint32_t buf = lt & 1;
+        mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * 256;
+        for (int cc = 0; cc < p.cin_blocks; ++cc) {
+          mbar_wait(fullA0 + 8 * slot, pha);
+          uint32_t a_tap = a_lo;                                // window of tap (0, 0); +dil rows per kx, +dil patch lines per ky
+          int kx = 0;
+          for (int tap0 = 0; tap0 < 9; tap0 += p.tps) {
+            mbar_wait(fullB0 + 8 * s, phb);
+            tc_fence_after();
+            uint64_t bt = bd;
+            for (int t = 0; t < p.tps; ++t, bt += b_tap) {
+              const uint64_t ad = desc_hi | (uint64_t)a_tap;
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) umma_f16(tmem_d, ad + 2 * k, bt + 2 * k, idesc, (cc | tap0 | t | k) ? 1u : 0u);
+              if (++kx == 3) { kx = 0; a_tap += line_step; } else a_tap += row_step;
+            }
+            if ((s & cmask) == cmask) umma_commit(emptyB0 + 8 * (s >> p.clog));
+            bd += b_step;
+            if (++s == (uint32_t)SB) { s = 0; phb ^= 1u; bd = bdesc0; }
+          }
+          umma_commit(emptyA0 + 8 * slot);
+          a_lo += (uint32_t)p.a_slot >> 4;
+          if (++slot == (uint32_t)SA) { slot = 0; pha ^= 1u; a_lo = (sA >> 4) & 0x3FFFu; }
+        }
+        umma_commit(accf0 + 8 * buf);
+      }
+    }
+    __syncwarp();
   } else {
     epilogue_role<1>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 3) >> 2, 0, group0, ngroups);
   }
@@ -810,7 +823,11 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
     // 6 slots — is the patch ring: patch loads are the long-latency ones
     t.PW = 8 + 2 * p->dil; t.PH = 16 + 2 * p->dil;
     t.a_slot = (int)align_up((size_t)t.PW * t.PH * 128, 1024);
-    const size_t b_stage = (size_t)t.bn * TC_BK * 2, budget = 232448 - 1024 - bias_bytes - 8 * (2 * 6 + 2 * 8 + 4) - 64;
+    // narrow tiles: a slot holds the three taps of a filter row and is released by its own commit — twelve MMAs per
+    // barrier wait instead of four (the MMA thread's issue loop is the pace there); an explicit commit group keeps 1 tap
+    t.tps = (t.bn <= 128 && tune_commit <= 0) ? 3 : 1;
+    if (t.tps == 3) t.clog = 0;
+    const size_t b_stage = (size_t)t.tps * t.bn * TC_BK * 2, budget = 232448 - 1024 - bias_bytes - 8 * (2 * 6 + 2 * 8 + 4) - 64;
     const int c = 1 << t.clog;
     t.sa = 0;
     for (int sb = 8; sb >= 3 && !t.sa; --sb) {
@@ -821,7 +838,7 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
     if (!t.sa) { delete pl; set_error("conv_tc: HALO mode does not fit shared memory (dilation %d, tile width %d)", p->dil, t.bn); return CTX_ERR_UNSUPPORTED; }
     pl->stages = t.sb;
   }
-  pl->smem = t.a_mode == A_HALO ? (size_t)t.sa * t.a_slot + (size_t)t.sb * t.bn * TC_BK * 2 + 8 * (2 * t.sa + 2 * t.sb + 4) + 64 + bias_bytes + 1024 :
+  pl->smem = t.a_mode == A_HALO ? (size_t)t.sa * t.a_slot + (size_t)t.sb * t.tps * t.bn * TC_BK * 2 + 8 * (2 * t.sa + 2 * t.sb + 4) + 64 + bias_bytes + 1024 :
              (size_t)pl->stages * stage_bytes + 24 * pl->stages + 64 + 4 * (((size_t)p->Cout + 31) / 32 * 32 + 32) + 1024;
   pl->grid = std::min(t.num_tiles, num_sms() / t.cluster) * t.cluster;
 
@@ -854,7 +871,7 @@ extern "C" int ctx_conv2d_tc_plan_info(void* plan, int* info8) {
   CTX_REQUIRE(plan && info8, "ctx_conv2d_tc_plan_info: null argument");
   const TcPlan* pl = (const TcPlan*)plan;
   int* info6 = info8;
-  info8[6] = 1 << pl->p.clog; info8[7] = pl->p.TW * 1000 + pl->p.TH;
+  info8[6] = pl->p.a_mode == A_HALO && pl->p.tps == 3 ? 3 : 1 << pl->p.clog; info8[7] = pl->p.TW * 1000 + pl->p.TH;
   info6[0] = pl->p.bn; info6[1] = pl->p.n_tiles_n; info6[2] = pl->p.cluster; info6[3] = pl->p.a_mode; info6[4] = pl->stages; info6[5] = pl->grid;
   return CTX_OK;
 }

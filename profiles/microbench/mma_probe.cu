@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128, 1) timing_kernel(long long* out, int N, i
         const long long t2 = clock64();
         if (rep == 1) { out[o++] = counts[c]; out[o++] = t1 - t0; out[o++] = t2 - t0; }
       }
-    // (2) G groups of {4 MMAs + commit} issued back to back on a ring of 8 barriers (waiting for group g - 8 before
+    // (2) G groups of {n MMAs + commit} issued back to back on a ring of `ring` barriers (waiting for group g - ring before
     //     issuing g, like the conv kernel's smem ring): clocks per group in steady state
     for (int ring = 2; ring <= 8; ring *= 2) {
       const int G = 64;
@@ -76,6 +76,61 @@ __global__ void __launch_bounds__(128, 1) timing_kernel(long long* out, int N, i
       for (int b = 0; b < ring; ++b) { mbar_spin(bars + 8 * b, ph[b]); ph[b] ^= 1u; }
       const long long t1 = clock64();
       out[o++] = -ring; out[o++] = G; out[o++] = t1 - t0;
+    }
+    // (2b) the same with n = 8, 12, 16, 36 MMAs per commit (ring of 8), and 36 MMAs followed by two commits
+    const int per[5] = {8, 12, 16, 36, 36};
+    for (int c = 0; c < 5; ++c) {
+      const int G = 32, ring = 8;
+      const long long t0 = clock64();
+      for (int g = 0; g < G; ++g) {
+        const int b = g % ring;
+        if (g >= ring) { mbar_spin(bars + 8 * b, ph[b]); ph[b] ^= 1u; if (c == 4) { mbar_spin(bars + 8 * (b + 8), ph[b + 8]); ph[b + 8] ^= 1u; } }
+        for (int i = 0; i < per[c]; ++i) umma_f16(tmem, ad + 2 * (i & 3), bd + 2 * (i & 3), idesc, (g | i) ? 1u : 0u);
+        umma_commit(bars + 8 * b);
+        if (c == 4) umma_commit(bars + 8 * (b + 8));
+      }
+      for (int b = 0; b < ring; ++b) { mbar_spin(bars + 8 * b, ph[b]); ph[b] ^= 1u; if (c == 4) { mbar_spin(bars + 8 * (b + 8), ph[b + 8]); ph[b + 8] ^= 1u; } }
+      const long long t1 = clock64();
+      out[o++] = -(1000 + per[c] + (c == 4 ? 100 : 0)); out[o++] = G; out[o++] = t1 - t0;
+    }
+    // (2c) variations of 32 x 36 MMAs: V1 one commit at the very end; V2 commit per group, no barrier polling inside the
+    //      loop; V3 commit per group, groups alternate between two accumulators; V4 commit per group to an unused barrier
+    for (int v = 1; v <= 4; ++v) {
+      const int G = 32;
+      const long long t0 = clock64();
+      for (int g = 0; g < G; ++g) {
+        const uint32_t d = tmem + ((v == 3 && (g & 1)) ? 256u : 0u);
+        for (int i = 0; i < 36; ++i) umma_f16(d, ad + 2 * (i & 3), bd + 2 * (i & 3), idesc, (g | i) ? 1u : 0u);
+        if (v == 2 || v == 3) umma_commit(bars + 8 * (16 + (g & 7)));
+        if (v == 4) umma_commit(bars + 8 * 31);
+      }
+      umma_commit(bars + 8 * 30);
+      mbar_spin(bars + 8 * 30, ph[30]); ph[30] ^= 1u;
+      const long long t1 = clock64();
+      out[o++] = -(2000 + v); out[o++] = G; out[o++] = t1 - t0;
+    }
+    // (2d) 288 groups of 4 MMAs: V5 + commit; V6 + commit + one mbarrier.test_wait on a long-completed barrier; V7 + commit +
+    //      a volatile shared-memory load; V8 test_wait only (no commit)
+    mbar_arrive(bars + 8 * 29);                                  // barrier 29: phase 0 complete from here on
+    for (int v = 5; v <= 8; ++v) {
+      const int G = 288;
+      uint32_t sink = 0;
+      const long long t0 = clock64();
+      for (int g = 0; g < G; ++g) {
+        for (int i = 0; i < 4; ++i) umma_f16(tmem, ad + 2 * i, bd + 2 * i, idesc, (g | i) ? 1u : 0u);
+        if (v != 8) umma_commit(bars + 8 * (16 + (g & 7)));
+        if (v == 6 || v == 8) {
+          uint32_t done;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done) : "r"(bars + 8 * 29), "r"(0) : "memory");
+          sink += done;
+        }
+        if (v == 7) { uint32_t x; asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(x) : "r"(bars + 8 * 29) : "memory"); sink += x; }
+      }
+      umma_commit(bars + 8 * 30);
+      mbar_spin(bars + 8 * 30, ph[30]); ph[30] ^= 1u;
+      const long long t1 = clock64();
+      out[o++] = -(2000 + v); out[o++] = G; out[o++] = (t1 - t0) * 9 + (sink == 12345u);      // x9: printed per 36 MMAs
     }
     out[o++] = 0;
   }
@@ -155,8 +210,11 @@ int main() {
     printf("== N = %d (floor %d clk / MMA), A window: start row %d, 8-row groups %d rows apart\n", Ns[n], Ns[n] / 2, variants[v][0], variants[v][1]);
     for (int o = 0; h[o] != 0; o += 3) {
       if (v > 0 && !(h[o] == 144 || h[o] == -8)) continue;
+      if (v > 0 && h[o] <= -1000) continue;
       if (h[o] > 0) printf("  %3lld MMAs + commit: issue %5lld clk, issue->arrival %6lld clk (%.1f clk/MMA)\n", h[o], h[o + 1], h[o + 2], (double)h[o + 2] / h[o]);
-      else printf("  ring of %lld: %lld groups of {4 MMA + commit}: %lld clk = %.1f clk/group\n", -h[o], h[o + 1], h[o + 2], (double)h[o + 2] / h[o + 1]);
+      else if (h[o] <= -2000) printf("  variation V%lld: %lld groups: %.1f clk/MMA\n", -h[o] - 2000, h[o + 1], (double)h[o + 2] / (36.0 * h[o + 1]));
+      else if (h[o] > -1000) printf("  ring of %lld: %lld groups of {4 MMA + commit}: %lld clk = %.1f clk/group\n", -h[o], h[o + 1], h[o + 2], (double)h[o + 2] / h[o + 1]);
+      else printf("  ring of 8: %lld groups of {%lld MMA + %d commit}: %lld clk = %.1f clk/group\n", h[o + 1], (-h[o] - 1000) % 100, -h[o] - 1000 >= 100 ? 2 : 1, h[o + 2], (double)h[o + 2] / h[o + 1]);
     }
   }
   // (3)
