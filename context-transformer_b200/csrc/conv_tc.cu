@@ -335,7 +335,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       const float* img = reinterpret_cast<const float*>(p.in);
       const bool bf16 = p.is_bf16 != 0;
       uint32_t g = 0;
-      // the 27 loads of the NEXT tile are issued before the current tile is packed and stored (software pipelining:
+      // the 27 loads of the tile after next are issued before the current tile is packed and stored (software pipelining:
       // with one pixel per thread there is no other memory-level parallelism in this role)
       auto load_patch = [&](int tile, float (&v)[28]) {
 #pragma unroll
@@ -357,13 +357,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             }
         }
       };
-      float vnext[28];
+      float vnext[28], vnext2[28];                // two tiles of loads in flight: a tile period is shorter than the load latency
       load_patch(group0, vnext);
+      load_patch(group0 + ngroups, vnext2);
       for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++g) {
         float v[28];
 #pragma unroll
-        for (int e = 0; e < 28; ++e) v[e] = vnext[e];
-        load_patch(tile + ngroups, vnext);
+        for (int e = 0; e < 28; ++e) { v[e] = vnext[e]; vnext[e] = vnext2[e]; }
+        load_patch(tile + 2 * ngroups, vnext2);
         const uint32_t s = g % S;
         if ((s & cmask) == 0) mbar_wait(empty0 + 8 * (s >> p.clog), ((g / S) & 1) ^ 1);
         const uint32_t row = sA + s * TC_A_STAGE + r * 128;
