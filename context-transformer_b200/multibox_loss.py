@@ -9,13 +9,15 @@ non-differentiable, data-dependent stages run as CUDA kernels for the whole batc
 
 The differentiable reductions (smooth-L1, the two cross-entropies on the mined set, the
 logit-combine of :106-117) stay as autograd tensor expressions on the same device so that
-``loss.backward()`` reaches the network exactly as upstream.
+``loss.backward()`` reaches the network exactly as upstream.  Under ``torch.distributed`` (one process
+per GPU) the normaliser N is all-reduced over the replicas (see ``shard.global_positive_count``).
 """
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from .box_utils import hard_negative_rank, match_batch
+from .shard import global_positive_count
 
 
 class MultiBoxLoss_combined(nn.Module):
@@ -31,6 +33,7 @@ class MultiBoxLoss_combined(nn.Module):
         self.negpos_ratio = neg_pos
         self.neg_overlap = neg_overlap
         self.variance = [0.1, 0.2]
+        self.process_group = None          # torch.distributed group of the data-parallel replicas (None = default group)
 
     def forward(self, predictions, priors, targets):
         loc_data, conf_data, obj_data = predictions
@@ -65,5 +68,9 @@ class MultiBoxLoss_combined(nn.Module):
         logit = torch.cat((logit_0, logit_k), 1).view(num, -1, self.num_classes)
         loss_c = torch.sum(F.cross_entropy(logit[mask], conf_t[mask][:, 0].long(), reduction='none') * weight)
 
-        N = num_pos.sum()
-        return {'loss_box_reg': loss_l / N, 'loss_cls': loss_c / N, 'loss_obj': loss_obj / N}
+        # single process: N = positives of the batch, as upstream.  One process per GPU (torch.distributed initialised):
+        # N is the positive count of the global batch (one scalar all-reduce) and the shard's sums are scaled by the world
+        # size, so that DDP's gradient averaging reproduces the reference's DataParallel loss exactly.
+        N, world = global_positive_count(num_pos.sum(), self.process_group)
+        k = float(world)
+        return {'loss_box_reg': loss_l * k / N, 'loss_cls': loss_c * k / N, 'loss_obj': loss_obj * k / N}

@@ -49,6 +49,19 @@ def gather_records(records, counts, group=None):
     return unpack_records(out)
 
 
+def global_positive_count(num_pos_local, group=None):
+    """Data-parallel fine-tuning (BASELINE config 5): the reference normalises every loss term by the positive count of
+    the WHOLE batch (``N = num_pos.sum()`` after ``nn.DataParallel`` has gathered the replicas' outputs on GPU 0,
+    multibox_loss_combined.py:119-122).  With one process per GPU each rank only sees its shard, so N needs one scalar
+    all-reduce.  Returns ``(N_global, world)``: a rank's loss is ``local_sum * world / N_global`` — gradient averaging
+    over ranks (DDP) then yields exactly ``global_sum / N_global``."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return num_pos_local, 1
+    n = num_pos_local.detach().clone()
+    dist.all_reduce(n, op=dist.ReduceOp.SUM, group=group)
+    return n, dist.get_world_size(group)
+
+
 class ShardedDetector(object):
     """net: RFBNet in eval mode on this rank's GPU; post: DetectPost; priors: [P,4]."""
 

@@ -29,6 +29,15 @@ def _worker(rank, world, port, out):
         lo, hi = shard.shard_bounds(B_global, world, rank)
         rec, cnt = shard.gather_records(rec_all[lo:hi].clone(), cnt_all[lo:hi].clone())
         ok = torch.equal(rec, rec_all) and torch.equal(cnt, cnt_all)
+        # loss normaliser of the data-parallel fine-tune loop: N is the positive count of the GLOBAL batch, and the
+        # world-scaled shard losses average (DDP) to global_sum / N_global
+        num_pos = torch.tensor([7, 0, 3, 11, 5, 2])
+        sums = torch.tensor([1.5, 0.0, 0.25, 4.0, 2.0, 0.5], dtype=torch.float64)
+        n, w = shard.global_positive_count(num_pos[lo:hi].sum())
+        mine = sums[lo:hi].sum() * w / n
+        tot = mine.clone()
+        dist.all_reduce(tot)
+        ok = ok and int(n) == 28 and w == world and abs(float(tot) / world - float(sums.sum()) / 28.0) < 1e-12
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
