@@ -55,6 +55,7 @@ struct TcParams {
   int cluster_req;
   int m_tiles, cluster;                  // cluster = 2: CTA pairs, one 2-CTA MMA per K-step (opt-in)
   int a_mode, TW, TH, tiles_x, tiles_y;       // TMA mode: output patch TW x TH (<= 128 pixels), tiles per image
+  int occ, acc_stride;                        // CTAs per SM the kernel is sized for (TMEM columns = 512 / occ), columns between the two accumulators
   int tps;                                    // HALO mode: filter taps per weight-ring slot (1 or 3)
   int PW, PH, a_slot, sa, sb;                 // HALO mode: staged patch (TW + 2 dil) x (TH + 2 dil) pixels, slot bytes, A / B ring depths
   int flat;                                   // TMA mode, 1x1 convs: the whole batch is one pixel row, tiles are 128-pixel runs
@@ -106,7 +107,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_
       const long long m_lin = (long long)n_img * p.Ho * p.Wo + pix;
       mbar_wait(accf0 + 8 * buf, (lt >> 1) & 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
+      const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.acc_stride + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int cb = 0; cb * 32 < BN; ++cb) {
         const int c0 = n0 + cb * 32;
@@ -439,7 +440,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const uint32_t buf = lt & 1;
         mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);            // (pair mode: both CTAs' epilogues) have drained it
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * 256;
+        const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.acc_stride;
         for (int it = 0; it < nk; ++it) {
           mbar_wait(full0 + 8 * s, ph);                            // pair mode: arrivals come from both CTAs
           tc_fence_after();
@@ -484,7 +485,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 // Weights stream through their own ring, one BN x 64 tile per (channel block, tap), released in commit groups.
 // Warp roles (352 threads): warp 0 patch producer (runs a full patch ring ahead: a patch load has several channel blocks
 // of MMA work to hide behind), warp 1 weight producer, warp 2 MMA issuer, warps 3-10 two epilogue sets.
-__global__ void __launch_bounds__(HALO_THREADS, 1)
+// OCC = 2 (tiles <= 128 wide): two CTAs per SM, each with half of TMEM and of shared memory — two MMA-issuing threads per
+// SM, because with narrow tiles the issue rate of ONE thread (~50-90 clk per tcgen05.mma against a tensor-pipe floor of
+// 32 / 64 clk for N = 64 / 128) is what bounds the kernel.
+template <int OCC>
+__global__ void __launch_bounds__(HALO_THREADS, OCC)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int BN = p.bn, SA = p.sa, SB = p.sb;
@@ -510,7 +515,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 512); tmem_relinquish();
+    tmem_alloc(tmem_slot, 512 / OCC); tmem_relinquish();
   }
   for (int c = threadIdx.x; c < ((p.Cout + 31) & ~31) + 32; c += HALO_THREADS) s_bias[c] = c < p.Cout ? p.bias[c] : 0.f;
   tc_fence_before();
@@ -576,7 +581,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const uint32_t buf = lt & 1;
         mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * 256;
+        const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.acc_stride;
         for (int cc = 0; cc < p.cin_blocks; ++cc) {
           mbar_wait(fullA0 + 8 * slot, pha);
           uint32_t a_tap = a_lo;                                // window of tap (0, 0); +dil rows per kx, +dil patch lines per ky
@@ -609,7 +614,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512 / OCC); }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -702,8 +707,9 @@ static int launch_tc(const TcPlan* pl, cudaStream_t st) {
   return CTX_OK;
 }
 
+template <int OCC>
 static int launch_halo(const TcPlan* pl, cudaStream_t st) {
-  CTX_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+  CTX_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)pl->grid);
   cfg.blockDim = dim3(HALO_THREADS);
@@ -715,7 +721,7 @@ static int launch_halo(const TcPlan* pl, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = pdl;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CTX_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_halo_kernel, pl->tmap_w, pl->tmap_a, pl->p));
+  CTX_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_halo_kernel<OCC>, pl->tmap_w, pl->tmap_a, pl->p));
   CTX_LAUNCH_CHECK();
   return CTX_OK;
 }
@@ -785,7 +791,8 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
   int tw = 0, th = 0;
   const bool halo_ok = tma_eligible(p) && p->KH == 3 && p->KW == 3 && p->pad_h == p->pad_w && t.cluster_req != 2 &&
                        (!p->pool2 || (((p->Ho | p->Wo) & 1) == 0 && p->Cin % 64 == 0));
-  if (tune_amode == 2 && halo_ok) { t.a_mode = A_HALO; tw = 8; th = 16; }
+  t.occ = 1; t.acc_stride = 256;
+  if ((tune_amode == 2 || tune_amode == 3) && halo_ok) { t.a_mode = A_HALO; tw = 8; th = 16; }
   else if (p->in_nchw) t.a_mode = A_STEM;
   else if (tune_amode == 0 && !p->pool2) t.a_mode = A_GATHER;
   else if (flat_eligible(p)) { t.a_mode = A_TMA; tw = 128; th = 1; }
@@ -826,22 +833,30 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
     t.a_slot = (int)align_up((size_t)t.PW * t.PH * 128, 1024);
     // narrow tiles: a slot holds the three taps of a filter row and is released by its own commit — twelve MMAs per
     // barrier wait instead of four (the MMA thread's issue loop is the pace there); an explicit commit group keeps 1 tap
-    t.tps = (t.bn <= 128 && tune_commit <= 0) ? 3 : 1;
-    if (t.tps == 3) t.clog = 0;
-    const size_t b_stage = (size_t)t.tps * t.bn * TC_BK * 2, budget = 232448 - 1024 - bias_bytes - 8 * (2 * 6 + 2 * 8 + 4) - 64;
-    const int c = 1 << t.clog;
+    const int clog_rule = t.clog;
     t.sa = 0;
-    for (int sb = 8; sb >= 3 && !t.sa; --sb) {
-      if (sb % c || sb < 2 * c || (size_t)sb * b_stage + 2 * (size_t)t.a_slot > budget) continue;
-      const int sa = (int)std::min<size_t>(6, (budget - (size_t)sb * b_stage) / t.a_slot);
-      if (sa >= 3 || sb <= 4) { t.sa = sa; t.sb = sb; }            // shrink the weight ring before going below 3 patches
+    for (int occ = (tune_amode == 3 && t.bn <= 128) ? 2 : 1; occ >= 1 && !t.sa; --occ) {     // two CTAs per SM if they fit, else one
+      t.occ = occ;
+      t.acc_stride = 256 / occ;
+      t.clog = clog_rule;
+      t.tps = (t.bn <= 128 && tune_commit <= 0 && occ == 1) ? 3 : 1;
+      if (t.tps == 3) t.clog = 0;
+      if (occ == 2 && t.clog > 1) t.clog = 1;
+      const size_t per_cta = occ == 2 ? (233472 - 2 * 1024) / 2 : 232448;
+      const size_t b_stage = (size_t)t.tps * t.bn * TC_BK * 2, budget = per_cta - 1024 - bias_bytes - 8 * (2 * 6 + 2 * 8 + 4) - 64;
+      const int c = 1 << t.clog;
+      for (int sb = 8; sb >= 2 && !t.sa; --sb) {
+        if (sb % c || sb < 2 * c || (size_t)sb * b_stage + 2 * (size_t)t.a_slot > budget) continue;
+        const int sa = (int)std::min<size_t>(6, (budget - (size_t)sb * b_stage) / t.a_slot);
+        if (sa >= 3 || sb <= 4) { t.sa = sa; t.sb = sb; }          // shrink the weight ring before going below 3 patches
+      }
     }
     if (!t.sa) { delete pl; set_error("conv_tc: HALO mode does not fit shared memory (dilation %d, tile width %d)", p->dil, t.bn); return CTX_ERR_UNSUPPORTED; }
     pl->stages = t.sb;
   }
   pl->smem = t.a_mode == A_HALO ? (size_t)t.sa * t.a_slot + (size_t)t.sb * t.tps * t.bn * TC_BK * 2 + 8 * (2 * t.sa + 2 * t.sb + 4) + 64 + bias_bytes + 1024 :
              (size_t)pl->stages * stage_bytes + 24 * pl->stages + 64 + 4 * (((size_t)p->Cout + 31) / 32 * 32 + 32) + 1024;
-  pl->grid = std::min(t.num_tiles, num_sms() / t.cluster) * t.cluster;
+  pl->grid = std::min(t.num_tiles, num_sms() * (t.a_mode == A_HALO ? t.occ : 1) / t.cluster) * t.cluster;
 
   // weights: [Cout_pad][KH*KW*Cin_pad] 16-bit, K-major; box = 64 (K) x BN (Cout), SWIZZLE_128B, OOB rows read as zero
   const unsigned long long ktot = (unsigned long long)t.nk * TC_BK;
@@ -873,7 +888,7 @@ extern "C" int ctx_conv2d_tc_plan_info(void* plan, int* info8) {
   const TcPlan* pl = (const TcPlan*)plan;
   int* info6 = info8;
   info8[6] = pl->p.a_mode == A_HALO && pl->p.tps == 3 ? 3 : 1 << pl->p.clog; info8[7] = pl->p.TW * 1000 + pl->p.TH;
-  info6[0] = pl->p.bn; info6[1] = pl->p.n_tiles_n; info6[2] = pl->p.cluster; info6[3] = pl->p.a_mode; info6[4] = pl->stages; info6[5] = pl->grid;
+  info6[0] = pl->p.bn; info6[1] = pl->p.n_tiles_n; info6[2] = pl->p.cluster; info6[3] = pl->p.a_mode == A_HALO && pl->p.occ == 2 ? 4 : pl->p.a_mode; info6[4] = pl->stages; info6[5] = pl->grid;
   return CTX_OK;
 }
 
@@ -881,7 +896,7 @@ extern "C" int ctx_conv2d_tc_plan_run(void* plan, void* stream) {
   CTX_REQUIRE(plan, "ctx_conv2d_tc_plan_run: null plan");
   const TcPlan* pl = (const TcPlan*)plan;
   cudaStream_t st = (cudaStream_t)stream;
-  if (pl->p.a_mode == A_HALO) return launch_halo(pl, st);
+  if (pl->p.a_mode == A_HALO) return pl->p.occ == 2 ? launch_halo<2>(pl, st) : launch_halo<1>(pl, st);
   if (pl->p.cluster == 2) {
     if (pl->stages == 8) return launch_tc<8, 2>(pl, st);
     if (pl->stages == 6) return launch_tc<6, 2>(pl, st);

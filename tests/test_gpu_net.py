@@ -134,7 +134,7 @@ def test_conv_every_tiling_is_bit_identical(case):
     seen = set()
     for n, cg in ((0, 0), (2, 1), (3, 2), (5, 4), (0, 4), (0, 1)):
         for cl in (1, 2):
-            for amode in (-1, 0, 1, 2):
+            for amode in (-1, 0, 1, 2, 3):
                 plan = C.c_void_p()
                 _lib.check(L.ctx_conv2d_tc_plan_create_tuned(C.byref(p), n, cl, amode, cg, C.byref(plan)), 'plan_create_tuned')
                 info = (C.c_int * 8)()
@@ -150,6 +150,7 @@ def test_conv_every_tiling_is_bit_identical(case):
     assert len(seen) >= 4
     assert {k[3] for k in seen} >= {0, 1}                         # gather and TMA-patch A-operand modes were exercised
     assert (3 in {k[3] for k in seen}) == (kh == 3 and kw == 3)   # ... and the halo mode for every 3x3 case
+    assert (4 in {k[3] for k in seen}) == (kh == 3 and kw == 3)   # ... also with two CTAs per SM (tiles <= 128 wide: n >= 2 splits any Cout here)
     assert len({k[4] for k in seen}) >= 2                         # ... and more than one commit-group size
 
 
