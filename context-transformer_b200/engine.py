@@ -235,8 +235,12 @@ class Engine(object):
         return self._emit_conv(name, src, w, b, c.stride[0], _pair(c.padding), c.dilation[0],
                                (m.relu is not None) if relu is None else relu, out=out, residual=residual)
 
-    def _rfb(self, name, m, src):
+    def _rfb(self, name, m, src, home=0):
+        """``home``: lane of the block's own chain (entry conv, first branch, ConvLinear).  The block input must already
+        be complete on lane 0; with home != 0 the whole block runs beside the trunk (its output only feeds a head)."""
         branches = m.branches()
+        if home:
+            self._lane(home, wait=(0,))
         stride = m.shortcut.conv.stride[0]
         Ho = (src.H - 1) // stride + 1
         Wo = (src.W - 1) // stride + 1
@@ -270,7 +274,7 @@ class Engine(object):
         # branch bi runs on lane bi (the block input / fused entry conv was produced on lane 0)
         off = 0
         for bi, br in enumerate(branches):
-            self._lane(min(bi, 3), wait=(0,))
+            self._lane(home if bi == 0 else min(bi, 3), wait=(home,))
             t = src
             for li, layer in enumerate(br):
                 last = li == len(br) - 1
@@ -280,7 +284,7 @@ class Engine(object):
                 t = self._basic_conv('%s.branch%d.%d' % (name, bi, li), layer, t,
                                      out=cat.slice(off, layer.out_channels) if last else None)
             off += br[-1].out_channels
-        self._lane(0, wait=tuple(range(1, min(len(branches), 4))))
+        self._lane(home, wait=tuple(range(1, min(len(branches), 4))))
         short = entry_out['shortcut'] if 'shortcut' in entry_out else self._basic_conv(name + '.shortcut', m.shortcut, src)
         # relu(ConvLinear(cat) * scale + short): scale folds into the weights, the add + ReLU into the epilogue
         return self._basic_conv(name + '.ConvLinear', m.ConvLinear, cat, residual=short, relu=True, scale=float(m.scale))
@@ -356,7 +360,7 @@ class Engine(object):
         self.obj_raw = self._alloc(B, P, 2, dtype=torch.float32)
         pooled_shapes = []
 
-        def add_source(s):
+        def add_source(s, lane=0):
             i = len(sources)
             sources.append(s)
             assert (s.H, s.W) == (fmaps[i], fmaps[i]), (i, s.H, s.W, fmaps[i])
@@ -371,7 +375,7 @@ class Engine(object):
             segs = [(self.loc.view(-1)[poff * 4:], 0, c1, P * 4, a * 4, 0),
                     (self.conf_raw.view(-1)[poff * Csrc:], c1, c2, P * Csrc, a * Csrc, 0),
                     (self.obj_raw.view(-1)[poff * 2:], c2, c3, P * 2, a * 2, 0)]
-            self._lane(5, wait=(0,))
+            self._lane(5, wait=(lane,))
             self._emit_conv('head.%d' % i, s, w, b, 1, (1, 1), 1, False, segs=segs)
             self._lane(0)
             if ours:
@@ -379,7 +383,9 @@ class Engine(object):
                 pooled_shapes.append((_pool_out(s.H, k, k, 0, True), _pool_out(s.W, k, k, 0, True), a))
 
         x = run_base(0, SOURCE_SPLIT, x)
-        add_source(self._rfb('Norm', net.Norm, x))
+        # RFB-a on conv4_3 only feeds the first head: it runs on lane 4 beside the rest of the trunk
+        norm_lane = 4 if self.use_lanes else 0
+        add_source(self._rfb('Norm', net.Norm, x, home=norm_lane), lane=norm_lane)
         x = run_base(SOURCE_SPLIT, len(net.base), x)
         for k, m in enumerate(net.extras):
             if isinstance(m, _RFBBlock):
