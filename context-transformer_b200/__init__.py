@@ -7,6 +7,7 @@ Public surface = the reference symbols that ``train.py`` / ``test.py`` import fo
   MultiBoxLoss_combined                                   layers/modules/multibox_loss_combined.py
   nms, gpu_nms, cpu_nms, cpu_soft_nms                     utils/nms_wrapper.py, utils/nms/
   match, decode, encode, jaccard, point_form              utils/box_utils.py
+  init_reweight                                           train.py:252-286 (OBJ(Target) prototype initialisation)
   VOC_300, VOC_512, COCO_300, COCO_512                    data/config.py (prior-box constants)
 
 plus the fused device-side post-processing ``DetectPost`` (test.py:133-161) and the multi-GPU
@@ -19,9 +20,10 @@ from .detection import Detect, DetectPost, records_to_all_boxes
 from .nms_wrapper import cpu_nms, cpu_soft_nms, gpu_nms, nms, nms_device, soft_nms
 from .box_utils import decode, encode, hard_negative_rank, jaccard, match, match_batch, point_form
 from .multibox_loss import MultiBoxLoss_combined
+from .reweight import PrototypeAccumulator, init_reweight
 from .rfb_net import BasicConv, BasicRFB, BasicRFB_a, RFBNet, build_net
 
 __all__ = ['build_net', 'RFBNet', 'BasicConv', 'BasicRFB', 'BasicRFB_a', 'PriorBox', 'Detect', 'DetectPost',
            'records_to_all_boxes', 'MultiBoxLoss_combined', 'nms', 'gpu_nms', 'cpu_nms', 'cpu_soft_nms', 'soft_nms',
            'nms_device', 'match', 'match_batch', 'decode', 'encode', 'jaccard', 'point_form', 'hard_negative_rank',
-           'VOC_300', 'VOC_512', 'COCO_300', 'COCO_512', 'MBOX', 'num_priors']
+           'init_reweight', 'PrototypeAccumulator', 'VOC_300', 'VOC_512', 'COCO_300', 'COCO_512', 'MBOX', 'num_priors']

@@ -108,6 +108,8 @@ SIGNATURES = {
     'ctx_match_encode': (_I, [_P, _P, _I, _P, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     'ctx_rank_workspace_bytes': (_SZ, [_I, _I]),
     'ctx_hard_negative_rank': (_I, [_P, _I, _I, _P, _P, _SZ, _P]),
+    'ctx_prototype_accumulate': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    'ctx_prototype_finalize': (_I, [_P, _P, _I, _I, _I, _P, _P]),
 }
 
 _lib = None

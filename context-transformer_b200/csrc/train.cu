@@ -172,3 +172,61 @@ extern "C" int ctx_hard_negative_rank(const float* loss, int batch, int num_prio
   CTX_LAUNCH_CHECK();
   return CTX_OK;
 }
+
+
+// ---- OBJ(Target) prototype initialisation : train.py:252-286 (init_reweight) -------------------------------------------
+// Upstream gathers, per foreground class, the raw conf features of every prior matched to that class over <= init_iter
+// batches (boolean-mask gathers + torch.cat growing lists), L2-normalises each row, averages per class and normalises the
+// mean.  Here one pass over the match labels adds each positive prior's normalised feature row to a per-class fp64 sum
+// (positives are a few dozen per image: the pass is bound by reading the [B, P] label plane), a tiny second kernel
+// produces the normalised class means.
+namespace ctx {
+__global__ void __launch_bounds__(256)
+prototype_accumulate_kernel(const float* __restrict__ feat, const float* __restrict__ conf_t, long long rows, int dim, int num_fg,
+                            double* __restrict__ sums, int* __restrict__ counts) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float label = conf_t[2 * r];                           // conf_t[..., 0]: 0 background, -1 ignore, 1..num_fg class
+  const int c = (int)label;
+  if (!(label >= 1.f) || (float)c != label || c > num_fg) return;
+  const float* x = feat + r * dim;
+  float ss = 0.f;
+  for (int d = 0; d < dim; ++d) ss = fmaf(x[d], x[d], ss);
+  const float nrm = sqrtf(ss);                                 // torch: item / item.norm(dim=1, keepdim=True), no eps
+  double* dst = sums + (long long)(c - 1) * dim;
+  for (int d = 0; d < dim; ++d) atomicAdd(dst + d, (double)(x[d] / nrm));
+  atomicAdd(counts + (c - 1), 1);
+}
+
+__global__ void prototype_finalize_kernel(const double* __restrict__ sums, const int* __restrict__ counts, int dim, int first_class,
+                                          float* __restrict__ out) {
+  // one warp per output class: mean over the class's rows (empty class -> NaN, as torch's mean of an empty tensor), / its norm
+  const int c = first_class + blockIdx.x, lane = threadIdx.x;
+  const double n = (double)counts[c];
+  float ss = 0.f;
+  for (int d = lane; d < dim; d += 32) { const float m = (float)(sums[(long long)c * dim + d] / n); ss = fmaf(m, m, ss); }
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float nrm = sqrtf(ss);
+  for (int d = lane; d < dim; d += 32) out[(long long)blockIdx.x * dim + d] = (float)(sums[(long long)c * dim + d] / n) / nrm;
+}
+}  // namespace ctx
+
+extern "C" int ctx_prototype_accumulate(const float* feat, const float* conf_t, int batch, int num_priors, int dim, int num_fg,
+                                        double* sums, int* counts, void* stream) {
+  CTX_REQUIRE(batch >= 0 && num_priors >= 1 && dim >= 1 && num_fg >= 1, "ctx_prototype_accumulate: bad sizes");
+  CTX_REQUIRE(feat && conf_t && sums && counts, "ctx_prototype_accumulate: null pointer");
+  const long long rows = (long long)batch * num_priors;
+  if (rows == 0) return CTX_OK;
+  prototype_accumulate_kernel<<<cdiv(rows, 256), 256, 0, (cudaStream_t)stream>>>(feat, conf_t, rows, dim, num_fg, sums, counts);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
+extern "C" int ctx_prototype_finalize(const double* sums, const int* counts, int num_fg, int dim, int first_class, float* out,
+                                      void* stream) {
+  CTX_REQUIRE(sums && counts && out, "ctx_prototype_finalize: null pointer");
+  CTX_REQUIRE(num_fg >= 1 && dim >= 1 && first_class >= 0 && first_class < num_fg, "ctx_prototype_finalize: bad sizes");
+  prototype_finalize_kernel<<<num_fg - first_class, 32, 0, (cudaStream_t)stream>>>(sums, counts, dim, first_class, out);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}

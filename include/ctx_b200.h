@@ -203,6 +203,15 @@ size_t ctx_rank_workspace_bytes(int batch, int num_priors);
 int ctx_hard_negative_rank(const float* loss, int batch, int num_priors, int* rank,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* OBJ(Target) prototype initialisation, train.py:252-286 (init_reweight).  feat[B,P,dim] = model(x, init=True) (raw conf
+ * features), conf_t[B,P,2] = the match() labels (ctx_match_encode).  Adds every positive prior's L2-normalised feature row
+ * to sums[num_fg, dim] (fp64, caller-zeroed before the first batch) and its class to counts[num_fg]; call once per batch.
+ * ctx_prototype_finalize writes out[num_fg - first_class, dim] = normalise(mean of the class's rows) for classes
+ * first_class.. (15 for the 'incre' setting, train.py:281-282); a class with no sample yields NaN, as upstream. */
+int ctx_prototype_accumulate(const float* feat, const float* conf_t, int batch, int num_priors, int dim, int num_fg,
+                             double* sums, int* counts, void* stream);
+int ctx_prototype_finalize(const double* sums, const int* counts, int num_fg, int dim, int first_class, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

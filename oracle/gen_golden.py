@@ -146,10 +146,52 @@ def gen_match_loss(r):
     np.savez_compressed(os.path.join(GOLD, 'match_loss.npz'), **out)
 
 
+def reweight_inputs(P, seed=0, batches=3, B=4, D=60):
+    """Seeded inputs of the init_reweight golden: `batches` batches of raw conf features [B,P,D] and config-5 targets
+    whose labels cover only part of the 20 classes (classes without a sample must come out NaN, as upstream)."""
+    feats, targets = [], []
+    for it in range(batches):
+        g = synth._gen(seed + it, 'reweight')
+        feats.append(torch.randn(B, P, D, generator=g) * 3.0 + 0.5)
+        t = synth.synthetic_targets(B, seed=100 + seed + it, num_classes=12)
+        targets.append(t)
+    targets[1][0][0, 4] = -1.0                       # an "ignore" label: never a class sample (train.py:276 compares == i)
+    return feats, targets
+
+
+def gen_reweight(r):
+    """train.py:252-286 executed literally on CPU tensors with the reference's own match() (train.py itself needs the
+    dataset / logger stack and is not importable; the statements below are its lines :257-286 with the model call
+    replaced by the seeded feature tensor)."""
+    priors = r.PriorBox(r.cfg.VOC_300).forward()
+    P = priors.size(0)
+    num_classes = 21
+    feats, targets_all = reweight_inputs(P)
+    cls_list = [torch.empty(0) for _ in range(num_classes - 1)]
+    labels_out = []
+    for conf_data, targets in zip(feats, targets_all):
+        num = conf_data.size(0)
+        loc_t = torch.Tensor(num, P, 4)
+        conf_t = torch.Tensor(num, P, 2)
+        obj_t = torch.BoolTensor(num, P)
+        for idx in range(num):
+            truths = targets[idx][:, :-2].data
+            labels = targets[idx][:, -2:].data
+            r.box_utils.match(0.5, truths, priors.data, [0.1, 0.2], labels, loc_t, conf_t, obj_t, idx)
+        conf_data_list = [conf_data[conf_t[:, :, 0] == i] for i in range(1, num_classes)]
+        cls_list = [torch.cat((cls_list[i], conf_data_list[i]), 0) for i in range(num_classes - 1)]
+        labels_out.append(conf_t[:, :, 0].numpy().copy())
+    counts = np.array([len(c) for c in cls_list], np.int32)
+    cls_list = [(item / item.norm(dim=1, keepdim=True)).mean(0) for item in cls_list]
+    weight = torch.stack([item / item.norm() for item in cls_list], 0)
+    np.savez_compressed(os.path.join(GOLD, 'reweight.npz'), weight=weight.numpy(), weight_incre=weight[15:].numpy(), counts=counts,
+                        labels_checksum=np.array([checksum(torch.from_numpy(l)) for l in labels_out]))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     r = ref_import.load()
-    which = sys.argv[1:] or ['priors', 'nms', 'post', 'match', 'net']
+    which = sys.argv[1:] or ['priors', 'nms', 'post', 'match', 'net', 'reweight']
     if 'priors' in which:
         gen_priors(r)
     if 'nms' in which:
@@ -158,6 +200,8 @@ def main():
         gen_post(r)
     if 'match' in which:
         gen_match_loss(r)
+    if 'reweight' in which:
+        gen_reweight(r)
     if 'net' in which:
         gen_net(r)
 

@@ -322,3 +322,27 @@ def multibox_loss(loc_data, conf_data, obj_data, priors, targets, num_classes=21
     N = float(num_pos.sum())
     return {'loss_box_reg': loss_l / N, 'loss_cls': loss_c / N, 'loss_obj': loss_obj / N,
             'mask': mask, 'rank': rank, 'num_pos': num_pos}
+
+
+# --------------------------------------------------------------------------------------------
+# OBJ(Target) prototype initialisation — train.py:252-286 (init_reweight)
+# --------------------------------------------------------------------------------------------
+def init_reweight_prototypes(conf_batches, label_batches, num_classes=21, setting='transfer'):
+    """conf_batches: list of [B,P,D] float32 (``model(data, init=True)``), label_batches: list of [B,P] float32
+    (``conf_t[:, :, 0]`` from ``match``).  Follows train.py:268-282 literally: per class i the rows with label == i are
+    concatenated over the batches in (batch, image, prior) order, each row divided by its L2 norm, averaged, then the
+    mean divided by its own norm (:283-286).  Returns [n_classes_kept, D] float32 (NaN rows for classes without samples)."""
+    n_fg = num_classes - 1
+    cls = [np.zeros((0, conf_batches[0].shape[-1]), F) for _ in range(n_fg)]
+    for conf, lab in zip(conf_batches, label_batches):
+        for i in range(1, num_classes):
+            cls[i - 1] = np.concatenate([cls[i - 1], conf[lab == i].astype(F)], 0)
+    out = []
+    for item in cls:
+        with np.errstate(invalid='ignore', divide='ignore'):
+            rows = item / np.sqrt((item * item).sum(1, keepdims=True, dtype=F)).astype(F)
+            m = rows.mean(0, dtype=F) if len(rows) else np.full(item.shape[1], np.nan, F)
+            out.append((m / np.sqrt((m * m).sum(dtype=F))).astype(F))
+    if setting == 'incre':
+        out = out[15:]
+    return np.stack(out, 0)

@@ -311,3 +311,47 @@ def test_multibox_loss_vs_golden_and_oracle(golden):
     assert np.allclose(got, g['loss'], rtol=2e-5)
     sum(out.values()).backward()
     assert loc_p.grad is not None and float(conf_p.grad.abs().sum()) > 0 and float(obj_p.grad.abs().sum()) > 0
+
+
+def test_init_reweight_vs_golden_and_oracle(golden):
+    """OBJ(Target) prototype initialisation (train.py:252-286): ctx_match_encode + ctx_prototype_accumulate / _finalize through
+    the reference-shaped ``init_reweight(args, model, data_loader, ...)`` against the golden of the reference's own statements.
+    Tolerance 2e-6 absolute on unit-norm rows (fp64 per-class sums here, fp32 ``mean`` upstream); NaN rows for classes
+    without a sample, exactly where upstream has them."""
+    import types
+    from oracle.gen_golden import reweight_inputs
+    g = golden('reweight.npz')
+    priors = ctx.PriorBox(ctx.VOC_300).forward()
+    feats, targets_all = reweight_inputs(priors.size(0))
+
+    class FakeNet(torch.nn.Module):
+        """Stands in for RFBNet: ``model(data, init=True)`` returns the seeded raw conf features of that batch."""
+        def __init__(self):
+            super().__init__()
+            self.OBJ_Target = torch.nn.Linear(60, 20, bias=False)
+            self.calls = 0
+
+        def forward(self, x, init=False):
+            assert init
+            self.calls += 1
+            return feats[self.calls - 1].to(x.device)
+
+    net = FakeNet().cuda()
+    loader = [(torch.zeros(4, 3, 8, 8), t) for t in targets_all] + [(torch.zeros(4, 3, 8, 8), targets_all[0])] * 2
+    w = ctx.init_reweight(types.SimpleNamespace(init_iter=3, setting='transfer'), net, loader, priors, 21, 0.5)
+    torch.cuda.synchronize()
+    assert net.calls == 3 and tuple(w.shape) == (20, 60) and net.OBJ_Target.weight.data_ptr() == w.data_ptr()
+    got = w.cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(g['weight']))
+    assert np.allclose(got, g['weight'], rtol=0, atol=2e-6, equal_nan=True)
+    # 'incre': only the last five classes become OBJ(Target) rows (train.py:281-282)
+    net2 = FakeNet().cuda()
+    w2 = ctx.init_reweight(types.SimpleNamespace(init_iter=50, setting='incre'), net2, loader[:3], priors, 21, 0.5)
+    assert tuple(w2.shape) == (5, 60) and np.allclose(w2.cpu().numpy(), g['weight_incre'], rtol=0, atol=2e-6, equal_nan=True)
+    # the accumulator alone: counts per class are exact
+    acc = ctx.PrototypeAccumulator(20, 60, 'cuda:0')
+    for f, t in zip(feats, targets_all):
+        acc.add(f.cuda(), ctx.match_batch(0.5, t, priors.cuda(), (0.1, 0.2))[1])
+    assert np.array_equal(acc.counts.cpu().numpy(), g['counts'])
+    with pytest.raises(_lib.CtxError):
+        ctx.PrototypeAccumulator(20, 60, 'cpu')

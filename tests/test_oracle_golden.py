@@ -120,3 +120,27 @@ def test_oracle_against_live_reference():
     want = r.box_utils.decode(loc, priors, [0.1, 0.2]).numpy()
     got = np_oracle.decode(loc.numpy(), priors.numpy())
     assert np.allclose(got, want, rtol=0, atol=2e-6)
+
+
+def test_init_reweight_prototypes_match_reference(golden):
+    """train.py:252-286 restated (np_oracle.init_reweight_prototypes + np_oracle.match) against the golden produced by
+    executing the reference's statements with the reference's own match()."""
+    from oracle.gen_golden import reweight_inputs
+    g = golden('reweight.npz')
+    priors = np_oracle.prior_box(ctx.VOC_300)
+    P = priors.shape[0]
+    feats, targets_all = reweight_inputs(P)
+    labels = []
+    for targets in targets_all:
+        lab = np.zeros((len(targets), P), np.float32)
+        for i, t in enumerate(targets):
+            t = t.numpy()
+            lab[i] = np_oracle.match(0.5, t[:, :4], priors, (0.1, 0.2), t[:, 4:6])[1][:, 0]
+        labels.append(lab)
+    assert np.array_equal(np.array([checksum(torch.from_numpy(l)) for l in labels]), g['labels_checksum'])
+    got = np_oracle.init_reweight_prototypes([f.numpy() for f in feats], labels, 21, 'transfer')
+    assert np.array_equal(np.isnan(got), np.isnan(g['weight']))
+    assert np.isnan(g['weight']).any(1).sum() == 10 and (g['counts'] > 0).sum() == 10        # both cases are covered
+    assert np.allclose(got, g['weight'], rtol=0, atol=2e-6, equal_nan=True)
+    inc = np_oracle.init_reweight_prototypes([f.numpy() for f in feats], labels, 21, 'incre')
+    assert inc.shape == (5, 60) and np.allclose(inc, g['weight_incre'], rtol=0, atol=2e-6, equal_nan=True)
