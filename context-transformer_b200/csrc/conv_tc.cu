@@ -64,6 +64,8 @@ struct TcParams {
   int pool2;                   // fused MaxPool2d(2,2): TMA mode with TW = 16 (2x2 windows live inside one warp)
   int clog;                    // log2 of the commit group: ring slots are handed back to the producers 1 << clog at a time
   int fast_out;                // single 16-bit segment, 8-channel aligned: 128-bit stores
+  int bulk_out;                // fast_out + pixel-linear tiles of a dense map: each epilogue warp stages its 32 rows in shared memory
+                               // and writes them with ONE bulk copy (the per-thread 16-B stores touch 32 lines per instruction)
   int vec_f32;                 // fp32 segments, 4-channel aligned: 128-bit stores
   SegTable segs;
 };
@@ -93,7 +95,7 @@ __device__ __forceinline__ bool tile_row_pixel(const TcParams& p, int mt, int r,
 // [2x2 max-pool], convert, vectorised NHWC store(s).
 template <int CL>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_bias, uint32_t tmem_base, uint32_t accf0, uint32_t acce0,
-                                              int warp, int lane, uint32_t eset, int rank, int group0, int ngroups) {
+                                              int warp, int lane, uint32_t eset, int rank, int group0, int ngroups, uint32_t stage_smem = 0u) {
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int BN = p.bn;
     const int r = q * 32 + lane;
@@ -108,6 +110,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_
       mbar_wait(accf0 + 8 * buf, (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.acc_stride + ((uint32_t)(q * 32) << 16);
+      if (p.bulk_out) {                                             // the previous tile's bulk store has read the staging rows
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int cb = 0; cb * 32 < BN; ++cb) {
         const int c0 = n0 + cb * 32;
@@ -159,7 +165,11 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_
               if (store) {
                 uint4 o;
                 o.x = pack2(f[0], f[1], bf16); o.y = pack2(f[2], f[3], bf16); o.z = pack2(f[4], f[5], bf16); o.w = pack2(f[6], f[7], bf16);
-                *reinterpret_cast<uint4*>(out + c) = o;
+                if (p.bulk_out)
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_smem + (uint32_t)(lane * p.Cout + c) * 2u), "r"(o.x), "r"(o.y),
+                               "r"(o.z), "r"(o.w) : "memory");
+                else
+                  *reinterpret_cast<uint4*>(out + c) = o;
               }
             }
           }
@@ -204,6 +214,19 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_
           }
         }
       }
+      if (p.bulk_out) {
+        // rows of this warp are 32 consecutive pixels of a dense NHWC map: one contiguous block (valid rows are a prefix)
+        const uint32_t nrow = (uint32_t)__popc(__ballot_sync(0xffffffffu, row_ok));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && nrow) {
+          const CtxOutSeg& sg = p.segs.seg[0];
+          uint16_t* dst = reinterpret_cast<uint16_t*>(sg.ptr) + (long long)n_img * sg.img_stride + (long long)pix * sg.pix_stride + sg.ch_offset;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(stage_smem), "r"(nrow * (uint32_t)p.Cout * 2u)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -211,6 +234,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_
         else mbar_arrive(acce0 + 8 * buf);
       }
     }
+    if (p.bulk_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -336,36 +360,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       const float* img = reinterpret_cast<const float*>(p.in);
       const bool bf16 = p.is_bf16 != 0;
       uint32_t g = 0;
-      // the 27 loads of the tile after next are issued before the current tile is packed and stored (software pipelining:
-      // with one pixel per thread there is no other memory-level parallelism in this role)
-      auto load_patch = [&](int tile, float (&v)[28]) {
+      // Software pipelining: the 27 loads of the tile after next are issued before the current tile is packed and stored
+      // (with one pixel per thread there is no other memory-level parallelism in this role).  The role is paced by its own
+      // instruction stream, so the loop is kept lean: the pixel cursor (n, y, x) advances incrementally (no division per
+      // tile), padding is decided by six predicates per pixel, and three register buffers rotate by unrolling (no copies).
+      // (STEM tiles are never split over N or CTA pairs: tile == M tile.)
+      const int step = ngroups * TC_BM, step_rows = step / p.W, step_cols = step - step_rows * p.W;
+      long long m_cur = (long long)group0 * TC_BM + r;            // pixel the NEXT load_patch call fetches
+      int cn = (int)(m_cur / HW), cy = (int)((m_cur - (long long)cn * HW) / p.W), cx = (int)(m_cur - (long long)cn * HW - (long long)cy * p.W);
+      auto load_patch = [&](float (&v)[28]) {
 #pragma unroll
         for (int e = 0; e < 28; ++e) v[e] = 0.f;
-        const int m = ((tile / p.n_tiles_n) * CL + rank) * TC_BM + r;
-        if (tile < p.num_tiles && m < p.M) {
-          const int n = m / HW, rem = m - n * HW;
-          const int y = rem / p.W, x = rem - y * p.W;
-          const float* base = img + (long long)n * 3 * HW;
+        if (m_cur < (long long)p.M) {
+          const float* base = img + (long long)cn * 3 * HW + cy * p.W + cx;
+          const bool yo[3] = {cy > 0, true, cy + 1 < p.H}, xo[3] = {cx > 0, true, cx + 1 < p.W};
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const int iy = y + ky - 1, ix = x + kx - 1;
-              if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+            for (int kx = 0; kx < 3; ++kx)
+              if (yo[ky] && xo[kx]) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = __ldg(base + (long long)c * HW + iy * p.W + ix);
+                for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = __ldg(base + c * HW + (ky - 1) * p.W + (kx - 1));
               }
-            }
         }
+        m_cur += step;
+        cx += step_cols; cy += step_rows;
+        if (cx >= p.W) { cx -= p.W; ++cy; }
+        while (cy >= p.H) { cy -= p.H; ++cn; }
       };
-      float vnext[28], vnext2[28];                // two tiles of loads in flight: a tile period is shorter than the load latency
-      load_patch(group0, vnext);
-      load_patch(group0 + ngroups, vnext2);
-      for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++g) {
-        float v[28];
-#pragma unroll
-        for (int e = 0; e < 28; ++e) { v[e] = vnext[e]; vnext[e] = vnext2[e]; }
-        load_patch(tile + 2 * ngroups, vnext2);
+      auto emit = [&](const float (&v)[28]) {
         const uint32_t s = g % S;
         if ((s & cmask) == 0) mbar_wait(empty0 + 8 * (s >> p.clog), ((g / S) & 1) ^ 1);
         const uint32_t row = sA + s * TC_A_STAGE + r * 128;
@@ -381,6 +404,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) arrive_full(full0 + 8 * s);
+        ++g;
+      };
+      float va[28], vb[28], vc[28];                // two tiles of loads in flight: a tile period is shorter than the load latency
+      load_patch(va);
+      load_patch(vb);
+      for (int tile = group0; tile < p.num_tiles;) {
+        load_patch(vc); emit(va); tile += ngroups;
+        if (tile >= p.num_tiles) break;
+        load_patch(va); emit(vb); tile += ngroups;
+        if (tile >= p.num_tiles) break;
+        load_patch(vb); emit(vc); tile += ngroups;
       }
     }
   } else if (warp == 4) {
@@ -462,7 +496,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     }
     __syncwarp();
   } else {
-    epilogue_role<CL>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 6) >> 2, rank, group0, ngroups);
+    // bulk_out: 8 staging blocks of 32 rows x Cout x 2 B behind the bias vector
+    const uint32_t stage0 = (smem_u32(s_bias) + 4u * (uint32_t)(((p.Cout + 31) & ~31) + 32) + 127u) & ~127u;
+    epilogue_role<CL>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 6) >> 2, rank, group0, ngroups,
+                      stage0 + (uint32_t)(warp - 6) * 64u * (uint32_t)p.Cout);
   }
 
   tc_fence_before();
@@ -769,6 +806,7 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
                ((uintptr_t)p->bias) % 16 == 0 &&
                (!p->residual || (p->res_dtype == op_dtype && p->res_cstride % 8 == 0 && p->res_coffset % 8 == 0 &&
                                  ((uintptr_t)p->residual) % 16 == 0));
+  t.bulk_out = 0;
   t.vec_f32 = 0;
   if (!t.fast_out && !p->residual && t.relu_cend % 4 == 0 && p->Cout % 4 == 0 && ((uintptr_t)p->bias) % 16 == 0) {
     bool ok = true;
@@ -856,6 +894,13 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
   }
   pl->smem = t.a_mode == A_HALO ? (size_t)t.sa * t.a_slot + (size_t)t.sb * t.tps * t.bn * TC_BK * 2 + 8 * (2 * t.sa + 2 * t.sb + 4) + 64 + bias_bytes + 1024 :
              (size_t)pl->stages * stage_bytes + 24 * pl->stages + 64 + 4 * (((size_t)p->Cout + 31) / 32 * 32 + 32) + 1024;
+  // bulk-copy epilogue: pixel-linear tiles (stem / gather / flat), the whole pixel in one tile, dense output map, small rows
+  if (t.fast_out && (t.a_mode == A_STEM || t.a_mode == A_GATHER || (t.a_mode == A_TMA && t.flat)) && t.n_tiles_n == 1 && t.cluster == 1 &&
+      !p->pool2 && p->Cout <= 64 && s0.pix_stride == p->Cout && s0.img_stride == (long long)p->Ho * p->Wo * p->Cout &&
+      pl->smem + 128 + 8 * 64 * (size_t)p->Cout <= 232448) {
+    t.bulk_out = 1;
+    pl->smem += 128 + 8 * 64 * (size_t)p->Cout;
+  }
   pl->grid = std::min(t.num_tiles, num_sms() * (t.a_mode == A_HALO ? t.occ : 1) / t.cluster) * t.cluster;
 
   // weights: [Cout_pad][KH*KW*Cin_pad] 16-bit, K-major; box = 64 (K) x BN (Cout), SWIZZLE_128B, OOB rows read as zero
