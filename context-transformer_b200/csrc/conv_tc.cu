@@ -90,12 +90,131 @@ __device__ __forceinline__ bool tile_row_pixel(const TcParams& p, int mt, int r,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Lean epilogue for the common case (one 16-bit output segment, 8-channel aligned: TcParams::fast_out), specialised at
+// compile time on fused pooling / residual / bulk-copy output so that the per-chunk code is branch-free: on the layers
+// with little K (the stem, conv1_2) the epilogue warps, not the MMAs, set the pace (ncu source view: ~320 warp
+// instructions per 32-column chunk in the generic path below, most of them flag tests and 64-bit index arithmetic).
+template <int CL, bool POOL, bool RES, bool BULK>
+__device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const float* s_bias, uint32_t tmem_base, uint32_t accf0, uint32_t acce0,
+                                                   int warp, int lane, uint32_t eset, int rank, int group0, int ngroups, uint32_t stage_smem) {
+  const int q = warp & 3;
+  const int BN = p.bn, Cout = p.Cout, relu_cend = p.relu ? p.relu_cend : 0;     // ReLU on channels < relu_cend (multiple of 8)
+  const int r = q * 32 + lane;
+  const bool bf16 = p.is_bf16 != 0;
+  uint16_t* const seg_ptr = reinterpret_cast<uint16_t*>(p.segs.seg[0].ptr) + p.segs.seg[0].ch_offset;
+  const long long img_stride = p.segs.seg[0].img_stride;
+  const int pix_stride = p.segs.seg[0].pix_stride;
+  const uint32_t stage_row = stage_smem + (uint32_t)(lane * Cout) * 2u;
+  uint32_t lt = eset;
+  for (int tile = group0 + (int)eset * ngroups; tile < p.num_tiles; tile += 2 * ngroups, lt += 2) {
+    const uint32_t buf = lt & 1;
+    const int mg = tile / p.n_tiles_n, n0 = (tile - mg * p.n_tiles_n) * BN, mt = mg * CL + rank;
+    int n_img, pix;
+    bool row_ok;
+    if (BULK) {            // pixel-linear tile of a dense map: the batch is one long pixel row (no per-tile division)
+      n_img = 0; pix = mt * TC_BM + r; row_ok = pix < p.M;
+    } else {
+      row_ok = tile_row_pixel(p, mt, r, n_img, pix);
+    }
+    long long opix = pix;
+    bool store = row_ok;
+    if (POOL) {            // row r = pixel (r / TW, r % TW) of the patch: 2 x 2 partners are lanes ^1 and ^TW; even/even lane stores
+      const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
+      opix = (long long)(oy >> 1) * (p.Wo >> 1) + (ox >> 1);
+      store = row_ok && !(lane & (1 | p.TW));
+    }
+    uint16_t* const out = seg_ptr + (long long)n_img * img_stride + opix * pix_stride;
+    const uint16_t* res = nullptr;
+    if (RES) res = reinterpret_cast<const uint16_t*>(p.residual) + ((long long)n_img * p.Ho * p.Wo + pix) * p.res_cstride + p.res_coffset;
+    const int c_end = min(Cout, n0 + BN);
+    mbar_wait(accf0 + 8 * buf, (lt >> 1) & 1);
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.acc_stride + ((uint32_t)(q * 32) << 16);
+    if (BULK) {                                                   // the previous tile's bulk store has read the staging rows
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int c0 = n0; c0 < c_end; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_d + (uint32_t)(c0 - n0), v);
+      tmem_ld_wait();
+      if (!POOL && !row_ok) continue;
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        const int c = c0 + gq * 8;
+        if (c < c_end) {
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
+          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
+          float f[8] = {__uint_as_float(v[gq * 8 + 0]) + b0.x, __uint_as_float(v[gq * 8 + 1]) + b0.y,
+                        __uint_as_float(v[gq * 8 + 2]) + b0.z, __uint_as_float(v[gq * 8 + 3]) + b0.w,
+                        __uint_as_float(v[gq * 8 + 4]) + b1.x, __uint_as_float(v[gq * 8 + 5]) + b1.y,
+                        __uint_as_float(v[gq * 8 + 6]) + b1.z, __uint_as_float(v[gq * 8 + 7]) + b1.w};
+          if (RES) {
+            if (row_ok) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(res + c);
+              const float2 r0 = unpack2(rv.x, bf16), r1 = unpack2(rv.y, bf16), r2 = unpack2(rv.z, bf16), r3 = unpack2(rv.w, bf16);
+              f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y; f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+            }
+          }
+          if (c < relu_cend) {                                      // warp-uniform
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+          }
+          if (POOL) {                                               // max is exact in any precision: pool the fp32 values
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 1));
+              f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], p.TW));
+            }
+          }
+          if (store) {
+            const uint32_t o0 = pack2(f[0], f[1], bf16), o1 = pack2(f[2], f[3], bf16), o2 = pack2(f[4], f[5], bf16), o3 = pack2(f[6], f[7], bf16);
+            if (BULK)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (uint32_t)c * 2u), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+            else
+              *reinterpret_cast<uint4*>(out + c) = make_uint4(o0, o1, o2, o3);
+          }
+        }
+      }
+    }
+    if (BULK) {
+      // rows of this warp are 32 consecutive pixels of a dense NHWC map: one contiguous block (valid rows are a prefix)
+      const uint32_t nrow = (uint32_t)__popc(__ballot_sync(0xffffffffu, row_ok));
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && nrow) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"(stage_smem), "r"(nrow * (uint32_t)Cout * 2u) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (CL == 2 && rank == 1) mbar_arrive_remote(acce0 + 8 * buf, 0);     // the leader's MMA owns the accumulator hand-off
+      else mbar_arrive(acce0 + 8 * buf);
+    }
+  }
+  if (BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Epilogue role (shared by the kernels below): epilogue set `eset` (four warps, one per TMEM lane quarter) drains
 // accumulator `eset` = local tiles eset, eset + 2, ...: tcgen05.ld, + bias (BatchNorm folded) [+ residual] [ReLU]
 // [2x2 max-pool], convert, vectorised NHWC store(s).
 template <int CL>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_bias, uint32_t tmem_base, uint32_t accf0, uint32_t acce0,
                                               int warp, int lane, uint32_t eset, int rank, int group0, int ngroups, uint32_t stage_smem = 0u) {
+    if (p.fast_out) {
+#define CTX_EPI_FAST(POOL, RES, BULK) epilogue_fast_role<CL, POOL, RES, BULK>(p, s_bias, tmem_base, accf0, acce0, warp, lane, eset, rank, group0, ngroups, stage_smem)
+      const bool res = p.residual != nullptr;
+      if (p.bulk_out) { if (res) CTX_EPI_FAST(false, true, true); else CTX_EPI_FAST(false, false, true); }
+      else if (p.pool2) CTX_EPI_FAST(true, false, false);           // fused pooling never has a residual (tc_supported)
+      else if (res) CTX_EPI_FAST(false, true, false);
+      else CTX_EPI_FAST(false, false, false);
+#undef CTX_EPI_FAST
+      return;
+    }
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int BN = p.bn;
     const int r = q * 32 + lane;
