@@ -11,5 +11,5 @@ ncu --profile-from-start off --set full --clock-control none --import-source on 
 ncu -i /tmp/rep/conv.ncu-rep --page raw --csv > gpurun_out/${T}_conv_raw.csv 2>/dev/null
 ncu --profile-from-start off --set full --clock-control none -k regex:attention -c 1 -f -o /tmp/rep/attn python bench.py --quick --no-graph --steps 1 --warmup 3 > gpurun_out/${T}_ncu_attn.log 2>&1
 ncu -i /tmp/rep/attn.ncu-rep --page raw --csv > gpurun_out/${T}_attn_raw.csv 2>/dev/null
-tail -3 gpurun_out/${T}_ncu_launch.log gpurun_out/${T}_ncu_conv.log gpurun_out/${T}_ncu_attn.log
+tail -n 3 gpurun_out/${T}_ncu_launch.log gpurun_out/${T}_ncu_conv.log gpurun_out/${T}_ncu_attn.log
 wc -l gpurun_out/${T}_*.csv
