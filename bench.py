@@ -190,6 +190,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--size', type=int, default=SIZE, choices=[300, 512], help='extra (non-contract) workload: 512 uses the ft head (BASELINE config 3)')
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='images per GPU (contract default 32)')
+    ap.add_argument('--nms', default=None, choices=['hard', 'linear', 'gaussian'],
+                    help='post-processing NMS: default hard at 300 (test.py), linear soft-NMS at 512 (BASELINE config 3: sigma .5, Nt .3, threshold .001)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='plain launches instead of one CUDA-graph replay')
     ap.add_argument('--quick', action='store_true', help='device-resident forward only (for ncu): no e2e, per-op or CPU legs')
@@ -230,7 +232,13 @@ def main():
     net.to(dev)
     cfg = ctx.VOC_512 if size == 512 else ctx.VOC_300
     priors = ctx.PriorBox(cfg).forward().to(dev)
-    post = ctx.DetectPost(21, 0, cfg)
+    nms_kind = args.nms or ('linear' if size == 512 else 'hard')
+    from context_transformer_b200 import detection as _det
+    if nms_kind == 'hard':
+        post = ctx.DetectPost(21, 0, cfg)
+    else:
+        post = ctx.DetectPost(21, 0, cfg, nms_thresh=0.3, soft_sigma=0.5, soft_threshold=0.001,
+                              nms_method=_det.NMS_SOFT_LINEAR if nms_kind == 'linear' else _det.NMS_SOFT_GAUSSIAN)
     B = args.batch
     x_host = synth.seeded_input(B, size, seed=rank).pin_memory()
     x_dev = x_host.to(dev)
@@ -425,7 +433,7 @@ def main():
             'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'fp16': 'f16', 'fp32': 'f32'}[args.precision], 'data': 'synthetic',
             'config': workload_config(args.precision, n_gpus, {'detections_per_batch_e2e': n_det[0], 'batch_per_gpu': B,
                                                                 'cuda_graph': bool(eng.graph_ready),
-                                                                'graph_lanes': bool(eng.use_lanes), 'tile_autotune': bool(eng.autotune)},
+                                                                'graph_lanes': bool(eng.use_lanes), 'tile_autotune': bool(eng.autotune), 'nms': nms_kind},
                                       size=size, batch=B),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -436,7 +444,8 @@ def main():
                                 'chain with one batch in flight' % ('all-gather, ' if world > 1 else '')},
             'gpu_launches': int(launches), 'roofline': roofline,
             'post': {'metric': 'decode+NMS us/img', 'value': post_us, 'unit': 'us/image',
-                     'includes': 'decode + score + threshold 0.01 + per-class NMS 0.45 + top-200 (test.py:133-161), predictions resident in HBM'}}
+                     'includes': 'decode + score + threshold 0.01 + per-class %s + top-200 (test.py:133-161), predictions resident in HBM'
+                                 % ('NMS 0.45' if nms_kind == 'hard' else nms_kind + ' soft-NMS (sigma .5, Nt .3, threshold .001; cpu_nms.pyx:70-163, exact positional semantics)')}}
 
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -200,10 +200,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       tma_load_2d(wstage + AT_TILE_W, &tm_w, 0, AT_DP, w_full);   // theta' lo
     }
     __syncwarp();
-    for (int u = 0; u < 2 * T; ++u) {
-      const int s = u % NST, j = u < T ? u : u - T;
+    for (int u = 0, s = 0, ph = 1; u < 2 * T; ++u) {             // ring slot / EMPTY parity tracked incrementally (no division)
+      const int j = u < T ? u : u - T;
       if (u == NST - 1) { mbar_wait(xq_done, 0); mbar_wait(xq_done + 8, 0); }
-      mbar_wait(kv_empty + 8 * s, ((u / NST) & 1) ^ 1);
+      mbar_wait(kv_empty + 8 * s, ph);
       if (elect_one()) {
         const uint32_t dst = sKV + s * STAGE;
         mbar_arrive_expect_tx(kv_full + 8 * s, u < T ? AT_TILE_K : STAGE);
@@ -215,6 +215,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         }
       }
       __syncwarp();
+      if (++s == NST) { s = 0; ph ^= 1; }
     }
   } else if (warp == 9) {
     // ================= MMA issuer ================= (whole warp converged, one elected lane issues)
@@ -241,9 +242,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       __syncwarp();
     }
     // ---- pass A: S = Qh Kh^T only — good to ~|q||k| 2^-10, enough for a softmax reference maximum
+    int s = 0, ph = 0, s_prev = 0;                               // ring slot / FULL parity of the key tile being consumed
     for (int u = 0; u < T; ++u) {
-      const int s = u % NST;
-      mbar_wait(kv_full + 8 * s, (u / NST) & 1);
+      mbar_wait(kv_full + 8 * s, ph);
       for (int t = 0; t < AT_QT; ++t) {
         if (u == 0) mbar_wait(q_ready + 8 * t, 0);
         // pass A ping-pongs S_t between its own columns and the (still unused) O / spare columns: u even -> 128 t,
@@ -260,12 +261,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         }
         __syncwarp();
       }
+      if (++s == NST) { s = 0; ph ^= 1; }
     }
     // ---- pass B: exact logits (12 UMMAs per q-tile and key tile) and O += P V (8 UMMAs)
     for (int j = 0; j <= T; ++j) {
+      const int s_cur = s;
       if (j < T) {
-        const int u = T + j, s = u % NST;
-        mbar_wait(kv_full + 8 * s, (u / NST) & 1);
+        mbar_wait(kv_full + 8 * s, ph);
         if (lane == 0) AT_DBG(j * 16 + 0);
         for (int t = 0; t < AT_QT; ++t) {
           mbar_wait(s_empty + 8 * (2 * t), ((nA0 + j) & 1) ^ 1);       // pass B uses S buffer 0 only (buffer 1 became O)
@@ -288,8 +290,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
           __syncwarp();
         }
       }
+      if (j < T && ++s == NST) { s = 0; ph ^= 1; }
       if (j > 0) {
-        const int jj = j - 1, s = (T + jj) % NST;
+        const int jj = j - 1, s = s_prev;
         for (int t = 0; t < AT_QT; ++t) {
           if (lane == 0 && t == 0) AT_DBG(jj * 16 + 3);
           mbar_wait(p_full + 8 * t, jj & 1);
@@ -308,6 +311,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
           if (lane == 0 && t == 1) AT_DBG(jj * 16 + 6);
         }
       }
+      s_prev = s_cur;
     }
   } else {
     // ================= softmax warps (4 per q-tile) + epilogue =================
