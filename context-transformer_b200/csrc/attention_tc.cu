@@ -429,6 +429,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     if (warp == 0 && lane == 0) AT_DBG(506);
 
     // ---- epilogue: z = x + (O/l)*Wz ; z/||z|| ; OBJ_Target*scale ; [fc_base] ; [softmax] ----
+    // classifier weights: fetched into registers while the last PV MMAs still run, stored once P_t is free
+    constexpr int W_PER_THREAD = (NN * D + D + AT_BQ - 1) / AT_BQ;
+    float wreg[W_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < W_PER_THREAD; ++k) {
+      const int i = r + k * AT_BQ;
+      wreg[k] = i < NN * D ? p.obj_w[i] : (i < NN * D + D ? p.Wz[i - NN * D] : 0.f);
+    }
     mbar_wait(pv_done + 8 * t, (T - 1) & 1);                 // all MMAs of this q-tile are complete: Q_t is dead
     tc_fence_after();
     // Q_t and P_t are free now.  Q_t <- the conf rows again (bulk copy), P_t <- classifier weights + output staging.
@@ -443,8 +451,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     float* s_fc = s_wz + D;                                                               // incre: [D][D] + [D]
     const int n_out = NN + (p.incre ? D : 0);
     float* s_out = s_fc + (p.incre ? D * D + D : 0);                                      // [128][n_out]
-    for (int i = r; i < NN * D; i += AT_BQ) s_obj[i] = p.obj_w[i];
-    for (int i = r; i < D; i += AT_BQ) s_wz[i] = p.Wz[i];
+#pragma unroll
+    for (int k = 0; k < W_PER_THREAD; ++k) {                 // s_wz directly follows s_obj
+      const int i = r + k * AT_BQ;
+      if (i < NN * D + D) s_obj[i] = wreg[k];
+    }
     if (p.incre) {
       for (int i = r; i < D * D; i += AT_BQ) s_fc[i] = p.fc_w[i];
       for (int i = r; i < D; i += AT_BQ) s_fc[D * D + i] = p.fc_b[i];
@@ -478,14 +489,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
           orow_s[c] = (a + s_fc[D * D + c]) + x[c];
         }
       }
+      // cosine classifier (OBJ_Target rows are unit vectors).  Feature chunks outermost, classes innermost: NN independent
+      // accumulation chains are in flight and each 128-bit weight load feeds four FMAs (per class the sum still runs over
+      // d in ascending order).  With classes outermost this loop was one D-deep dependent chain after another and the
+      // whole CTA waited on it at its end.
       float nov[NN];
 #pragma unroll
-      for (int c = 0; c < NN; ++c) {
-        float a = 0.f;
+      for (int c = 0; c < NN; ++c) nov[c] = 0.f;
+      static_assert(D % 4 == 0 || D == 15, "classifier loop assumes 16-byte rows (D % 4 == 0) or the scalar path");
+      if (D % 4 == 0) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) a = fmaf(s_obj[c * D + d], z[d], a);
-        nov[c] = a * p.scale;
+        for (int d = 0; d < D; d += 4) {
+#pragma unroll
+          for (int c = 0; c < NN; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(s_obj + c * D + d);
+            nov[c] = fmaf(w.x, z[d], nov[c]); nov[c] = fmaf(w.y, z[d + 1], nov[c]);
+            nov[c] = fmaf(w.z, z[d + 2], nov[c]); nov[c] = fmaf(w.w, z[d + 3], nov[c]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+          for (int c = 0; c < NN; ++c) nov[c] = fmaf(s_obj[c * D + d], z[d], nov[c]);
       }
+#pragma unroll
+      for (int c = 0; c < NN; ++c) nov[c] *= p.scale;
       if (p.apply_softmax) {
         float mxo = -INFINITY;
 #pragma unroll
