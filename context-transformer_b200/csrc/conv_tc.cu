@@ -943,6 +943,9 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
   t.cluster_req = tune_cluster;
   t.n_tiles_n = std::max(cdiv(p->Cout, 256), std::min(tune_n, cdiv(p->Cout, 16)));
   t.bn = (cdiv(p->Cout, t.n_tiles_n) + 15) / 16 * 16;
+  // CTA pairs split the weight tile in two halves of a multiple of 16 rows: an explicitly requested pair rounds the tile
+  // up to a multiple of 32 (the fused heads: 396 channels = 2 x 208 -> 2 x 224) when that does not cost another tile
+  if (tune_cluster == 2 && t.bn % 32 && t.bn + 16 <= 256) t.bn += 16;
   t.n_tiles_n = cdiv(p->Cout, t.bn);
 
   int tw = 0, th = 0;
@@ -962,9 +965,9 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
   const int m_tiles = patches ? (t.flat ? t.tiles_x : p->N * t.tiles_x * t.tiles_y) : cdiv(t.M, TC_BM);
   t.m_tiles = m_tiles;
   {
-    // CTA pairs (one tcgen05.mma.cta_group::2 spanning both SMs of a cluster of two, each CTA staging half of the weight
-    // tile) are implemented and parity-tested, but on this network they measure within 2 % of the single-CTA path
-    // (profiles/README.md), so they stay opt-in: CTX_CONV_CLUSTER=2.
+    // CTA pairs: one tcgen05.mma.cta_group::2 spanning both SMs of a cluster of two, each CTA staging half of the weight
+    // tile.  Chosen per layer by the autotuner (they win on the wide trunk layers); CTX_CONV_CLUSTER=2 makes them the
+    // default where eligible.
     const char* e = getenv("CTX_CONV_CLUSTER");
     const bool want2 = tune_cluster ? tune_cluster == 2 : (e && e[0] == '2');
     t.cluster = (want2 && m_tiles >= 2 && t.bn % 32 == 0 && t.bn >= 128 && t.a_mode != A_HALO) ? 2 : 1;
