@@ -135,3 +135,32 @@ def records_to_all_boxes(records, counts, num_classes):
         for j in np.unique(cls):
             all_boxes[j][i] = r[cls == j, :5].copy()
     return all_boxes
+
+
+class DetectionCollector(object):
+    """The reference's evaluation hand-off (test.py:107-108, 150-154, 171-175): ``all_boxes[j][i]`` = float32 ndarray
+    ``[k, 5]`` (x1, y1, x2, y2, score) for class j >= 1 and image i of the dataset (class 0 keeps the reference's empty
+    lists), filled batch by batch from the fixed-shape records of ``DetectPost`` / ``shard.gather_records`` and pickled
+    as ``detections.pkl`` so that ``dataset.evaluate_detections(all_boxes, save_folder)`` runs unchanged."""
+
+    def __init__(self, num_images, num_classes):
+        self.num_images, self.num_classes = int(num_images), int(num_classes)
+        self.all_boxes = [[[] for _ in range(self.num_images)] for _ in range(self.num_classes)]
+
+    def add(self, first_image, records, counts):
+        """records [B, K, 6] / counts [B] of images first_image .. first_image + B - 1 (host or device tensors)."""
+        import numpy as np
+        batch = records_to_all_boxes(records, counts, self.num_classes)
+        B = int(records.shape[0])
+        if first_image < 0 or first_image + B > self.num_images:
+            raise IndexError('images %d..%d outside the dataset of %d' % (first_image, first_image + B - 1, self.num_images))
+        for j in range(1, self.num_classes):
+            for i in range(B):
+                self.all_boxes[j][first_image + i] = np.ascontiguousarray(batch[j][i], dtype=np.float32)
+        return self
+
+    def save(self, det_file):
+        import pickle
+        with open(det_file, 'wb') as f:
+            pickle.dump(self.all_boxes, f, pickle.HIGHEST_PROTOCOL)
+        return det_file

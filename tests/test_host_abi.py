@@ -158,3 +158,33 @@ def test_records_to_all_boxes():
     ab = ctx.records_to_all_boxes(rec, torch.tensor([3]), 21)
     assert ab[3][0].shape == (2, 5) and ab[17][0].shape == (1, 5) and ab[1][0].shape == (0, 5)
     assert ab[3][0][1, 4] == np.float32(.8)
+
+
+def test_detection_collector_builds_the_reference_result_structure(tmp_path):
+    """test.py:107-108,150-154,171-172: all_boxes[class][image] float32 [k,5] arrays (class 0 untouched), pickled."""
+    import pickle
+    import numpy as np
+    import torch
+    import context_transformer_b200 as ctx
+    K = 8
+    rec = torch.zeros(3, K, 6)
+    cnt = torch.tensor([3, 0, 11], dtype=torch.int32)                 # image 2 kept more than max_out rows: truncated to K
+    rows0 = torch.tensor([[1, 2, 3, 4, .9, 2], [5, 6, 7, 8, .5, 2], [0, 0, 9, 9, .7, 7]])
+    rec[0, :3] = rows0
+    rec[2] = torch.arange(K * 6, dtype=torch.float32).view(K, 6)
+    rec[2, :, 5] = torch.tensor([1, 1, 3, 3, 3, 20, 20, 20])
+    col = ctx.DetectionCollector(num_images=5, num_classes=21)
+    col.add(1, rec, cnt)
+    ab = col.all_boxes
+    assert all(ab[0][i] == [] for i in range(5))                       # background class keeps the reference's empty lists
+    assert ab[2][1].dtype == np.float32 and np.array_equal(ab[2][1], rows0[:2, :5].numpy())
+    assert np.array_equal(ab[7][1], rows0[2:3, :5].numpy())
+    assert all(ab[j][2].shape == (0, 5) for j in range(1, 21))         # image with no detection: empty [0,5] arrays
+    assert [ab[j][3].shape[0] for j in (1, 3, 20)] == [2, 3, 3] and np.array_equal(ab[3][3], rec[2, 2:5, :5].numpy())
+    assert ab[5][0] == [] and ab[5][4] == []                           # images not yet processed
+    f = col.save(str(tmp_path / 'detections.pkl'))
+    back = pickle.load(open(f, 'rb'))
+    assert np.array_equal(back[20][3], ab[20][3]) and back[0][0] == []
+    import pytest
+    with pytest.raises(IndexError):
+        col.add(4, rec, cnt)
