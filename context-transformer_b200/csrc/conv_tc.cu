@@ -127,6 +127,30 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
     const uint16_t* res = nullptr;
     if (RES) res = reinterpret_cast<const uint16_t*>(p.residual) + ((long long)n_img * p.Ho * p.Wo + pix) * p.res_cstride + p.res_coffset;
     const int c_end = min(Cout, n0 + BN);
+    // Transposed stores (plain case): a thread owns one output row, so its 16-byte pieces of a 32-column chunk would go out
+    // as four requests touching 32 half-written sectors each.  The four lanes of a quad exchange pieces (4 x 4 transpose, 16
+    // shuffles per chunk) so that a request writes, per row, the 64 contiguous bytes of the chunk from four adjacent lanes:
+    // whole 32-byte sectors, half as many of them.
+    constexpr bool TR = !POOL && !BULK;
+    unsigned long long outq[4] = {0ull, 0ull, 0ull, 0ull};
+    unsigned okbits = 0u;
+    if (TR) {
+      okbits = __ballot_sync(0xffffffffu, row_ok);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) outq[k] = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)out, (lane & ~3) + k);
+    }
+    // residual (RFB shortcut): the 64 bytes a thread needs per 32-column chunk are fetched one chunk ahead — the first
+    // chunk before the accumulator is even complete — so their latency hides behind the MMAs / the previous chunk
+    // (ncu what-if: without this the ConvLinear layers spent 70 % of their time waiting on these loads)
+    uint4 rnext[4];
+    auto load_res = [&](int c0) {
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        const int c = c0 + gq * 8;
+        rnext[gq] = (row_ok && c < c_end) ? __ldg(reinterpret_cast<const uint4*>(res + c)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    if (RES) load_res(n0);
     mbar_wait(accf0 + 8 * buf, (lt >> 1) & 1);
     tc_fence_after();
     const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.acc_stride + ((uint32_t)(q * 32) << 16);
@@ -138,11 +162,19 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
     for (int c0 = n0; c0 < c_end; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_d + (uint32_t)(c0 - n0), v);
+      uint4 rcur[4];
+      if (RES) {
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) rcur[gq] = rnext[gq];
+        if (c0 + 32 < c_end) load_res(c0 + 32);
+      }
       tmem_ld_wait();
-      if (!POOL && !row_ok) continue;
+      if (BULK && !row_ok) continue;
+      uint4 o[4];
 #pragma unroll
       for (int gq = 0; gq < 4; ++gq) {
         const int c = c0 + gq * 8;
+        o[gq] = make_uint4(0u, 0u, 0u, 0u);
         if (c < c_end) {
           const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
           const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
@@ -152,7 +184,7 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
                         __uint_as_float(v[gq * 8 + 6]) + b1.z, __uint_as_float(v[gq * 8 + 7]) + b1.w};
           if (RES) {
             if (row_ok) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(res + c);
+              const uint4 rv = rcur[gq];
               const float2 r0 = unpack2(rv.x, bf16), r1 = unpack2(rv.y, bf16), r2 = unpack2(rv.z, bf16), r3 = unpack2(rv.w, bf16);
               f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y; f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
             }
@@ -168,13 +200,38 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
               f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], p.TW));
             }
           }
-          if (store) {
-            const uint32_t o0 = pack2(f[0], f[1], bf16), o1 = pack2(f[2], f[3], bf16), o2 = pack2(f[4], f[5], bf16), o3 = pack2(f[6], f[7], bf16);
+          o[gq] = make_uint4(pack2(f[0], f[1], bf16), pack2(f[2], f[3], bf16), pack2(f[4], f[5], bf16), pack2(f[6], f[7], bf16));
+          if (!TR && store) {
             if (BULK)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (uint32_t)c * 2u), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (uint32_t)c * 2u), "r"(o[gq].x), "r"(o[gq].y), "r"(o[gq].z),
+                           "r"(o[gq].w) : "memory");
             else
-              *reinterpret_cast<uint4*>(out + c) = make_uint4(o0, o1, o2, o3);
+              *reinterpret_cast<uint4*>(out + c) = o[gq];
           }
+        }
+      }
+      if (TR) {
+        // 4 x 4 transpose of the 16-byte pieces inside each quad: afterwards lane j of the quad holds piece j of rows 0..3
+        const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          uint4 t = hi2 ? o[k] : o[k + 2];
+          t.x = __shfl_xor_sync(0xffffffffu, t.x, 2); t.y = __shfl_xor_sync(0xffffffffu, t.y, 2);
+          t.z = __shfl_xor_sync(0xffffffffu, t.z, 2); t.w = __shfl_xor_sync(0xffffffffu, t.w, 2);
+          if (hi2) o[k] = t; else o[k + 2] = t;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+          uint4 t = hi1 ? o[k] : o[k + 1];
+          t.x = __shfl_xor_sync(0xffffffffu, t.x, 1); t.y = __shfl_xor_sync(0xffffffffu, t.y, 1);
+          t.z = __shfl_xor_sync(0xffffffffu, t.z, 1); t.w = __shfl_xor_sync(0xffffffffu, t.w, 1);
+          if (hi1) o[k] = t; else o[k + 1] = t;
+        }
+        const int c = c0 + (lane & 3) * 8;
+        if (c < c_end) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if ((okbits >> ((lane & ~3) + k)) & 1u) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>((uintptr_t)outq[k]) + c) = o[k];
         }
       }
     }
