@@ -424,7 +424,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024-B alignment
   const uint32_t sA = smem_base, sB = smem_base + S * TC_A_STAGE;
   const uint32_t bars = sB + S * B_STAGE;
-  const uint32_t full0 = bars, empty0 = bars + 8 * S, pfull0 = bars + 16 * S, accf0 = bars + 24 * S, acce0 = accf0 + 16,
+  const uint32_t full0 = bars, empty0 = bars + 8 * S, accf0 = bars + 24 * S, acce0 = accf0 + 16,
                  tmem_slot = acce0 + 16;
   // per-channel epilogue vector (bias with BatchNorm folded), staged once per CTA: [ceil32(Cout) + 32] floats
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 24 * S + 64 - smem_u32(smem_raw)));
@@ -444,7 +444,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       // arrivals per phase: the (leader's) TMA thread, plus four producer warps per CTA unless the TMA unit stages A too;
       // in pair mode every producer of either CTA signals the LEADER's barrier (the peer's own full barriers stay unused)
       const uint32_t full_count = p.a_mode == A_TMA ? 1u : 1u + 4u * (uint32_t)CL;
-      for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, full_count); mbar_init(empty0 + 8 * s, 1); mbar_init(pfull0 + 8 * s, 1); }
+      for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, full_count); mbar_init(empty0 + 8 * s, 1); }
       // pair mode: the leader's MMA also waits for the peer's four epilogue warps (remote arrivals)
       for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 4u * (uint32_t)CL); }
       fence_barrier_init();
