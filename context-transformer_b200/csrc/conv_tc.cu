@@ -6,9 +6,9 @@
 //   D[m, co] = sum_{tap, ci} A[m, (tap, ci)] * Wt[co, (tap, ci)]          fp32 accumulate in TMEM
 //   A  = the NHWC activation gathered on the fly (im2col never exists in HBM)
 //
-// One CTA per SM walks a static round-robin list of (128 output pixels) x (BN output channels) tiles;
-// K is walked in steps of 64 channels of one filter tap through a ring of S shared-memory stages
-// {A tile 16 KB, B tile BN*128 B}.  Warp roles (448 threads):
+// conv_tc_kernel: one CTA per SM walks a static round-robin list of (128 output pixels) x (BN output channels) tiles;
+// K is walked channel block by channel block, taps innermost, in steps of 64 channels of one filter tap through a
+// ring of S shared-memory stages {A tile 16 KB, B tile BN*128 B} released in commit groups.  Warp roles (448 threads):
 //   warps 0-3  im2col gather producers (mode GATHER): 16-byte cp.async with zero-fill for padding /
 //              channel tails, written straight into the 128B-swizzled K-major layout of the UMMA
 //              descriptor.  M is the flattened (n, oy, ox) pixel index of the whole batch: no tile waste
@@ -17,19 +17,26 @@
 //              27-value 3x3x3 patch in registers and st.shared it as one 64-channel K-step row, so conv1_1
 //              runs on the tensor cores without an im2col tensor in HBM.
 //   warp 4     TMA producer: the BN x 64 weight tile of each K-step (cp.async.bulk.tensor.2d), and in
-//              mode TMA also the activation tile: the output tile is a TW x TH pixel patch of one image
+//              mode TMA also the activation tile: the output tile is a TW x TH <= 128 pixel patch of one image
 //              and the A tile of tap (ky, kx) is the 4-D box {64 ch, TW, TH, 1} at
-//              (x0 + kx*dil - pad, y0 + ky*dil - pad); out-of-image pixels are zero-filled by the TMA unit,
-//              i.e. conv padding costs nothing and no thread touches an address (stride-1 convs with
-//              Cin % 64 == 0 on the large feature maps: the VGG trunk).
+//              (x0 + kx*dil - pad, y0 + ky*dil - pad); out-of-image pixels and channels past the slice are
+//              zero-filled by the TMA unit, i.e. conv padding costs nothing and no thread touches an address
+//              (stride-1 convs; 1x1 convs see the whole batch as one pixel row: "flat" 128-pixel runs).
 //   warp 5     TMEM allocator + MMA issuer: one elected lane issues 4 x tcgen05.mma (M128 x N=BN x K16,
-//              kind::f16) per K-step, tcgen05.commit's the stage back to the producers and, after the
+//              kind::f16) per K-step, tcgen05.commit's ring slots back to the producers and, after the
 //              last K-step of a tile, the accumulator to the epilogue.  Two accumulators (2 x 256 TMEM
-//              columns) let tile i+1 start while tile i drains.
+//              columns) let tile i+1 start while tile i drains.  CL = 2: CTA pairs, one cta_group::2 MMA (M = 256)
+//              issued by the leader, each CTA staging half of the weight tile.
 //   warps 6-13 epilogue, two sets of four warps (set 0 drains accumulator 0 = even tiles, set 1 accumulator 1 =
-//              odd tiles, so two tiles drain concurrently): tcgen05.ld the accumulator, + bias (BatchNorm folded) [+ residual] [ReLU],
-//              convert, vectorised NHWC store — or up to three fp32 segments for the fused
-//              loc / conf / obj heads (writes land directly in the concatenated [B,P,*] buffers).
+//              odd tiles, so two tiles drain concurrently): tcgen05.ld the accumulator, + bias (BatchNorm folded)
+//              [+ residual] [ReLU] [2x2 max-pool], convert, NHWC store — compile-time-specialised for the 16-bit
+//              single-segment case (residual prefetch, sector-aligned transposed stores, bulk-copy rows), generic
+//              for the up to three fp32 segments of the fused loc / conf / obj heads (writes land directly in the
+//              concatenated [B,P,*] buffers).
+// conv_halo_kernel (3x3 stride-1 convs): the tile's input neighbourhood is staged once and read through nine shifted
+// descriptor windows; optionally two CTAs per SM.  See its own header below.
+// Which kernel / tiling a layer uses is decided per layer by measurement (ctx_prog_autotune); every choice gives
+// bit-identical results.
 #include "tc_common.cuh"
 
 #include <algorithm>
