@@ -16,7 +16,7 @@ sm_100a CUDA behind the C ABI of ``include/ctx_b200.h``); nothing here falls bac
 """
 from .config import COCO_300, COCO_512, MBOX, VOC_300, VOC_512, num_priors
 from .prior_box import PriorBox
-from .detection import Detect, DetectionCollector, DetectPost, records_to_all_boxes
+from .detection import BaseTransform, Detect, DetectionCollector, DetectPost, records_to_all_boxes
 from .nms_wrapper import cpu_nms, cpu_soft_nms, gpu_nms, nms, nms_device, soft_nms
 from .box_utils import decode, encode, hard_negative_rank, jaccard, match, match_batch, point_form
 from .multibox_loss import MultiBoxLoss_combined
@@ -24,6 +24,6 @@ from .reweight import PrototypeAccumulator, init_reweight
 from .rfb_net import BasicConv, BasicRFB, BasicRFB_a, RFBNet, build_net
 
 __all__ = ['build_net', 'RFBNet', 'BasicConv', 'BasicRFB', 'BasicRFB_a', 'PriorBox', 'Detect', 'DetectPost',
-           'records_to_all_boxes', 'DetectionCollector', 'MultiBoxLoss_combined', 'nms', 'gpu_nms', 'cpu_nms', 'cpu_soft_nms', 'soft_nms',
+           'records_to_all_boxes', 'DetectionCollector', 'BaseTransform', 'MultiBoxLoss_combined', 'nms', 'gpu_nms', 'cpu_nms', 'cpu_soft_nms', 'soft_nms',
            'nms_device', 'match', 'match_batch', 'decode', 'encode', 'jaccard', 'point_form', 'hard_negative_rank',
            'init_reweight', 'PrototypeAccumulator', 'VOC_300', 'VOC_512', 'COCO_300', 'COCO_512', 'MBOX', 'num_priors']

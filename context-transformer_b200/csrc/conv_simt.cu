@@ -254,6 +254,22 @@ nchw_to_nhwc_kernel(const float* __restrict__ in, void* __restrict__ out, int N,
   }
 }
 
+// BaseTransform without the resize (data/data_augment.py:258-261 for an image that already has the network's size:
+// cv2.resize to the same size is a copy): x[n, c, y, x] = float(img[n, y, x, c]) - means[c], uint8 HWC -> fp32 CHW.
+// One thread per pixel: 3 bytes in (coalesced over the warp), three coalesced plane writes.
+__global__ void __launch_bounds__(256)
+u8hwc_to_f32chw_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, int N, int H, int W, float m0, float m1, float m2) {
+  const long long hw = (long long)H * W, total = (long long)N * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / hw, r = i - n * hw;
+    const uint8_t* px = img + i * 3;
+    float* o = out + n * 3 * hw + r;
+    o[0] = (float)px[0] - m0;
+    o[hw] = (float)px[1] - m1;
+    o[2 * hw] = (float)px[2] - m2;
+  }
+}
+
 // softmax over the last dimension (output activation, RFB_Net_vgg.py:279-285); one thread per row
 __global__ void __launch_bounds__(256)
 softmax_lastdim_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int cols) {
@@ -340,6 +356,15 @@ int nchw_to_nhwc_launch(const float* in, void* out, int N, int C, int H, int W, 
   return CTX_OK;
 }
 
+int base_transform_launch(const unsigned char* img, float* out, int N, int H, int W, const float* means3, cudaStream_t st) {
+  CTX_REQUIRE(img && out && means3 && N > 0 && H > 0 && W > 0, "base_transform: bad arguments");
+  long long total = (long long)N * H * W;
+  int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+  u8hwc_to_f32chw_kernel<<<blocks, 256, 0, st>>>(img, out, N, H, W, means3[0], means3[1], means3[2]);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
 int patch27_launch(const float* in, void* out, int N, int H, int W, int dtype, cudaStream_t st) {
   CTX_REQUIRE(in && out && N > 0 && H > 0 && W > 0, "patch27: bad arguments");
   CTX_REQUIRE(dtype == CTX_BF16 || dtype == CTX_F16, "patch27: 16-bit output only");
@@ -366,6 +391,9 @@ extern "C" int ctx_conv2d_simt(const CtxConvParams* p, void* stream) { return ct
 extern "C" int ctx_maxpool2d_nhwc(const CtxPoolParams* p, void* stream) { return ctx::maxpool_launch(p, (cudaStream_t)stream); }
 extern "C" int ctx_nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, int out_dtype, void* stream) {
   return ctx::nchw_to_nhwc_launch(in, out, N, C, H, W, out_dtype, (cudaStream_t)stream);
+}
+extern "C" int ctx_base_transform(const unsigned char* img_hwc, float* out_chw, int N, int H, int W, const float* means3, void* stream) {
+  return ctx::base_transform_launch(img_hwc, out_chw, N, H, W, means3, (cudaStream_t)stream);
 }
 extern "C" int ctx_nchw_to_patch27(const float* in, void* out, int N, int H, int W, int out_dtype, void* stream) {
   return ctx::patch27_launch(in, out, N, H, W, out_dtype, (cudaStream_t)stream);

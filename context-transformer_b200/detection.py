@@ -164,3 +164,40 @@ class DetectionCollector(object):
         with open(det_file, 'wb') as f:
             pickle.dump(self.all_boxes, f, pickle.HIGHEST_PROTOCOL)
         return det_file
+
+
+class BaseTransform(object):
+    """Mirror of reference ``data/data_augment.py:224-266`` for the inference path: ``transform(img)`` -> fp32 ``[3,S,S]``.
+    The mean subtraction and the HWC -> CHW change run on the GPU (``ctx_base_transform``); images must already have the
+    network's size — the reference's ``cv2.resize`` (a fixed-point bilinear kernel) is not reimplemented because it cannot be
+    pinned without cv2 in the build image, so other sizes raise instead of silently differing.  Batches:
+    ``transform.batch(imgs_u8[B,S,S,3])`` -> ``[B,3,S,S]`` on the device; or pass the uint8 batch straight to ``net(...)``."""
+
+    def __init__(self, resize, rgb_means, swap=(2, 0, 1), device='cuda'):
+        if tuple(swap) != (2, 0, 1):
+            raise ValueError('BaseTransform: only the reference swap (2, 0, 1) is supported')
+        self.resize, self.means, self.swap, self.device = int(resize), tuple(float(m) for m in rgb_means), tuple(swap), device
+
+    def batch(self, imgs):
+        import ctypes as C
+        import torch
+        t = torch.as_tensor(imgs)
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.size(3) != 3:
+            raise ValueError('BaseTransform.batch expects uint8 [B,H,W,3]')
+        if t.size(1) != self.resize or t.size(2) != self.resize:
+            raise NotImplementedError('BaseTransform: image size %dx%d != %d — resize on the host (cv2.resize) first; the on-device '
+                                      'path covers mean subtraction and layout only' % (t.size(1), t.size(2), self.resize))
+        t = t.to(self.device).contiguous()
+        _lib.require_cuda(t, 'imgs')
+        out = torch.empty(t.size(0), 3, self.resize, self.resize, device=t.device)
+        means = (C.c_float * 3)(*self.means)
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.lib().ctx_base_transform(t.data_ptr(), out.data_ptr(), t.size(0), self.resize, self.resize, means,
+                                                     _lib.current_stream_ptr()), 'ctx_base_transform')
+        return out
+
+    def __call__(self, img, target=None):
+        import torch
+        if target is not None:
+            raise NotImplementedError('BaseTransform with targets is the training-time path (host side, data_augment.py:249-256)')
+        return self.batch(torch.as_tensor(img).unsqueeze(0))[0]

@@ -82,6 +82,8 @@ class Engine(object):
         self.prog = C.c_void_p()
         _lib.check(self.L.ctx_prog_create(C.byref(self.prog)), 'ctx_prog_create')
         self.graph_ready = False
+        self.x_u8 = None
+        self.rgb_means = tuple(float(m) for m in getattr(net, 'rgb_means', (104.0, 117.0, 123.0)))   # test.py:87
         self.use_graph = use_graph
         # independent chains (RFB branches, per-level heads) on their own graph lanes; CTX_LANES=0 keeps one chain
         self.use_lanes = os.environ.get('CTX_LANES', '1') != '0'
@@ -461,7 +463,20 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     def load_input(self, x):
         """Stage ``x`` ([B,3,S,S], any device, fp32) into the program's input buffer (async on the
-        current stream; a pinned host tensor becomes one H2D copy)."""
+        current stream; a pinned host tensor becomes one H2D copy).  A uint8 ``[B,S,S,3]`` batch (cv2 images that already
+        have the network's size) takes the on-device ``BaseTransform`` path instead: a quarter of the H2D bytes, the
+        mean subtraction and HWC -> CHW change done by ``ctx_base_transform``."""
+        if x.dtype == torch.uint8:
+            B, _, S, _ = self.x_in.shape
+            if tuple(x.shape) != (B, S, S, 3):
+                raise ValueError('uint8 input must be [B,S,S,3] = %s (resize on the host first), got %s' % ((B, S, S, 3), tuple(x.shape)))
+            if self.x_u8 is None:
+                self.x_u8 = torch.empty(B, S, S, 3, dtype=torch.uint8, device=self.dev)
+            self.x_u8.copy_(x, non_blocking=True)
+            means = (C.c_float * 3)(*self.rgb_means)
+            _lib.check(self.L.ctx_base_transform(self.x_u8.data_ptr(), self.x_in.data_ptr(), B, S, S, means,
+                                                 _lib.current_stream_ptr(self.dev)), 'ctx_base_transform')
+            return
         if tuple(x.shape) != tuple(self.x_in.shape):
             raise ValueError('engine compiled for input %s, got %s' % (tuple(self.x_in.shape), tuple(x.shape)))
         self.x_in.copy_(x, non_blocking=True)

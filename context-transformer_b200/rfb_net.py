@@ -253,7 +253,7 @@ class RFBNet(nn.Module):
         if torch.device(self.device).type != 'cuda':
             raise RuntimeError("RFBNet inference runs only on a CUDA device (sm_100a kernels, no CPU fallback); "
                                "got model.device = %r" % (self.device,))
-        return self.engine(x.size(0)).run(x)
+        return self.engine(x.size(0)).run(x)           # fp32 [B,3,S,S], or uint8 [B,S,S,3] (on-device BaseTransform)
 
     # ---- training / prototype init: autograd expression of the same graph ---------------------
     def _forward_autograd(self, x, init=False):

@@ -346,3 +346,14 @@ def init_reweight_prototypes(conf_batches, label_batches, num_classes=21, settin
     if setting == 'incre':
         out = out[15:]
     return np.stack(out, 0)
+
+
+# --------------------------------------------------------------------------------------------
+# BaseTransform without the resize — data/data_augment.py:258-261 for an image of the network's size
+# --------------------------------------------------------------------------------------------
+def base_transform_same_size(img_u8, means=(104, 117, 123)):
+    """img_u8 [H,W,3] uint8 -> [3,H,W] float32: ``img.astype(np.float32)``, ``img -= means``, ``transpose(2,0,1)``
+    (cv2.resize to the image's own size is a plain copy, so these three statements are the whole transform)."""
+    img = img_u8.astype(F)
+    img -= np.asarray(means, F)
+    return img.transpose(2, 0, 1)

@@ -431,3 +431,24 @@ def test_two_gpu_shard_matches_single_gpu():
                         '--master-addr', '127.0.0.1', '--master-port', '29517',
                         os.path.join(root, 'tests', 'shard_check.py')], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and 'SHARD_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_base_transform_on_device_and_uint8_input():
+    """BaseTransform (data_augment.py:224-266) for images of the network's size: bit-exact against the numpy restatement of
+    its statements; a uint8 [B,S,S,3] batch fed to the network gives exactly the outputs of the fp32 [B,3,S,S] batch."""
+    from oracle import np_oracle
+    g = synth._gen(21, 'u8img')
+    imgs = torch.randint(0, 256, (2, 300, 300, 3), generator=g, dtype=torch.uint8)
+    want = np.stack([np_oracle.base_transform_same_size(i.numpy()) for i in imgs])
+    tr = ctx.BaseTransform(300, (104, 117, 123))
+    got = tr.batch(imgs)
+    assert got.dtype == torch.float32 and np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(tr(imgs[1].numpy()).cpu().numpy(), want[1])
+    with pytest.raises(NotImplementedError):
+        tr.batch(torch.zeros(1, 200, 300, 3, dtype=torch.uint8))
+    net = _build(NET_CASES[0], 'bf16')
+    a = [t.clone() for t in net(torch.from_numpy(want).cuda())]
+    b = [t.clone() for t in net(imgs.pin_memory())]
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
