@@ -360,7 +360,14 @@ class Engine(object):
         self.loc = self._alloc(B, P, 4, dtype=torch.float32)
         self.conf_raw = self._alloc(B, P, Csrc, dtype=torch.float32)
         self.obj_raw = self._alloc(B, P, 2, dtype=torch.float32)
+        # conf max-pool (RFB_Net_vgg.py:242-244): level i's pooled map only needs head i, so it follows it on the heads' lane
         pooled_shapes = []
+        if ours:
+            for f, a, k in zip(fmaps, anchors, CONF_POOL):
+                pooled_shapes.append((_pool_out(f, k, k, 0, True), _pool_out(f, k, k, 0, True), a))
+            Pk = sum(h * w * a for h, w, a in pooled_shapes)
+            self.num_pooled = Pk
+            self.pooled = self._alloc(B, Pk, Csrc, dtype=torch.float32)
 
         def add_source(s, lane=0):
             i = len(sources)
@@ -379,10 +386,14 @@ class Engine(object):
                     (self.obj_raw.view(-1)[poff * 2:], c2, c3, P * 2, a * 2, 0)]
             self._lane(5, wait=(lane,))
             self._emit_conv('head.%d' % i, s, w, b, 1, (1, 1), 1, False, segs=segs)
-            self._lane(0)
             if ours:
-                k = CONF_POOL[i]
-                pooled_shapes.append((_pool_out(s.H, k, k, 0, True), _pool_out(s.W, k, k, 0, True), a))
+                hp, wp, _ = pooled_shapes[i]
+                koff = sum(h * w * aa for h, w, aa in pooled_shapes[:i])
+                src = View(self.conf_raw.view(-1), B, s.H, s.W, a * Csrc, a * Csrc, poff * Csrc)
+                dst = View(self.pooled.view(-1), B, hp, wp, a * Csrc, a * Csrc, koff * Csrc)
+                self._emit_pool('conf_pool.%d' % i, src, CONF_POOL[i], CONF_POOL[i], 0, True, out=dst,
+                                in_img_stride=P * Csrc, out_img_stride=Pk * Csrc)
+            self._lane(0)
 
         x = run_base(0, SOURCE_SPLIT, x)
         # RFB-a on conv4_3 only feeds the first head: it runs on lane 4 beside the rest of the trunk
@@ -404,18 +415,6 @@ class Engine(object):
 
         # ---- Context-Transformer (phase 2, method 'ours') ----------------------------------------
         if ours:
-            Pk = sum(h * w * a for h, w, a in pooled_shapes)
-            self.num_pooled = Pk
-            self.pooled = self._alloc(B, Pk, Csrc, dtype=torch.float32)
-            poff, koff = 0, 0
-            for i, (s, a) in enumerate(zip(sources, anchors)):
-                hp, wp, _ = pooled_shapes[i]
-                src = View(self.conf_raw.view(-1), B, s.H, s.W, a * Csrc, a * Csrc, poff * Csrc)
-                dst = View(self.pooled.view(-1), B, hp, wp, a * Csrc, a * Csrc, koff * Csrc)
-                self._emit_pool('conf_pool.%d' % i, src, CONF_POOL[i], CONF_POOL[i], 0, True, out=dst,
-                                in_img_stride=P * Csrc, out_img_stride=Pk * Csrc)
-                poff += level_p[i]
-                koff += hp * wp * a
             incre = net.setting == 'incre'
             n_novel = net.OBJ_Target.out_features
             n_out = n_novel + (Csrc if incre else 0)
@@ -446,9 +445,11 @@ class Engine(object):
                        'ctx_prog_add_softmax')
             self.layers.append(('conf.softmax', 'softmax', 0.0, (B * P, Csrc)))
         self.obj = self._alloc(B, P, 2, dtype=torch.float32)
+        self._lane(5)                        # independent of the conf path: runs beside the Context-Transformer kernel
         _lib.check(self.L.ctx_prog_add_softmax(self.prog, self.obj_raw.data_ptr(), self.obj.data_ptr(), B * P, 2),
                    'ctx_prog_add_softmax')
         self.layers.append(('obj.softmax', 'softmax', 0.0, (B * P, 2)))
+        self._lane(0, wait=(5,))
         self.num_ops = self.L.ctx_prog_num_ops(self.prog)
         if self.autotune:
             # per-layer tiling picked by timing each candidate on this GPU (bit-identical outputs)
