@@ -64,6 +64,7 @@ struct TcParams {
   int a_mode, TW, TH, tiles_x, tiles_y;       // TMA mode: output patch TW x TH (<= 128 pixels), tiles per image
   int occ, acc_stride;                        // CTAs per SM the kernel is sized for (TMEM columns = 512 / occ), columns between the two accumulators
   int tps;                                    // HALO mode: filter taps per weight-ring slot (1 or 3)
+  int resident;                               // HALO mode: the layer's whole weight tensor stays in shared memory (loaded once per CTA)
   int PW, PH, a_slot, sa, sb;                 // HALO mode: staged patch (TW + 2 dil) x (TH + 2 dil) pixels, slot bytes, A / B ring depths
   int flat;                                   // TMA mode, 1x1 convs: the whole batch is one pixel row, tiles are 128-pixel runs
   int res_cstride, res_coffset, res_dtype;
@@ -771,6 +772,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ================= weight producer =================
+    if (p.resident) {
+      // small layers (conv1_2: 72 KB, conv2_1: 144 KB): all nine taps of every channel block are loaded ONCE per CTA and
+      // stay; the MMA thread then has a single barrier to wait for per channel block (the patch)
+      if (elect_one() && group0 < p.num_tiles) {
+        mbar_arrive_expect_tx(fullB0, 9u * (uint32_t)p.cin_blocks * B_TAP);
+        for (int cc = 0; cc < p.cin_blocks; ++cc)
+          for (int tap = 0; tap < 9; ++tap)
+            tma_load_2d(sB + (uint32_t)(cc * 9 + tap) * B_TAP, &tmap_w, (tap * p.cin_blocks + cc) * TC_BK, 0, fullB0);
+      }
+    } else
     if (elect_one()) {
       uint32_t s = 0, ph = 1, dst = sB;
       for (int tile = group0; tile < p.num_tiles; tile += ngroups) {
@@ -797,6 +808,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       const uint32_t row_step = (uint32_t)(p.dil * 128) >> 4, line_step = (uint32_t)((p.PW - 2) * p.dil * 128) >> 4;   // descriptor units (16 B)
       uint32_t slot = 0, pha = 0, s = 0, phb = 0, lt = 0, a_lo = (sA >> 4) & 0x3FFFu;
       uint64_t bd = bdesc0;
+      if (p.resident && group0 < p.num_tiles) mbar_wait(fullB0, 0);
       for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++lt) {
         const uint32_t buf = lt & 1;
         mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);
@@ -806,6 +818,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           mbar_wait(fullA0 + 8 * slot, pha);
           uint32_t a_tap = a_lo;                                // window of tap (0, 0); +dil rows per kx, +dil patch lines per ky
           int kx = 0;
+          if (p.resident) {
+            tc_fence_after();
+            uint64_t bt = bdesc0 + (uint64_t)(cc * 9) * b_tap;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap, bt += b_tap) {
+              const uint64_t ad = desc_hi | (uint64_t)a_tap;
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) umma_f16(tmem_d, ad + 2 * k, bt + 2 * k, idesc, (cc | tap | k) ? 1u : 0u);
+              a_tap += (tap % 3 == 2) ? line_step : row_step;
+            }
+          } else
           for (int tap0 = 0; tap0 < 9; tap0 += p.tps) {
             mbar_wait(fullB0 + 8 * s, phb);
             tc_fence_after();
@@ -1016,7 +1039,8 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
   const bool halo_ok = tma_eligible(p) && p->KH == 3 && p->KW == 3 && p->pad_h == p->pad_w && t.cluster_req != 2 &&
                        (!p->pool2 || (((p->Ho | p->Wo) & 1) == 0 && p->Cin % 64 == 0));
   t.occ = 1; t.acc_stride = 256;
-  if ((tune_amode == 2 || tune_amode == 3) && halo_ok) { t.a_mode = A_HALO; tw = 8; th = 16; }
+  t.resident = 0;
+  if ((tune_amode == 2 || tune_amode == 3 || tune_amode == 4) && halo_ok) { t.a_mode = A_HALO; tw = 8; th = 16; }
   else if (p->in_nchw) t.a_mode = A_STEM;
   else if (tune_amode == 0 && !p->pool2) t.a_mode = A_GATHER;
   else if (flat_eligible(p)) { t.a_mode = A_TMA; tw = 128; th = 1; }
@@ -1059,7 +1083,17 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
     // barrier wait instead of four (the MMA thread's issue loop is the pace there); an explicit commit group keeps 1 tap
     const int clog_rule = t.clog;
     t.sa = 0;
-    for (int occ = (tune_amode == 3 && t.bn <= 128) ? 2 : 1; occ >= 1 && !t.sa; --occ) {     // two CTAs per SM if they fit, else one
+    if (tune_amode == 4) {                  // weights resident: the whole layer is one N tile and fits beside >= 3 patches
+      const size_t wbytes = (size_t)9 * t.cin_blocks * t.bn * TC_BK * 2, budget = 232448 - 1024 - bias_bytes - 8 * (2 * 6 + 2 * 18 + 4) - 64;
+      if (t.n_tiles_n == 1 && t.cin_blocks <= 2 && wbytes + 3 * (size_t)t.a_slot <= budget) {
+        t.resident = 1; t.occ = 1; t.acc_stride = 256; t.tps = 1; t.clog = 0;
+        t.sb = 9 * t.cin_blocks;
+        t.sa = (int)std::min<size_t>(6, (budget - wbytes) / t.a_slot);
+      } else {
+        delete pl; set_error("conv_tc: HALO mode with resident weights does not apply (tile %d, %d channel blocks)", t.bn, t.cin_blocks); return CTX_ERR_UNSUPPORTED;
+      }
+    }
+    for (int occ = (tune_amode == 3 && t.bn <= 128) ? 2 : 1; occ >= 1 && !t.sa && !t.resident; --occ) {     // two CTAs per SM if they fit, else one
       t.occ = occ;
       t.acc_stride = 256 / occ;
       t.clog = clog_rule;
@@ -1119,7 +1153,7 @@ extern "C" int ctx_conv2d_tc_plan_info(void* plan, int* info8) {
   const TcPlan* pl = (const TcPlan*)plan;
   int* info6 = info8;
   info8[6] = pl->p.a_mode == A_HALO && pl->p.tps == 3 ? 3 : 1 << pl->p.clog; info8[7] = pl->p.TW * 1000 + pl->p.TH;
-  info6[0] = pl->p.bn; info6[1] = pl->p.n_tiles_n; info6[2] = pl->p.cluster; info6[3] = pl->p.a_mode == A_HALO && pl->p.occ == 2 ? 4 : pl->p.a_mode; info6[4] = pl->stages; info6[5] = pl->grid;
+  info6[0] = pl->p.bn; info6[1] = pl->p.n_tiles_n; info6[2] = pl->p.cluster; info6[3] = pl->p.a_mode == A_HALO && pl->p.resident ? 5 : (pl->p.a_mode == A_HALO && pl->p.occ == 2 ? 4 : pl->p.a_mode); info6[4] = pl->stages; info6[5] = pl->grid;
   return CTX_OK;
 }
 

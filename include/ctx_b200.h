@@ -124,9 +124,10 @@ int ctx_conv2d_tc_supported(const CtxConvParams* p);                /* 1 if the 
 int ctx_conv2d_tc_plan_create(const CtxConvParams* p, void** plan_out);
 /* Same, with the tiling chosen by the caller: n_tiles_n = number of output-channel tiles (0: ceil(Cout/256)), cluster = 1 | 2
  * CTAs per MMA (0: default), a_mode = -1 rule of thumb | 0 im2col gather | 1 TMA pixel patches | 2 halo patches (3x3: the 8x16
- * tile's neighbourhood staged once, nine shifted descriptors) | 3 halo patches with two CTAs per SM (tiles <= 128 wide), commit_group = K-steps per
+ * tile's neighbourhood staged once, nine shifted descriptors) | 3 halo patches with two CTAs per SM (tiles <= 128 wide) | 4 halo patches with the
+ * layer's whole weight tensor resident in shared memory (single N tile, <= 2 channel blocks), commit_group = K-steps per
  * tcgen05.commit (0: by tile width | 1 | 2 | 4).  Outputs are bit-identical for every setting; ctx_prog_autotune() picks per
- * layer by measurement.  info8 = {tile width, N tiles, cluster, A mode (0 gather, 1 TMA, 2 stem, 3 halo, 4 halo x 2 CTAs/SM), ring stages, grid,
+ * layer by measurement.  info8 = {tile width, N tiles, cluster, A mode (0 gather, 1 TMA, 2 stem, 3 halo, 4 halo x 2 CTAs/SM, 5 halo with resident weights), ring stages, grid,
  * commit group, TMA patch TW * 1000 + TH}. */
 int ctx_conv2d_tc_plan_create_tuned(const CtxConvParams* p, int n_tiles_n, int cluster, int a_mode, int commit_group, void** plan_out);
 int ctx_conv2d_tc_plan_info(void* plan, int* info8);

@@ -134,9 +134,11 @@ def test_conv_every_tiling_is_bit_identical(case):
     seen = set()
     for n, cg in ((0, 0), (2, 1), (3, 2), (5, 4), (0, 4), (0, 1)):
         for cl in (1, 2):
-            for amode in (-1, 0, 1, 2, 3):
+            for amode in (-1, 0, 1, 2, 3, 4):
                 plan = C.c_void_p()
-                _lib.check(L.ctx_conv2d_tc_plan_create_tuned(C.byref(p), n, cl, amode, cg, C.byref(plan)), 'plan_create_tuned')
+                if L.ctx_conv2d_tc_plan_create_tuned(C.byref(p), n, cl, amode, cg, C.byref(plan)) != 0:
+                    assert amode == 4                                  # resident weights apply to small single-tile layers only
+                    continue
                 info = (C.c_int * 8)()
                 _lib.check(L.ctx_conv2d_tc_plan_info(plan, info))
                 key = (info[0], info[1], info[2], info[3], info[6])
@@ -152,6 +154,8 @@ def test_conv_every_tiling_is_bit_identical(case):
     assert (3 in {k[3] for k in seen}) == (kh == 3 and kw == 3)   # ... and the halo mode for every 3x3 case
     assert (4 in {k[3] for k in seen}) == (kh == 3 and kw == 3)   # ... also with two CTAs per SM (tiles <= 128 wide: n >= 2 splits any Cout here)
     assert len({k[4] for k in seen}) >= 2                         # ... and more than one commit-group size
+    if kh == 3 and kw == 3 and cin == 64 and cout <= 128 and dil == 1:
+        assert 5 in {k[3] for k in seen}                           # resident weights (they fit: 9 x Cout x 128 B beside three patches)
 
 
 @pytest.mark.parametrize('case', [(64, 64, 32, 48), (128, 128, 30, 64), (64, 96, 24, 32)], ids=str)
