@@ -33,7 +33,6 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 SIZE, NUM_SRC_CLASSES, BATCH_PER_GPU = 300, 60, 32
-CONV_GFLOP_PER_IMG = 77.29 - 7.57      # SURVEY §8d (each conv once; the reference runs the conf heads twice)
 SCALE = [500.0, 375.0, 500.0, 375.0]
 
 
@@ -186,7 +185,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp16', 'fp32'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp16', 'fp32', 'fp32x3'])
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--size', type=int, default=SIZE, choices=[300, 512], help='extra (non-contract) workload: 512 uses the ft head (BASELINE config 3)')
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='images per GPU (contract default 32)')
@@ -453,7 +452,7 @@ def main():
 
     line = {'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': n_gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'fp16': 'f16', 'fp32': 'f32'}[args.precision], 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': {'bf16': 'bf16', 'fp16': 'f16', 'fp32': 'f32', 'fp32x3': 'f32 (3 x f16 tcgen05)'}[args.precision], 'data': 'synthetic',
             'config': workload_config(args.precision, n_gpus, {'detections_per_batch_e2e': n_det[0], 'batch_per_gpu': B,
                                                                 'cuda_graph': bool(eng.graph_ready),
                                                                 'graph_lanes': bool(eng.use_lanes), 'tile_autotune': bool(eng.autotune), 'nms': nms_kind,

@@ -40,14 +40,17 @@ class CtxConvParams(C.Structure):
                 ('Ho', C.c_int), ('Wo', C.c_int), ('relu', C.c_int), ('pool2', C.c_int), ('relu_channels', C.c_int), ('in_dtype', C.c_int), ('in_nchw', C.c_int),
                 ('in', C.c_void_p), ('weight', C.c_void_p), ('bias', C.c_void_p), ('residual', C.c_void_p),
                 ('res_dtype', C.c_int), ('res_cstride', C.c_int), ('res_coffset', C.c_int),
-                ('nseg', C.c_int), ('seg', CtxOutSeg * 3)]
+                ('nseg', C.c_int), ('seg', CtxOutSeg * 3),
+                ('split', C.c_int), ('in_lo', C.c_void_p), ('residual_lo', C.c_void_p), ('out_lo', C.c_void_p),
+                ('out_scale', C.c_void_p)]
 
 
 class CtxPoolParams(C.Structure):
     _fields_ = [('N', C.c_int), ('H', C.c_int), ('W', C.c_int), ('C', C.c_int), ('Ho', C.c_int), ('Wo', C.c_int),
                 ('k', C.c_int), ('stride', C.c_int), ('pad', C.c_int), ('dtype', C.c_int),
                 ('in', C.c_void_p), ('in_img_stride', C.c_longlong), ('in_pix_stride', C.c_int),
-                ('out', C.c_void_p), ('out_img_stride', C.c_longlong), ('out_pix_stride', C.c_int)]
+                ('out', C.c_void_p), ('out_img_stride', C.c_longlong), ('out_pix_stride', C.c_int),
+                ('in_lo', C.c_void_p), ('out_lo', C.c_void_p)]
 
 
 class CtxAttnParams(C.Structure):
@@ -82,6 +85,12 @@ SIGNATURES = {
     'ctx_conv2d_tc_plan_info': (_I, [_P, C.POINTER(_I)]),
     'ctx_conv2d_tc_plan_run': (_I, [_P, _P]),
     'ctx_conv2d_tc_plan_destroy': (None, [_P]),
+    'ctx_conv2d_x3_supported': (_I, [C.POINTER(CtxConvParams)]),
+    'ctx_conv2d_x3_plan_create': (_I, [C.POINTER(CtxConvParams), _I, C.POINTER(_P)]),
+    'ctx_conv2d_x3_plan_run': (_I, [_P, _P]),
+    'ctx_conv2d_x3_plan_info': (_I, [_P, C.POINTER(_I)]),
+    'ctx_conv2d_x3_plan_destroy': (None, [_P]),
+    'ctx_prog_add_conv_x3': (_I, [_P, C.POINTER(CtxConvParams)]),
     'ctx_maxpool2d_nhwc': (_I, [C.POINTER(CtxPoolParams), _P]),
     'ctx_nchw_to_nhwc': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'ctx_base_transform': (_I, [_P, _P, _I, _I, _I, C.POINTER(C.c_float), _P]),

@@ -326,8 +326,61 @@ int conv_simt_launch(const CtxConvParams* p, cudaStream_t st) {
   return CTX_OK;
 }
 
+// Split mode (fp16 hi / lo planes, value = hi + lo): the maximum is taken on the fp32 sums and the winner's two halves are
+// copied (re-splitting the fp32 sum would give the same pair: hi = fp16(hi + lo) by construction).  8 channels per thread.
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_split_kernel(CtxPoolParams p) {
+  const int C8 = p.C >> 3;
+  const long long total = (long long)p.N * p.Ho * p.Wo * C8;
+  const uint16_t* in_hi = reinterpret_cast<const uint16_t*>(p.in);
+  const uint16_t* in_lo = reinterpret_cast<const uint16_t*>(p.in_lo);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    long long r = i / C8;
+    const int ox = (int)(r % p.Wo); r /= p.Wo;
+    const int oy = (int)(r % p.Ho);
+    const int n = (int)(r / p.Ho);
+    const int y0 = max(oy * p.stride - p.pad, 0), y1 = min(oy * p.stride - p.pad + p.k, p.H);
+    const int x0 = max(ox * p.stride - p.pad, 0), x1 = min(ox * p.stride - p.pad + p.k, p.W);
+    float m[8];
+    uint16_t bh[8], bl[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { m[e] = -INFINITY; bh[e] = 0xFC00u; bl[e] = 0u; }
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        const long long off = (long long)n * p.in_img_stride + (long long)(y * p.W + x) * p.in_pix_stride + c;
+        const uint4 vh = *reinterpret_cast<const uint4*>(in_hi + off), vl = *reinterpret_cast<const uint4*>(in_lo + off);
+        const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint16_t hh = (uint16_t)(wh[e >> 1] >> ((e & 1) * 16)), ll = (uint16_t)(wl[e >> 1] >> ((e & 1) * 16));
+          const float f = __half2float(__ushort_as_half(hh)) + __half2float(__ushort_as_half(ll));
+          if (f > m[e]) { m[e] = f; bh[e] = hh; bl[e] = ll; }
+        }
+      }
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { oh[e] = (uint32_t)bh[2 * e] | ((uint32_t)bh[2 * e + 1] << 16); ol[e] = (uint32_t)bl[2 * e] | ((uint32_t)bl[2 * e + 1] << 16); }
+    const long long o = (long long)n * p.out_img_stride + (long long)(oy * p.Wo + ox) * p.out_pix_stride + c;
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + o) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_lo) + o) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+  }
+}
+
 int maxpool_launch(const CtxPoolParams* p, cudaStream_t st) {
   CTX_REQUIRE(p && p->in && p->out, "maxpool: null pointer");
+  if (p->in_lo || p->out_lo) {
+    CTX_REQUIRE(p->in_lo && p->out_lo && p->dtype == CTX_F16 && p->C % 8 == 0 && p->in_pix_stride % 8 == 0 && p->out_pix_stride % 8 == 0 &&
+                p->in_img_stride % 8 == 0 && p->out_img_stride % 8 == 0 && ((uintptr_t)p->in) % 16 == 0 && ((uintptr_t)p->out) % 16 == 0 &&
+                ((uintptr_t)p->in_lo) % 16 == 0 && ((uintptr_t)p->out_lo) % 16 == 0,
+                "maxpool (split mode): needs both fp16 planes, 8-channel aligned");
+    CTX_REQUIRE(p->N > 0 && p->k > 0 && p->stride > 0 && p->Ho > 0 && p->Wo > 0 && (p->Ho - 1) * p->stride - p->pad < p->H && (p->Wo - 1) * p->stride - p->pad < p->W,
+                "maxpool (split mode): bad dims");
+    const long long total8 = (long long)p->N * p->Ho * p->Wo * (p->C / 8);
+    maxpool_nhwc_split_kernel<<<(int)std::min<long long>((total8 + 255) / 256, 148LL * 32), 256, 0, st>>>(*p);
+    CTX_LAUNCH_CHECK();
+    return CTX_OK;
+  }
   CTX_REQUIRE(p->N > 0 && p->C > 0 && p->k > 0 && p->stride > 0 && p->Ho > 0 && p->Wo > 0, "maxpool: bad dims");
   CTX_REQUIRE((p->Ho - 1) * p->stride - p->pad < p->H && (p->Wo - 1) * p->stride - p->pad < p->W,
               "maxpool: last window starts outside the input");

@@ -18,7 +18,7 @@ int softmax_launch(const float* in, float* out, long long rows, int cols, cudaSt
 int patch27_launch(const float* in, void* out, int N, int H, int W, int dtype, cudaStream_t st);
 int attention_simt_launch(const CtxAttnParams* p, cudaStream_t st);
 
-enum OpKind { OP_CONV_SIMT, OP_CONV_TC, OP_POOL, OP_NCHW2NHWC, OP_PATCH27, OP_ATTN, OP_SOFTMAX };
+enum OpKind { OP_CONV_SIMT, OP_CONV_TC, OP_CONV_X3, OP_POOL, OP_NCHW2NHWC, OP_PATCH27, OP_ATTN, OP_SOFTMAX };
 
 constexpr int MAX_LANES = 8;
 
@@ -30,6 +30,7 @@ struct Op {
   CtxPoolParams pool;
   CtxAttnParams attn;
   void* tc_plan = nullptr;
+  void* x3_plan = nullptr;
   struct { const float* in; void* out; int N, C, H, W, dtype; } cvt;
   struct { const float* in; float* out; long long rows; int cols; } sm;
 };
@@ -56,6 +57,7 @@ static int run_op(Op& op, cudaStream_t st) {
   switch (op.kind) {
     case OP_CONV_SIMT: return conv_simt_launch(&op.conv, st);
     case OP_CONV_TC: return ctx_conv2d_tc_plan_run(op.tc_plan, st);
+    case OP_CONV_X3: return ctx_conv2d_x3_plan_run(op.x3_plan, st);
     case OP_POOL: return maxpool_launch(&op.pool, st);
     case OP_NCHW2NHWC: return nchw_to_nhwc_launch(op.cvt.in, op.cvt.out, op.cvt.N, op.cvt.C, op.cvt.H, op.cvt.W, op.cvt.dtype, st);
     case OP_PATCH27: return patch27_launch(op.cvt.in, op.cvt.out, op.cvt.N, op.cvt.H, op.cvt.W, op.cvt.dtype, st);
@@ -86,6 +88,8 @@ extern "C" void ctx_prog_destroy(void* prog) {
   drop_graph(pr);
   for (Op& op : pr->ops)
     if (op.tc_plan) ctx_conv2d_tc_plan_destroy(op.tc_plan);
+  for (Op& op : pr->ops)
+    if (op.x3_plan) ctx_conv2d_x3_plan_destroy(op.x3_plan);
   for (cudaEvent_t e : pr->events) cudaEventDestroy(e);
   for (cudaStream_t s : pr->lane_stream) if (s) cudaStreamDestroy(s);
   delete pr;
@@ -109,6 +113,16 @@ extern "C" int ctx_prog_add_conv_tc(void* prog, const CtxConvParams* p) {
   CTX_REQUIRE(p, "ctx_prog_add_conv_tc: null params");
   Op op{}; op.kind = OP_CONV_TC; op.conv = *p;
   int rc = ctx_conv2d_tc_plan_create(p, &op.tc_plan);
+  if (rc) return rc;
+  push_op(pr, op);
+  return CTX_OK;
+}
+
+extern "C" int ctx_prog_add_conv_x3(void* prog, const CtxConvParams* p) {
+  PROG_OR_FAIL(prog);
+  CTX_REQUIRE(p, "ctx_prog_add_conv_x3: null params");
+  Op op{}; op.kind = OP_CONV_X3; op.conv = *p;
+  int rc = ctx_conv2d_x3_plan_create(p, 0, &op.x3_plan);
   if (rc) return rc;
   push_op(pr, op);
   return CTX_OK;
@@ -167,6 +181,7 @@ extern "C" int ctx_prog_conv_config(void* prog, int op_index, int* info6) {     
   Prog* pr = (Prog*)prog;
   CTX_REQUIRE(op_index >= 0 && op_index < (int)pr->ops.size(), "ctx_prog_conv_config: bad op index %d", op_index);
   for (int i = 0; i < 8; ++i) info6[i] = 0;
+  if (pr->ops[op_index].kind == OP_CONV_X3) return ctx_conv2d_x3_plan_info(pr->ops[op_index].x3_plan, info6);
   if (pr->ops[op_index].kind != OP_CONV_TC) return CTX_OK;
   return ctx_conv2d_tc_plan_info(pr->ops[op_index].tc_plan, info6);
 }

@@ -26,24 +26,29 @@ import torch.nn as nn
 from . import _lib
 from .rfb_net import CONF_POOL, SOURCE_SPLIT, BasicConv, _RFBBlock
 
-_DT = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'fp16': torch.float16}
+_DT = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'fp16': torch.float16, 'fp32x3': torch.float16}
+_TC16 = ('bf16', 'fp16')             # plain 16-bit tensor-core modes ('fp32x3' keeps fp16 hi / lo plane PAIRS: fp32 emulated, csrc/conv_x3.cu)
 
 
 class View(object):
     """A [N,H,W,C] channels-last activation living at channel offset ``coff`` of a buffer whose
     pixels are ``cstride`` channels wide."""
-    __slots__ = ('buf', 'N', 'H', 'W', 'C', 'cstride', 'coff')
+    __slots__ = ('buf', 'N', 'H', 'W', 'C', 'cstride', 'coff', 'lo')
 
-    def __init__(self, buf, N, H, W, C, cstride=None, coff=0):
+    def __init__(self, buf, N, H, W, C, cstride=None, coff=0, lo=None):
         self.buf, self.N, self.H, self.W, self.C = buf, N, H, W, C
         self.cstride = C if cstride is None else cstride
         self.coff = coff
+        self.lo = lo                         # 'fp32x3': buffer of the lo plane (same geometry), value = buf + lo
 
     def slice(self, off, c):
-        return View(self.buf, self.N, self.H, self.W, c, self.cstride, self.coff + off)
+        return View(self.buf, self.N, self.H, self.W, c, self.cstride, self.coff + off, self.lo)
 
     def tensor(self):
-        return self.buf.view(self.N, self.H, self.W, self.cstride)[..., self.coff:self.coff + self.C]
+        t = self.buf.view(self.N, self.H, self.W, self.cstride)[..., self.coff:self.coff + self.C]
+        if self.lo is not None:
+            t = t.float() + self.lo.view(self.N, self.H, self.W, self.cstride)[..., self.coff:self.coff + self.C].float()
+        return t
 
 
 def _pair(v):
@@ -63,7 +68,7 @@ def _pool_out(h, k, s, pad, ceil_mode):
 class Engine(object):
     def __init__(self, net, batch, precision, device, use_graph=True):
         if precision not in _DT:
-            raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
+            raise ValueError("precision must be 'fp32', 'fp32x3', 'bf16' or 'fp16'")
         if not torch.cuda.is_available():
             raise _lib.CtxError('no CUDA device: the detection hot path has no CPU fallback')
         self.L = _lib.lib()
@@ -87,7 +92,8 @@ class Engine(object):
         self.use_graph = use_graph
         # independent chains (RFB branches, per-level heads) on their own graph lanes; CTX_LANES=0 keeps one chain
         self.use_lanes = os.environ.get('CTX_LANES', '1') != '0'
-        self.autotune = os.environ.get('CTX_AUTOTUNE', '1') != '0' and precision != 'fp32'
+        self.autotune = os.environ.get('CTX_AUTOTUNE', '1') != '0' and precision in _TC16
+        self.split = precision == 'fp32x3'
         self.stream = torch.cuda.Stream(device=self.dev)
         with torch.cuda.device(self.dev), torch.no_grad():
             self._compile(net)
@@ -123,7 +129,7 @@ class Engine(object):
         _lib.check(self.L.ctx_prog_set_lane(self.prog, lane, mask), 'ctx_prog_set_lane')
 
     def _new_view(self, N, H, W, C):
-        return View(self._alloc(N * H * W * C), N, H, W, C)
+        return View(self._alloc(N * H * W * C), N, H, W, C, lo=self._alloc(N * H * W * C) if self.split else None)
 
     # ------------------------------------------------------------------------------------------
     def _fold(self, conv, bn, scale=1.0):
@@ -184,6 +190,8 @@ class Engine(object):
             p.seg[i].dtype = _lib.dtype_code(t.dtype)
         self.last_conv_params = p            # (tests re-plan the same conv under other tilings)
         flops = algo_flops if algo_flops is not None else 2.0 * src.N * Ho * Wo * Cout * Cin * KH * KW
+        if self.split:
+            return self._emit_conv_x3(name, p, src, w, residual, segs, result, flops, in_nchw, pool2)
         use_tc = self.precision != 'fp32' and self.L.ctx_conv2d_tc_supported(C.byref(p)) == 1
         if pool2 and not use_tc:
             return None                     # caller falls back to conv + separate pool
@@ -213,6 +221,40 @@ class Engine(object):
         self.layers.append((name, kind, flops, (src.N, src.H, src.W, Cin, Cout, KH, KW, stride, dil)))
         return result
 
+    def _emit_conv_x3(self, name, p, src, w, residual, segs, result, flops, in_nchw, pool2):
+        """'fp32x3' (csrc/conv_x3.cu): fp16 hi / lo planes of the activations and of the weights, the latter scaled per
+        output channel by a power of two so that their lo plane stays in fp16's normal range (undone by ``out_scale``)."""
+        if pool2:
+            return None                     # the split-aware pool kernel follows as its own op
+        Cout, Cin, KH, KW = w.shape
+        amax = w.abs().amax(dim=(1, 2, 3)).clamp_min(1e-30)
+        sc = torch.exp2(torch.floor(torch.log2(4096.0 / amax)))
+        ws = w * sc.view(-1, 1, 1, 1)
+        hi = ws.to(torch.float16)
+        lo = (ws - hi.float()).to(torch.float16)
+        cout_p = (Cout + 15) // 16 * 16
+        if in_nchw:                         # stem: one 64-wide K-step per plane, k = (ky*3 + kx)*3 + ci
+            wt = torch.zeros(cout_p, 2, 64, dtype=torch.float16, device=self.dev)
+            wt[:Cout, 0, :27] = hi.permute(0, 2, 3, 1).reshape(Cout, 27)
+            wt[:Cout, 1, :27] = lo.permute(0, 2, 3, 1).reshape(Cout, 27)
+        else:
+            cin_p = (Cin + 63) // 64 * 64
+            wt = torch.zeros(cout_p, 2, KH * KW, cin_p, dtype=torch.float16, device=self.dev)
+            wt[:Cout, 0, :, :Cin] = hi.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin)
+            wt[:Cout, 1, :, :Cin] = lo.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin)
+        inv = (1.0 / sc).contiguous()
+        self.keep += [wt, inv]
+        p.weight, p.out_scale, p.split = wt.data_ptr(), inv.data_ptr(), 1
+        if not in_nchw:
+            p.in_lo = src.lo.data_ptr()
+        if residual is not None:
+            p.residual_lo = residual.lo.data_ptr()
+        if result is not None:
+            p.out_lo = result.lo.data_ptr()
+        _lib.check(self.L.ctx_prog_add_conv_x3(self.prog, C.byref(p)), 'ctx_prog_add_conv_x3(%s)' % name)
+        self.layers.append((name, 'conv_x3', flops, (src.N, src.H, src.W, Cin, Cout, KH, KW, p.stride, p.dil)))
+        return result
+
     def _emit_pool(self, name, src, k, s, pad, ceil_mode, out=None, in_img_stride=None, out_img_stride=None):
         Ho, Wo = _pool_out(src.H, k, s, pad, ceil_mode), _pool_out(src.W, k, s, pad, ceil_mode)
         if out is None:
@@ -227,6 +269,9 @@ class Engine(object):
         p.out = out.buf.data_ptr() + out.coff * out.buf.element_size()
         p.out_img_stride = out_img_stride if out_img_stride is not None else Ho * Wo * out.cstride
         p.out_pix_stride = out.cstride
+        if src.lo is not None:
+            p.in_lo = src.lo.data_ptr() + src.coff * esz
+            p.out_lo = out.lo.data_ptr() + out.coff * esz
         _lib.check(self.L.ctx_prog_add_pool(self.prog, C.byref(p)), 'ctx_prog_add_pool(%s)' % name)
         self.layers.append((name, 'pool', 0.0, (src.N, src.H, src.W, src.C, k, s)))
         return out
@@ -324,7 +369,7 @@ class Engine(object):
                     nxt = k + (2 if relu else 1)
                     pool = net.base[nxt] if nxt < hi else None
                     fused = None
-                    if (self.precision != 'fp32' and isinstance(pool, nn.MaxPool2d) and pool.kernel_size == 2 and pool.stride == 2
+                    if (self.precision in _TC16 and isinstance(pool, nn.MaxPool2d) and pool.kernel_size == 2 and pool.stride == 2
                             and pool.padding == 0 and x.H % 2 == 0 and x.W % 2 == 0 and m.stride[0] == 1):
                         # conv -> ReLU -> MaxPool2d(2,2): the pooled map is all that leaves the conv's epilogue
                         fused = self._emit_conv('base.%d+pool%d' % (k, nxt), x, w, b, 1, _pair(m.padding), m.dilation[0], relu, pool2=True)
@@ -432,7 +477,10 @@ class Engine(object):
             ap.Wz = f32(net.Wz)
             ap.obj_target_w = f32(net.OBJ_Target.weight)
             ap.scale = float(net.scale.detach().float().cpu().item())
-            ap.use_tensor_cores = int(self.precision != 'fp32')
+            # 0: fp32 CUDA cores; 1: tcgen05, fp16 logits; 2: tcgen05, fp16 hi/lo split logits
+            ap.use_tensor_cores = {'fp32': 0, 'fp32x3': 0}.get(self.precision, 1)
+            if os.environ.get('CTX_ATTN_MODE'):                  # development aid: force a Context-Transformer kernel variant
+                ap.use_tensor_cores = int(os.environ['CTX_ATTN_MODE'])
             ws_bytes = self.L.ctx_attention_workspace_bytes(C.byref(ap))
             self.attn_ws = self._alloc(ws_bytes + 1024, dtype=torch.uint8)
             ws_ptr = (self.attn_ws.data_ptr() + 1023) // 1024 * 1024

@@ -109,6 +109,14 @@ typedef struct CtxConvParams {
   int res_dtype, res_cstride, res_coffset;
   int nseg;
   CtxOutSeg seg[3];
+  /* split mode ("fp32x3": fp32 arithmetic emulated on the tensor cores; ctx_conv2d_x3_* only, 0 / NULL elsewhere).  Every 16-bit
+   * tensor is a PAIR of fp16 planes of identical geometry, value = hi + lo (hi = fp16(v), lo = fp16(v - hi)): */
+  int split;
+  const void* in_lo;         /* lo plane of `in` (not used by the fp32 NCHW stem input) */
+  const void* residual_lo;   /* lo plane of `residual` */
+  void* out_lo;              /* lo plane of seg[0] when seg[0] is 16-bit */
+  const float* out_scale;    /* [Cout]: the accumulator is multiplied by out_scale[c] before the bias — undoes the per-channel
+                              * power-of-two scaling that keeps the fp16 weight planes in the normal range */
 } CtxConvParams;
 
 typedef struct CtxPoolParams { /* nn.MaxPool2d on NHWC views (vgg 'M'/'C'/pool5, conf pool :242-244) */
@@ -116,6 +124,7 @@ typedef struct CtxPoolParams { /* nn.MaxPool2d on NHWC views (vgg 'M'/'C'/pool5,
   int dtype;
   const void* in; long long in_img_stride; int in_pix_stride;
   void* out; long long out_img_stride; int out_pix_stride;
+  const void* in_lo; void* out_lo;   /* split mode (fp16 hi/lo planes, see CtxConvParams::split): the window maximum is taken on hi + lo */
 } CtxPoolParams;
 
 int ctx_conv2d_simt(const CtxConvParams* p, void* stream);          /* fp32-accumulate CUDA-core path */
@@ -133,6 +142,17 @@ int ctx_conv2d_tc_plan_create_tuned(const CtxConvParams* p, int n_tiles_n, int c
 int ctx_conv2d_tc_plan_info(void* plan, int* info8);
 int ctx_conv2d_tc_plan_run(void* plan, void* stream);
 void ctx_conv2d_tc_plan_destroy(void* plan);
+/* fp32 emulated on the tensor cores (precision 'fp32x3'): activations and weights are fp16 hi/lo plane pairs (p->split = 1),
+ * weights [Cout_pad16][2 planes: hi, lo][KH*KW][Cin_pad64] scaled per output channel by a power of two (p->out_scale undoes it).
+ * Per 64-channel K-step of one filter tap the kernel chains lo*Whi + hi*Wlo + hi*Whi (12 tcgen05.mma) into a fresh TMEM
+ * accumulator and adds the result to an fp32 running sum in registers: the tensor core's fp32 adder truncates
+ * (profiles/r2_acc_probe.txt), short chains + round-to-nearest adds keep the result within fp32 accuracy of the exact conv.
+ * n_tiles_n = number of output-channel tiles (0: ceil(Cout/128)). */
+int ctx_conv2d_x3_supported(const CtxConvParams* p);
+int ctx_conv2d_x3_plan_create(const CtxConvParams* p, int n_tiles_n, void** plan_out);
+int ctx_conv2d_x3_plan_run(void* plan, void* stream);
+int ctx_conv2d_x3_plan_info(void* plan, int* info8);
+void ctx_conv2d_x3_plan_destroy(void* plan);
 int ctx_maxpool2d_nhwc(const CtxPoolParams* p, void* stream);
 /* x[N,3,H,W] fp32 NCHW (RFBNet.forward input, :210) -> NHWC of dtype */
 int ctx_nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, int out_dtype, void* stream);
@@ -175,6 +195,7 @@ int ctx_softmax_lastdim(const float* in, float* out, long long rows, int cols, v
 int ctx_prog_create(void** prog_out);
 int ctx_prog_add_conv_simt(void* prog, const CtxConvParams* p);
 int ctx_prog_add_conv_tc(void* prog, const CtxConvParams* p);
+int ctx_prog_add_conv_x3(void* prog, const CtxConvParams* p);
 int ctx_prog_add_pool(void* prog, const CtxPoolParams* p);
 int ctx_prog_add_nchw_to_nhwc(void* prog, const float* in, void* out, int N, int C, int H, int W, int out_dtype);
 int ctx_prog_add_nchw_to_patch27(void* prog, const float* in, void* out, int N, int H, int W, int out_dtype);

@@ -28,7 +28,8 @@ class _Scratch(Engine):
         self.L = _lib.lib()
         self.dev = DEV
         self.precision = precision
-        self.act_dtype = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'fp16': torch.float16}[precision]
+        self.act_dtype = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'fp16': torch.float16, 'fp32x3': torch.float16}[precision]
+        self.split = precision == 'fp32x3'
         self.act_code = _lib.dtype_code(self.act_dtype)
         self.keep, self.layers = [], []
         self.prog = C.c_void_p()
@@ -45,6 +46,17 @@ def _nhwc_view(x_nchw, dtype=torch.float32, pad_c=0, coff=0):
     buf = torch.zeros(N, H, W, Cc + pad_c, dtype=dtype, device=DEV)
     buf[..., coff:coff + Cc] = x_nchw.permute(0, 2, 3, 1).to(DEV, dtype)
     return View(buf.view(-1), N, H, W, Cc, Cc + pad_c, coff), buf
+
+
+def _split_view(x_nchw, pad_c=0, coff=0):
+    """'fp32x3' layout: fp16 hi / lo planes of an NHWC tensor (value = hi + lo)."""
+    N, Cc, H, W = x_nchw.shape
+    v = x_nchw.permute(0, 2, 3, 1).to(DEV, torch.float32)
+    hi = torch.zeros(N, H, W, Cc + pad_c, dtype=torch.float16, device=DEV)
+    lo = torch.zeros_like(hi)
+    hi[..., coff:coff + Cc] = v.half()
+    lo[..., coff:coff + Cc] = (v - v.half().float()).half()
+    return View(hi.view(-1), N, H, W, Cc, Cc + pad_c, coff, lo=lo.view(-1))
 
 
 CONV_CASES = [  # cin, cout, k, stride, pad, dil, H
@@ -84,6 +96,88 @@ def test_conv_kernel_vs_torch(case, precision):
         xq, wq = x.bfloat16().float(), (w.bfloat16().float() if e.layers[-1][1] == 'conv_tc' else w)
         want = F.relu(F.conv2d(xq, wq, b, stride, (ph, pw), dil))
         assert torch.allclose(got, want, rtol=1e-2, atol=1e-2)            # bf16 output rounding (8 bits)
+
+
+X3_CASES = CONV_CASES + [(512, 512, 3, 1, 1, 1, 19), (1024, 264, 1, 1, 0, 1, 9), (48, 64, 3, 2, 1, 1, 9), (32, 48, 3, 1, 1, 1, 8)]
+
+
+@pytest.mark.parametrize('case', X3_CASES, ids=[str(c) for c in X3_CASES])
+def test_conv_x3_kernel_vs_fp64(case):
+    """precision 'fp32x3' (csrc/conv_x3.cu): fp16 hi/lo operand planes, 12-instruction tcgen05 chains flushed into fp32
+    registers.  Held to the accuracy of an fp32 conv: the error against the exact (fp64) result must not exceed twice
+    torch's own fp32 conv error + 2e-6 of the output scale, and must show no systematic shrink (the signature of the
+    tensor core's truncating accumulator, profiles/r2_acc_probe.txt)."""
+    cin, cout, k, stride, pad, dil, H = case
+    g = synth._gen(21, 'x3conv%s' % (case,))
+    kh, kw = (k, k) if isinstance(k, int) else k
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    N = 3
+    x = torch.randn(N, cin, H, H + 1, generator=g).abs() * 3.0          # post-ReLU-like: all-positive partial sums are the worst case
+    w = torch.randn(cout, cin, kh, kw, generator=g) * (2.0 / (cin * kh * kw)) ** 0.5
+    w = w * torch.exp2(torch.randint(-6, 3, (cout, 1, 1, 1), generator=g).float())     # channels of very different magnitude
+    b = torch.randn(cout, generator=g) * 0.1
+    e = _Scratch('fp32x3')
+    if cin == 3:
+        src = View(x.to(DEV).contiguous().view(-1), N, H, H + 1, 3)
+        out = e._emit_conv('t', src, w.to(DEV), b.to(DEV), stride, (ph, pw), dil, True, in_nchw=True)
+    else:
+        src = _split_view(x, pad_c=72, coff=8)
+        x = src.tensor().cpu().permute(0, 3, 1, 2)                      # the 22-bit values the kernel actually sees
+        out = e._emit_conv('t', src, w.to(DEV), b.to(DEV), stride, (ph, pw), dil, True)
+    assert e.layers[-1][1] == 'conv_x3'
+    e.go()
+    got = out.tensor().cpu().permute(0, 3, 1, 2).double()
+    want = F.relu(F.conv2d(x.double(), w.double(), b.double(), stride, (ph, pw), dil))
+    ref32 = F.relu(F.conv2d(x, w, b, stride, (ph, pw), dil)).double()
+    scale = want.abs().amax(dim=(0, 2, 3), keepdim=True).clamp_min(1e-6)     # per output channel
+    err = ((got - want).abs() / scale).max().item()
+    err32 = ((ref32 - want).abs() / scale).max().item()
+    pos = want > 0.1 * scale
+    shrink = ((got - want) / want)[pos].mean().item()
+    print('x3 %s: max err / channel scale %.2e (torch fp32 %.2e), mean signed rel err %.2e' % (case, err, err32, shrink))
+    assert err < 2 * err32 + 2e-6
+    # 7e-8 .. 1e-7 without the epilogue's truncation compensation (CTX_X3_COMP=0); small samples only bound the noise
+    assert abs(shrink) < (3e-8 if int(pos.sum()) >= 20000 else 3e-7)
+
+
+def test_x3_residual_heads_and_pool():
+    """'fp32x3': ConvLinear epilogue (+ split residual, ReLU), a three-segment fp32 head conv, the split-aware max-pool."""
+    g = synth._gen(22, 'x3segs')
+    N, H, A, Cs = 2, 5, 6, 20
+    x = torch.randn(N, 256, H, H, generator=g)
+    w = torch.randn(512, 256, 1, 1, generator=g) * 0.06
+    b = torch.randn(512, generator=g) * 0.1
+    short = torch.randn(N, 512, H, H, generator=g)
+    e = _Scratch('fp32x3')
+    src, res = _split_view(x), _split_view(short)
+    x, short = src.tensor().cpu().permute(0, 3, 1, 2), res.tensor().cpu().permute(0, 3, 1, 2)
+    out = e._emit_conv('cl', src, w.to(DEV), b.to(DEV), 1, (0, 0), 1, True, residual=res)
+    P = H * H * A + 7
+    loc = torch.zeros(N, P, 4, device=DEV)
+    conf = torch.zeros(N, P, Cs, device=DEV)
+    obj = torch.zeros(N, P, 2, device=DEV)
+    wh = torch.randn(A * (4 + Cs + 2), 256, 3, 3, generator=g) * 0.02
+    bh = torch.randn(A * (4 + Cs + 2), generator=g) * 0.1
+    c1, c2, c3 = A * 4, A * 4 + A * Cs, A * (4 + Cs + 2)
+    off = 7
+    segs = [(loc.view(-1)[off * 4:], 0, c1, P * 4, A * 4, 0), (conf.view(-1)[off * Cs:], c1, c2, P * Cs, A * Cs, 0),
+            (obj.view(-1)[off * 2:], c2, c3, P * 2, A * 2, 0)]
+    e._emit_conv('head', src, wh.to(DEV), bh.to(DEV), 1, (1, 1), 1, False, segs=segs)
+    xp = torch.randn(2, 24, 75, 75, generator=g) * 5
+    psrc = _split_view(xp)
+    pooled = e._emit_pool('p', psrc, 2, 2, 0, True)
+    pooled3 = e._emit_pool('p3', psrc, 3, 1, 1, False)
+    e.go()
+    want = F.relu(F.conv2d(x.double(), w.double(), b.double()) + short.double())
+    assert torch.allclose(out.tensor().cpu().permute(0, 3, 1, 2).double(), want, rtol=2e-6, atol=2e-6)
+    y = F.conv2d(x.double(), wh.double(), bh.double(), 1, 1).permute(0, 2, 3, 1)
+    assert torch.allclose(loc[:, off:].cpu().reshape(N, H, H, -1).double(), y[..., :c1], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(conf[:, off:].cpu().reshape(N, H, H, -1).double(), y[..., c1:c2], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(obj[:, off:].cpu().reshape(N, H, H, -1).double(), y[..., c2:c3], rtol=1e-6, atol=1e-6)
+    assert float(loc[:, :off].abs().sum()) == 0.0
+    xv = psrc.tensor().cpu().permute(0, 3, 1, 2)
+    assert torch.equal(pooled.tensor().cpu().permute(0, 3, 1, 2), F.max_pool2d(xv, 2, 2, 0, ceil_mode=True))
+    assert torch.equal(pooled3.tensor().cpu().permute(0, 3, 1, 2), F.max_pool2d(xv, 3, 1, 1))
 
 
 @pytest.mark.parametrize('case', [(256, 512, 3, 1, 6, 6, 19), (512, 128, 1, 1, 0, 1, 19), (128, 224, 3, 1, 3, 3, 31), (192, 256, 3, 2, 1, 1, 19)],
@@ -283,11 +377,14 @@ def _build(case, precision='fp32'):
     return net
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'fp32x3'])
 @pytest.mark.parametrize('case', NET_CASES, ids=[c[0] for c in NET_CASES])
-def test_full_forward_fp32_vs_reference_golden(golden, case):
+def test_full_forward_fp32_vs_reference_golden(golden, case, precision):
+    """north_star bar (scores / coords within 1e-4, class ids exact) in BOTH parity-grade modes: 'fp32' (CUDA cores) and
+    'fp32x3' (tcgen05 tensor cores, fp16 hi/lo operands + short chains, csrc/conv_x3.cu)."""
     tag, method, phase, setting, size, ncls, batch = case
     g = golden('net_%s.npz' % tag)
-    net = _build(case)
+    net = _build(case, precision)
     x = synth.seeded_input(batch, size, seed=0)
     loc, conf, obj = net(x)                                    # host tensor in, like test.py:130
     torch.cuda.synchronize()

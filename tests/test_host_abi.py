@@ -43,13 +43,24 @@ def test_library_exports_every_declared_symbol():
     assert L.ctx_rank_workspace_bytes(4, 11620) >= 4 * 16384 * 8
 
 
-def test_struct_layouts_match_header_sizes():
-    # the C structs are plain ints/floats/pointers: ctypes' natural alignment == the compiler's
-    assert ctypes.sizeof(_lib.CtxPostParams) == 14 * 4
-    assert ctypes.sizeof(_lib.CtxOutSeg) == 40
-    assert ctypes.sizeof(_lib.CtxConvParams) == 20 * 4 + 4 * 8 + 4 * 4 + 3 * 40
-    assert ctypes.sizeof(_lib.CtxPoolParams) == 10 * 4 + 8 + 8 + 8 + 8 + 8 + 8
-    assert ctypes.sizeof(_lib.CtxAttnParams) == 7 * 4 + 4 + 12 * 8 + 8 + 8 + 8 + 8
+def test_struct_layouts_match_header_sizes(tmp_path):
+    """sizeof / last-field offset of every struct as the C compiler sees include/ctx_b200.h == the ctypes mirrors."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = ['CtxPostParams', 'CtxOutSeg', 'CtxConvParams', 'CtxPoolParams', 'CtxAttnParams']
+    last = {n: getattr(_lib, n)._fields_[-1][0] for n in names}
+    src = tmp_path / 'sz.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ctx_b200.h"\nint main(void) {\n' +
+                   ''.join('  printf("%%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));\n' % (n, n, last[n]) for n in names) + '  return 0;\n}\n')
+    exe = tmp_path / 'sz'
+    subprocess.check_call(['gcc', '-I', os.path.join(root, 'include'), str(src), '-o', str(exe)])
+    lines = subprocess.check_output([str(exe)]).decode().split('\n')
+    for n, line in zip(names, lines):
+        size, off = (int(v) for v in line.split())
+        cls = getattr(_lib, n)
+        assert ctypes.sizeof(cls) == size, n
+        assert getattr(cls, last[n]).offset == off, n
 
 
 @pytest.mark.parametrize('name', ['VOC_300', 'VOC_512', 'COCO_300', 'COCO_512'])
