@@ -66,7 +66,10 @@ def _pool_out(h, k, s, pad, ceil_mode):
 
 
 class Engine(object):
-    def __init__(self, net, batch, precision, device, use_graph=True):
+    def __init__(self, net, batch, precision, device, use_graph=True, trace=False):
+        """``trace``: keep, per conv op, what a checker needs to recompute it from the op's own input buffer (folded fp32
+        weights, geometry, the views it reads / writes) in ``self.trace`` — tests walk the compiled net layer by layer."""
+        self.trace = [] if trace else None
         if precision not in _DT:
             raise ValueError("precision must be 'fp32', 'fp32x3', 'bf16' or 'fp16'")
         if not torch.cuda.is_available():
@@ -189,6 +192,10 @@ class Engine(object):
             p.seg[i].img_stride, p.seg[i].pix_stride, p.seg[i].ch_offset = img_stride, pix_stride, ch_off
             p.seg[i].dtype = _lib.dtype_code(t.dtype)
         self.last_conv_params = p            # (tests re-plan the same conv under other tilings)
+        if getattr(self, 'trace', None) is not None:
+            self.trace.append(dict(name=name, src=src, w=w, b=b, stride=stride, pad=(ph, pw), dil=dil, relu=bool(relu),
+                                   relu_channels=int(relu_channels), residual=residual, segs=segs, out=result, pool2=bool(pool2),
+                                   in_nchw=bool(in_nchw), op=self.L.ctx_prog_num_ops(self.prog)))
         flops = algo_flops if algo_flops is not None else 2.0 * src.N * Ho * Wo * Cout * Cin * KH * KW
         if self.split:
             return self._emit_conv_x3(name, p, src, w, residual, segs, result, flops, in_nchw, pool2)

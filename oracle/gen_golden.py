@@ -64,6 +64,31 @@ def gen_net(r):
         print(tag, loc.shape, conf.shape, float(conf.max()), flush=True)
 
 
+def gen_autocast(r):
+    """The REFERENCE module under torch.autocast('cpu', bfloat16) on the same seeded state / input as net_ours_transfer_300:
+    what 16-bit arithmetic costs the reference itself (SURVEY.md App. B measured 99.38 % argmax agreement on default-init
+    weights; this pins the figure on the seeded state the GPU tests use), the yardstick for the bf16 / fp16 engine modes."""
+    tag, method, phase, setting, size, ncls, batch = NET_CASES[0]
+    args = types.SimpleNamespace(method=method, phase=phase, setting=setting)
+    torch.manual_seed(0)
+    net = r.build_net(args, size, ncls)
+    net.load_state_dict(synth.seeded_state(net.state_dict(), seed=0))
+    net.eval()
+    net.device = 'cpu'
+    x = synth.seeded_input(batch, size, seed=0)
+    with torch.no_grad():
+        ref = net(x)
+        with torch.autocast('cpu', dtype=torch.bfloat16):
+            ac = [t.float() for t in net(x)]
+    d = dict(loc=ac[0].numpy()[:, ::ROW_STRIDE], conf=ac[1].numpy()[:, ::ROW_STRIDE], obj=ac[2].numpy()[:, ::ROW_STRIDE],
+             conf_argmax=ac[1].argmax(-1).numpy().astype(np.int16),
+             max_abs=np.array([float((a - b).abs().max()) for a, b in zip(ac, ref)]),
+             mean_abs=np.array([float((a - b).abs().mean()) for a, b in zip(ac, ref)]),
+             argmax_agreement=np.array(float((ac[1].argmax(-1) == ref[1].argmax(-1)).float().mean())))
+    np.savez_compressed(os.path.join(GOLD, 'net_%s_autocast_bf16.npz' % tag), **d)
+    print('autocast bf16 vs fp32 (reference, seeded state): max', d['max_abs'], 'mean', d['mean_abs'], 'argmax agreement', d['argmax_agreement'])
+
+
 def gen_post(r):
     """Detect.forward + the numpy loop of test.py:133-161 with the reference's own NMS routines."""
     priors = r.PriorBox(r.cfg.VOC_300).forward()
@@ -191,7 +216,7 @@ def gen_reweight(r):
 def main():
     os.makedirs(GOLD, exist_ok=True)
     r = ref_import.load()
-    which = sys.argv[1:] or ['priors', 'nms', 'post', 'match', 'net', 'reweight']
+    which = sys.argv[1:] or ['priors', 'nms', 'post', 'match', 'net', 'reweight', 'autocast']
     if 'priors' in which:
         gen_priors(r)
     if 'nms' in which:
@@ -204,6 +229,8 @@ def main():
         gen_reweight(r)
     if 'net' in which:
         gen_net(r)
+    if 'autocast' in which:
+        gen_autocast(r)
 
 
 if __name__ == '__main__':

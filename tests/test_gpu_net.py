@@ -464,7 +464,141 @@ def test_full_forward_16bit_tolerance(golden, precision):
     max_tol = 2e-2 if precision == 'fp16' else 2.5e-1
     assert dc.max() < max_tol and do.max() < max_tol and dl.max() < 2.5 * max_tol
     assert dc.mean() < (5e-4 if precision == 'fp16' else 4e-3) and do.mean() < (5e-4 if precision == 'fp16' else 4e-3)
-    assert agree > (0.97 if precision == 'fp16' else 0.90)
+    assert agree > (0.97 if precision == 'fp16' else 0.955)    # reference under bf16 autocast on this state: 0.9618
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+def test_16bit_forward_vs_quantisation_faithful_oracle(golden, precision):
+    """The 16-bit engine against an oracle that SHARES its quantisation (oracle/torch_net.py ``Quant``: BN folded then weights
+    rounded, every stored activation rounded once, fp16 K / V / P in the Context-Transformer, fp32 accumulate): what remains is
+    summation order and the activations that round to the other 16-bit neighbour — which cascade, so this is a statistical
+    comparison (the tight, layer-by-layer one is test_every_conv_of_the_compiled_net_vs_torch).  It pins the 16-bit-vs-fp32
+    gap to the oracle's prediction of it and to the REFERENCE's own: the reference module
+    under torch.autocast(bfloat16) on the same seeded state (tests/golden/net_ours_transfer_300_autocast_bf16.npz, generated
+    from /root/reference by oracle/gen_golden.py) loses as much or more."""
+    case = NET_CASES[0]
+    net = _build(case, precision)
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    x = synth.seeded_input(2, 300, seed=0)
+    got = [t.cpu() for t in net(x.cuda())]
+    dt = torch.bfloat16 if precision == 'bf16' else torch.float16
+    with torch.no_grad():
+        want = torch_net.forward(sd, x, 300, 60, 'ours', 2, 'transfer', quant=torch_net.Quant(dt, split_logits=False))
+        ref = torch_net.forward(sd, x, 300, 60, 'ours', 2, 'transfer')
+    d = [(a - b).abs() for a, b in zip(got, want)]
+    agree_q = (got[1].argmax(-1) == want[1].argmax(-1)).float().mean().item()
+    agree_ref = (got[1].argmax(-1) == ref[1].argmax(-1)).float().mean().item()
+    ac = golden('net_ours_transfer_300_autocast_bf16.npz')
+    print('%s vs quantised oracle: loc max %.2e mean %.2e | conf max %.2e mean %.2e | obj max %.2e mean %.2e | argmax agreement %.4f; '
+          'vs fp32 oracle: conf max %.2e argmax agreement %.4f (reference under bf16 autocast: conf max %.2e, agreement %.4f)'
+          % (precision, d[0].max(), d[0].mean(), d[1].max(), d[1].mean(), d[2].max(), d[2].mean(), agree_q,
+             (got[1] - ref[1]).abs().max(), agree_ref, ac['max_abs'][1], float(ac['argmax_agreement'])))
+    # Two correct 16-bit evaluations with different summation orders decorrelate (one flipped rounding changes its 9 * Cout
+    # consumers by up to an ulp, and so on): their distance is statistically the same as the distance to fp32 — the layer-wise
+    # test below is the tight one.  Here: the engine is as close to the quantised oracle as that oracle is to fp32 (+25 %),
+    # and no further from fp32 than the reference under bf16 autocast is.
+    for g_, w_, r_ in zip(got, want, ref):
+        assert (g_ - w_).abs().mean() < 1.25 * (w_ - r_).abs().mean() + 1e-6
+    if precision == 'bf16':
+        for g_, r_, m_ in zip(got, ref, ac['mean_abs']):
+            assert (g_ - r_).abs().mean() < 1.1 * float(m_)
+    # no worse than the reference's own bf16 behaviour (96.2 % on this state); fp16 keeps 3 more bits
+    assert agree_ref > (float(ac['argmax_agreement']) - 0.005 if precision == 'bf16' else 0.99)
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp16', 'fp32x3'])
+@pytest.mark.parametrize('case', [NET_CASES[0], NET_CASES[3]], ids=[NET_CASES[0][0], NET_CASES[3][0]])
+def test_every_conv_of_the_compiled_net_vs_torch(case, precision):
+    """Layer-by-layer parity walk over the COMPILED network (all 84 / 107 convs, real geometries, fused entries, residual
+    epilogues, fused pools, three-segment heads): every conv op is recomputed with torch fp32 from the op's OWN input buffer
+    and folded weights (rounded like the kernel's operands) and compared with what the kernel stored.  16-bit outputs must be
+    the correctly rounded value give or take the fp32 summation order and the tensor core's truncating adder (half an ulp of the 16-bit
+    type + 3e-5 of the layer's scale); fp32 head outputs and 'fp32x3' outputs are held to fp32 accuracy.  A whole-net comparison cannot do this for
+    bf16: two correct bf16 evaluations decorrelate after a few layers (rounding flips cascade), see the test above."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    tag, method, phase, setting, size, ncls, batch = case
+    net = _build(case, precision)
+    eng = Engine(net, 2, precision, DEV, use_graph=False, trace=True)
+    eng.run(synth.seeded_input(2, size, seed=0).cuda())
+    torch.cuda.synchronize()
+    dt = eng.act_dtype
+    half_ulp = {torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -11}[dt]
+    worst16, worst32, n16, n32 = 0.0, 0.0, 0, 0
+    assert len(eng.trace) > 60
+    for t in eng.trace:
+        src = t['src']
+        if t['in_nchw']:
+            x = eng.x_in if precision == 'fp32x3' else eng.x_in.to(dt).float()
+        else:
+            x = src.tensor().float().permute(0, 3, 1, 2)
+        w = t['w'] if precision == 'fp32x3' else t['w'].to(dt).float()
+        y = F.conv2d(x.double(), w.double(), t['b'].double(), t['stride'], t['pad'], t['dil'])
+        if t['residual'] is not None:
+            y = y + t['residual'].tensor().double().permute(0, 3, 1, 2)
+        if t['relu']:
+            rc = t['relu_channels'] or y.size(1)
+            y = torch.cat((F.relu(y[:, :rc]), y[:, rc:]), 1)
+        if t['pool2']:
+            y = F.max_pool2d(y, 2, 2)
+        y = y.permute(0, 2, 3, 1)                                   # NHWC
+        scale = y.abs().max().item() + 1e-30
+        if t['out'] is not None:
+            got = t['out'].tensor().double()
+            if precision == 'fp32x3':
+                e = ((got - y).abs().max() / scale).item()
+                worst32, n32 = max(worst32, e), n32 + 1
+                assert e < 2e-6, (t['name'], e)
+            else:
+                excess = ((got - y).abs() - half_ulp * y.abs() * 1.0001 - 3e-5 * scale).max().item()
+                worst16, n16 = max(worst16, ((got - y).abs().max() / scale).item()), n16 + 1
+                assert excess <= 0, (t['name'], excess, scale)
+        else:
+            N, HW = y.size(0), y.size(1) * y.size(2)
+            y = y.reshape(N, HW, -1)
+            for (buf, c0, c1, img_stride, pix_stride, ch_off) in t['segs']:
+                got = torch.as_strided(buf, (N, HW, c1 - c0), (img_stride, pix_stride, 1), buf.storage_offset() + ch_off).double()
+                e = ((got - y[..., c0:c1]).abs().max() / scale).item()
+                worst32, n32 = max(worst32, e), n32 + 1
+                assert e < (2e-6 if precision == 'fp32x3' else 2e-5), (t['name'], e)
+    print('%s %s: %d convs; 16-bit outputs (%d) worst |err|/scale %.2e (all within half an ulp); fp32-grade outputs (%d) worst %.2e'
+          % (tag, precision, len(eng.trace), n16, worst16, n32, worst32))
+
+
+@pytest.mark.parametrize('precision', ['fp32x3', 'bf16', 'fp16'])
+def test_detections_of_tensor_core_modes_vs_fp32_oracle(precision):
+    """Detection-level parity: top-200 records (prior index, class) of DetectPost on the tensor-core forward against the
+    oracle's post-processing of the ORACLE's fp32 forward (test.py:130-161 end to end, nothing shared).  'fp32x3' must
+    reproduce every detection; the 16-bit modes state their agreement."""
+    from oracle import c_oracle, np_oracle
+    case = NET_CASES[0]
+    net = _build(case, precision)
+    from bench import bench_state                              # objectness biased towards background: O(10^2) candidates per class
+    sd = bench_state(net)
+    net.load_state_dict(sd)
+    x = synth.seeded_input(2, 300, seed=2)
+    priors = ctx.PriorBox(ctx.VOC_300).forward()
+    scale = np.array([500, 375, 500, 375], np.float32)
+    post = ctx.DetectPost(21, 0, ctx.VOC_300, score_thresh=0.01)
+    rec, cnt, pidx = post.forward(net(x.cuda()), priors.cuda(), scale)
+    with torch.no_grad():
+        wl, wc, wo = torch_net.forward(sd, x, 300, 60, 'ours', 2, 'transfer')
+    boxes, scores = np_oracle.detect(wl.numpy(), wc.numpy(), wo.numpy(), priors.numpy())
+    tot, hit = 0, 0
+    for b in range(2):
+        dets, idx = np_oracle.postprocess_image(boxes[b], scores[b], scale, 0.01, 0.45, 200, nms_fn=lambda d, t: c_oracle.cpu_nms(d, t, False))
+        wrec, widx = np_oracle.records_from_dets(dets, idx)
+        n = int(cnt[b])
+        got = set(zip(pidx[b, :n].cpu().numpy().tolist(), rec[b, :n, 5].cpu().numpy().astype(int).tolist()))
+        want = set(zip(widx.astype(int).tolist(), wrec[:, 5].astype(int).tolist()))
+        assert len(want) > 50
+        tot += len(want | got)
+        hit += len(want & got)
+        if precision == 'fp32x3':
+            assert n == len(wrec) and np.array_equal(pidx[b, :n].cpu().numpy(), widx.astype(np.int32))
+            assert np.abs(rec[b, :n].cpu().numpy()[:, :5] - wrec[:, :5]).max() < 1e-4 * 500
+    print('%s: detection (prior, class) agreement with the fp32 oracle: %d / %d = %.4f' % (precision, hit, tot, hit / tot))
+    assert hit / tot >= {'fp32x3': 1.0, 'fp16': 0.93, 'bf16': 0.75}[precision]
 
 
 def test_512_fp16_full_detect_soft_nms():
