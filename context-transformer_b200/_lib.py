@@ -118,6 +118,11 @@ SIGNATURES = {
     'ctx_match_encode': (_I, [_P, _P, _I, _P, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     'ctx_rank_workspace_bytes': (_SZ, [_I, _I]),
     'ctx_hard_negative_rank': (_I, [_P, _I, _I, _P, _P, _SZ, _P]),
+    'ctx_loss_mining': (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
+    'ctx_loss_forward_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    'ctx_point_form': (_I, [_P, _I, _P, _P]),
+    'ctx_jaccard': (_I, [_P, _I, _P, _I, _P, _P]),
+    'ctx_encode': (_I, [_P, _P, _I, _F, _F, _P, _P]),
     'ctx_prototype_accumulate': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     'ctx_prototype_finalize': (_I, [_P, _P, _I, _I, _I, _P, _P]),
 }

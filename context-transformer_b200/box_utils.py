@@ -3,39 +3,50 @@
 ``match`` (box_utils.py:83-132) keeps the reference's in-place signature but runs on the GPU
 (``ctx_match_encode``); ``match_batch`` is the batched form the loss uses (one launch for the whole
 batch instead of the Python loop of multibox_loss_combined.py:70-74).  ``decode`` (:184-202) goes
-through the ``Detect`` kernel.  ``point_form`` / ``jaccard`` / ``encode`` are thin tensor
-expressions kept for API completeness (they are not on the timed path).
+through the ``Detect`` kernel.  ``point_form`` / ``jaccard`` / ``encode`` call the stand-alone device ops that share
+the match kernel's device functions (``ctx_point_form`` / ``ctx_jaccard`` / ``ctx_encode``).
 """
 import torch
 
 from . import _lib
 
 
+def _boxes(t, name):
+    t = _lib.require_cuda(t, name).detach().float().contiguous()
+    if t.dim() != 2 or t.size(1) != 4:
+        raise ValueError('%s must be [n,4]' % name)
+    return t
+
+
 def point_form(boxes):
-    return torch.cat((boxes[:, :2] - boxes[:, 2:] / 2, boxes[:, :2] + boxes[:, 2:] / 2), 1)
-
-
-def intersect(box_a, box_b):
-    A, B = box_a.size(0), box_b.size(0)
-    max_xy = torch.min(box_a[:, 2:].unsqueeze(1).expand(A, B, 2), box_b[:, 2:].unsqueeze(0).expand(A, B, 2))
-    min_xy = torch.max(box_a[:, :2].unsqueeze(1).expand(A, B, 2), box_b[:, :2].unsqueeze(0).expand(A, B, 2))
-    inter = torch.clamp((max_xy - min_xy), min=0)
-    return inter[:, :, 0] * inter[:, :, 1]
+    """(cx, cy, w, h) -> corners (box_utils.py:5-14), ``ctx_point_form``."""
+    boxes = _boxes(boxes, 'boxes')
+    out = torch.empty_like(boxes)
+    with torch.cuda.device(boxes.device):
+        _lib.check(_lib.lib().ctx_point_form(boxes.data_ptr(), boxes.size(0), out.data_ptr(), _lib.current_stream_ptr()), 'ctx_point_form')
+    return out
 
 
 def jaccard(box_a, box_b):
-    inter = intersect(box_a, box_b)
-    area_a = ((box_a[:, 2] - box_a[:, 0]) * (box_a[:, 3] - box_a[:, 1])).unsqueeze(1).expand_as(inter)
-    area_b = ((box_b[:, 2] - box_b[:, 0]) * (box_b[:, 3] - box_b[:, 1])).unsqueeze(0).expand_as(inter)
-    return inter / (area_a + area_b - inter)
+    """IoU matrix [A,B] of corner-form boxes (box_utils.py:50-68), ``ctx_jaccard`` — the device function the match kernel uses."""
+    box_a, box_b = _boxes(box_a, 'box_a'), _boxes(box_b, 'box_b')
+    out = torch.empty(box_a.size(0), box_b.size(0), device=box_a.device)
+    with torch.cuda.device(box_a.device):
+        _lib.check(_lib.lib().ctx_jaccard(box_a.data_ptr(), box_a.size(0), box_b.data_ptr(), box_b.size(0), out.data_ptr(),
+                                          _lib.current_stream_ptr()), 'ctx_jaccard')
+    return out
 
 
 def encode(matched, priors, variances):
-    g_cxcy = (matched[:, :2] + matched[:, 2:]) / 2 - priors[:, :2]
-    g_cxcy /= (variances[0] * priors[:, 2:])
-    g_wh = (matched[:, 2:] - matched[:, :2]) / priors[:, 2:]
-    g_wh = torch.log(g_wh) / variances[1]
-    return torch.cat([g_cxcy, g_wh], 1)
+    """Regression targets of matched corner boxes w.r.t. centre-form priors (box_utils.py:135-156), ``ctx_encode``."""
+    matched, priors = _boxes(matched, 'matched'), _boxes(priors, 'priors')
+    if matched.size(0) != priors.size(0):
+        raise ValueError('encode: %d matched boxes for %d priors' % (matched.size(0), priors.size(0)))
+    out = torch.empty_like(matched)
+    with torch.cuda.device(matched.device):
+        _lib.check(_lib.lib().ctx_encode(matched.data_ptr(), priors.data_ptr(), matched.size(0), float(variances[0]), float(variances[1]),
+                                         out.data_ptr(), _lib.current_stream_ptr()), 'ctx_encode')
+    return out
 
 
 def decode(loc, priors, variances):
@@ -48,7 +59,7 @@ def decode(loc, priors, variances):
     return boxes[0]
 
 
-def match_batch(threshold, targets, priors, variances, want_overlap=False):
+def match_batch(threshold, targets, priors, variances, want_overlap=False, obj_as_u8=False):
     """Batched ``match``: targets is a list of [n_i,6] tensors (x1,y1,x2,y2,label,weight).
     Returns loc_t[B,P,4] f32, conf_t[B,P,2] f32, obj_t[B,P] bool, best_truth_idx[B,P] int32
     (and best_truth_overlap[B,P] when asked)."""
@@ -56,15 +67,19 @@ def match_batch(threshold, targets, priors, variances, want_overlap=False):
     dev = priors.device
     B, P = len(targets), priors.size(0)
     max_obj = max([int(t.size(0)) for t in targets] + [1])
-    packed = torch.zeros(B, max_obj, 6)
-    nobj = torch.zeros(B, dtype=torch.int32)
-    for i, t in enumerate(targets):
-        n = int(t.size(0))
-        nobj[i] = n
-        if n:
-            packed[i, :n] = t.detach().float().cpu()
-    packed = packed.to(dev)
-    nobj = nobj.to(dev)
+    nobj = torch.tensor([int(t.size(0)) for t in targets], dtype=torch.int32)
+    if all(t.is_cuda for t in targets):               # already on the device: pad there, no host round trip per image
+        packed = torch.zeros(B, max_obj, 6, device=dev)
+        for i, t in enumerate(targets):
+            if t.size(0):
+                packed[i, :t.size(0)] = t.detach().float()
+    else:                                               # host targets (the reference's collate output): ONE stacked transfer
+        packed = torch.zeros(B, max_obj, 6)
+        for i, t in enumerate(targets):
+            if t.size(0):
+                packed[i, :t.size(0)] = t.detach().float().cpu()
+        packed = packed.to(dev, non_blocking=True)
+    nobj = nobj.to(dev, non_blocking=True)
     loc_t = torch.empty(B, P, 4, device=dev)
     conf_t = torch.empty(B, P, 2, device=dev)
     obj_u8 = torch.empty(B, P, dtype=torch.uint8, device=dev)
@@ -75,7 +90,7 @@ def match_batch(threshold, targets, priors, variances, want_overlap=False):
             packed.data_ptr(), nobj.data_ptr(), max_obj, priors.data_ptr(), B, P, float(threshold),
             float(variances[0]), float(variances[1]), loc_t.data_ptr(), conf_t.data_ptr(), obj_u8.data_ptr(),
             bti.data_ptr(), ovl.data_ptr() if want_overlap else None, _lib.current_stream_ptr()), 'ctx_match_encode')
-    out = (loc_t, conf_t, obj_u8.bool(), bti)
+    out = (loc_t, conf_t, obj_u8 if obj_as_u8 else obj_u8.bool(), bti)
     return out + (ovl,) if want_overlap else out
 
 

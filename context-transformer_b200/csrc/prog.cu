@@ -8,6 +8,9 @@
 #include "common.cuh"
 
 #include <stdlib.h>
+#include <array>
+#include <map>
+#include <mutex>
 #include <vector>
 
 namespace ctx {
@@ -66,6 +69,18 @@ static int run_op(Op& op, cudaStream_t st) {
   }
   set_error("prog: corrupt op kind");
   return CTX_ERR_INVALID;
+}
+
+// Tilings found by ctx_prog_autotune, per conv geometry, for the life of the process: recompiling a program after a
+// parameter change (load_state_dict, normalize(), another batch of the same size) re-uses them instead of timing ~30
+// candidates per layer again.  Key: everything the candidate timings depend on (shapes, strides, dtypes, epilogue kind).
+using TuneKey = std::array<int, 22>;
+struct TuneVal { int n, cl, amode, cg; };
+static std::map<TuneKey, TuneVal>& tune_cache() { static std::map<TuneKey, TuneVal> m; return m; }
+static std::mutex& tune_mutex() { static std::mutex m; return m; }
+static TuneKey tune_key(const CtxConvParams& c) {
+  return TuneKey{c.N, c.H, c.W, c.Cin, c.in_cstride, c.in_coffset % 64, c.Cout, c.KH, c.KW, c.stride, c.pad_h, c.pad_w, c.dil, c.relu,
+                 c.pool2, c.relu_channels, c.in_dtype, c.nseg, c.seg[0].dtype, c.residual ? 1 : 0, c.seg[0].pix_stride, c.res_cstride};
 }
 
 static void drop_graph(Prog* pr) {
@@ -221,6 +236,20 @@ extern "C" int ctx_prog_autotune(void* prog, void* stream, int reps) {
   for (Op& op : pr->ops) {
     ++op_index;
     if (op.kind != OP_CONV_TC || op.conv.in_nchw) continue;
+    const TuneKey tkey = tune_key(op.conv);
+    {
+      std::lock_guard<std::mutex> lock(tune_mutex());
+      auto it = tune_cache().find(tkey);
+      if (it != tune_cache().end()) {
+        void* cand = nullptr;
+        const TuneVal& v = it->second;
+        if (ctx_conv2d_tc_plan_create_tuned(&op.conv, v.n, v.cl, v.amode, v.cg, &cand) == CTX_OK) {
+          ctx_conv2d_tc_plan_destroy(op.tc_plan);
+          op.tc_plan = cand;
+          continue;
+        }
+      }
+    }
     float best_ms = 0.f;
     if ((rc = time_plan(op.tc_plan, &best_ms))) break;
     int base[8];
@@ -256,8 +285,14 @@ extern "C" int ctx_prog_autotune(void* prog, void* stream, int reps) {
         for (int cl = 1; cl <= 2 && !rc; ++cl)
           if (consider(n, cl, amode, 0)) { best_n = n; best_cl = cl; best_amode = amode; }
     }
-    for (int cg = 1; cg <= 4 && !rc; cg *= 2) consider(best_n, best_cl, best_amode, cg);
+    int best_cg = 0;
+    for (int cg = 1; cg <= 4 && !rc; cg *= 2)
+      if (consider(best_n, best_cl, best_amode, cg)) best_cg = cg;
     if (rc) break;
+    {
+      std::lock_guard<std::mutex> lock(tune_mutex());
+      tune_cache()[tkey] = TuneVal{best_n, best_cl, best_amode, best_cg};
+    }
   }
   if (log) fclose(log);
   cudaEventDestroy(e0);

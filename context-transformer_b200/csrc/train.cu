@@ -230,3 +230,218 @@ extern "C" int ctx_prototype_finalize(const double* sums, const int* counts, int
   CTX_LAUNCH_CHECK();
   return CTX_OK;
 }
+
+
+// ---- MultiBoxLoss_combined, forward + backward : layers/modules/multibox_loss_combined.py:76-122 ------------------------
+// Upstream is ~40 framework ops with boolean-mask gathers (dynamic shapes -> host syncs) and an autograd tape.  Here:
+//   ctx_loss_mining            the no-grad objectness CE used for mining (:88-90) + the per-image weighted positive count (:77)
+//   (ctx_hard_negative_rank    the two sorts, :91-93)
+//   ctx_loss_forward_backward  one pass over the priors: smooth-L1 on positives (:81-85), objectness CE on pos | neg (:98-100),
+//                              class CE on the logit-combined scores [obj0 + log sum exp(conf), obj1 + conf_k] (:106-117), the
+//                              three sums in fp64, and — since every term is a closed-form function of one prior's row — the
+//                              gradients w.r.t. loc / conf / obj in the same pass (no tape, no second read).
+namespace ctx {
+constexpr int kLossThreads = 256;
+constexpr int kMaxLossClasses = 64;
+
+__device__ __forceinline__ double block_sum(double v, double* s_red) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  v = lane < (int)(blockDim.x >> 5) ? s_red[lane] : 0.0;
+  if (warp == 0) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  return v;                                   // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+loss_mining_kernel(const float* __restrict__ obj_p, const float* __restrict__ conf_t, const unsigned char* __restrict__ obj_t, int P,
+                   float* __restrict__ mining, double* __restrict__ num_pos_w) {
+  __shared__ double s_red[32];
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double w = 0.0;
+  if (p < P) {
+    const long long i = (long long)b * P + p;
+    const float2 o = reinterpret_cast<const float2*>(obj_p)[i];
+    const float2 t = reinterpret_cast<const float2*>(conf_t)[i];
+    float l = 0.f;
+    if (!obj_t[i]) {                          // target 0: lse(o) - o0; positives and ignored boxes do not compete (:90)
+      const float m = fmaxf(o.x, o.y);
+      l = (m + logf(expf(o.x - m) + expf(o.y - m))) - o.x;
+    }
+    mining[i] = l;
+    if (t.x > 0.f) w = (double)t.y;
+  }
+  const double s = block_sum(w, s_red);
+  if (threadIdx.x == 0 && s != 0.0) atomicAdd(num_pos_w + b, s);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kLossThreads)
+loss_fwd_bwd_kernel(const float* __restrict__ loc_p, const float* __restrict__ conf_p, const float* __restrict__ obj_p,
+                    const float* __restrict__ loc_t, const float* __restrict__ conf_t, const unsigned char* __restrict__ obj_t,
+                    const int* __restrict__ rank, const long long* __restrict__ num_neg, int P,
+                    double* __restrict__ sums, float* __restrict__ dloc, float* __restrict__ dconf, float* __restrict__ dobj_c,
+                    float* __restrict__ dobj_o) {
+  __shared__ double s_red[32];
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double sl = 0.0, sc = 0.0, so = 0.0;
+  if (p < P) {
+    const long long i = (long long)b * P + p;
+    const float2 t = reinterpret_cast<const float2*>(conf_t)[i];
+    const float w = t.y;
+    const bool pos = t.x > 0.f;
+    const bool neg = (long long)rank[i] < num_neg[b];
+    float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pos) {                                 // smooth-L1 (beta = 1), weighted (:81-85)
+      const float4 a = reinterpret_cast<const float4*>(loc_p)[i], g = reinterpret_cast<const float4*>(loc_t)[i];
+      const float d[4] = {a.x - g.x, a.y - g.y, a.z - g.z, a.w - g.w};
+      float s = 0.f, gd[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float ad = fabsf(d[k]);
+        s += ad < 1.f ? 0.5f * d[k] * d[k] : ad - 0.5f;
+        gd[k] = (ad < 1.f ? d[k] : (d[k] > 0.f ? 1.f : -1.f)) * w;
+      }
+      sl = (double)(s * w);
+      gl = make_float4(gd[0], gd[1], gd[2], gd[3]);
+    }
+    reinterpret_cast<float4*>(dloc)[i] = gl;
+    float2 go = make_float2(0.f, 0.f), gc = make_float2(0.f, 0.f);
+    float* dcr = dconf + i * C;
+    const long long label = (long long)t.x;     // conf_t[..., 0].long()
+    if ((pos || neg) && label >= 0 && label <= C) {
+      const float2 o = reinterpret_cast<const float2*>(obj_p)[i];
+      // objectness CE against obj_t (:98-100)
+      {
+        const float m = fmaxf(o.x, o.y), e0 = expf(o.x - m), e1 = expf(o.y - m), z = e0 + e1;
+        const bool tt = obj_t[i] != 0;
+        so = (double)(((m + logf(z)) - (tt ? o.y : o.x)) * w);
+        go = make_float2((e0 / z - (tt ? 0.f : 1.f)) * w, (e1 / z - (tt ? 1.f : 0.f)) * w);
+      }
+      // class CE on the combined logits (:106-117); log(sum(exp(conf))) un-stabilised, as upstream
+      float c[C], S = 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) { c[k] = conf_p[i * C + k]; S += expf(c[k]); }
+      const float l0 = o.x + logf(S);
+      float M = l0;
+#pragma unroll
+      for (int k = 0; k < C; ++k) M = fmaxf(M, o.y + c[k]);
+      float Z = expf(l0 - M);
+#pragma unroll
+      for (int k = 0; k < C; ++k) Z += expf(o.y + c[k] - M);
+      const float l_lab = label == 0 ? l0 : o.y + c[label - 1];
+      sc = (double)(((M + logf(Z)) - l_lab) * w);
+      const float g0 = (expf(l0 - M) / Z - (label == 0 ? 1.f : 0.f)) * w;
+      float gsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        const float gk = (expf(o.y + c[k] - M) / Z - (label == k + 1 ? 1.f : 0.f)) * w;
+        gsum += gk;
+        dcr[k] = gk + g0 * (expf(c[k]) / S);    // d l0 / d conf_k = softmax(conf)_k
+      }
+      gc = make_float2(g0, gsum);
+    }                                           // rows outside pos | neg stay zero (dconf is cleared by the launcher)
+    reinterpret_cast<float2*>(dobj_o)[i] = go;
+    reinterpret_cast<float2*>(dobj_c)[i] = gc;
+  }
+  double v = block_sum(sl, s_red);
+  if (threadIdx.x == 0 && v != 0.0) atomicAdd(sums + 0, v);
+  v = block_sum(sc, s_red);
+  if (threadIdx.x == 0 && v != 0.0) atomicAdd(sums + 1, v);
+  v = block_sum(so, s_red);
+  if (threadIdx.x == 0 && v != 0.0) atomicAdd(sums + 2, v);
+}
+}  // namespace ctx
+
+extern "C" int ctx_loss_mining(const float* obj_p, const float* conf_t, const unsigned char* obj_t, int batch, int num_priors,
+                               float* mining, double* num_pos_w, void* stream) {
+  CTX_REQUIRE(obj_p && conf_t && obj_t && mining && num_pos_w, "ctx_loss_mining: null pointer");
+  CTX_REQUIRE(batch >= 0 && num_priors >= 1, "ctx_loss_mining: bad sizes");
+  if (batch == 0) return CTX_OK;
+  CTX_CUDA_TRY(cudaMemsetAsync(num_pos_w, 0, sizeof(double) * batch, (cudaStream_t)stream));
+  loss_mining_kernel<<<dim3(cdiv(num_priors, kLossThreads), batch), kLossThreads, 0, (cudaStream_t)stream>>>(obj_p, conf_t, obj_t, num_priors, mining, num_pos_w);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
+extern "C" int ctx_loss_forward_backward(const float* loc_p, const float* conf_p, const float* obj_p, const float* loc_t, const float* conf_t,
+                                         const unsigned char* obj_t, const int* rank, const long long* num_neg, int batch, int num_priors,
+                                         int num_fg_classes, double* sums3, float* dloc, float* dconf, float* dobj_cls, float* dobj_obj,
+                                         void* stream) {
+  CTX_REQUIRE(loc_p && conf_p && obj_p && loc_t && conf_t && obj_t && rank && num_neg && sums3 && dloc && dconf && dobj_cls && dobj_obj,
+              "ctx_loss_forward_backward: null pointer");
+  CTX_REQUIRE(batch >= 0 && num_priors >= 1, "ctx_loss_forward_backward: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  CTX_CUDA_TRY(cudaMemsetAsync(sums3, 0, 3 * sizeof(double), st));
+  if (batch == 0) return CTX_OK;
+  CTX_CUDA_TRY(cudaMemsetAsync(dconf, 0, sizeof(float) * (size_t)batch * num_priors * num_fg_classes, st));
+  const dim3 grid(cdiv(num_priors, kLossThreads), batch);
+#define CTX_LOSS(CN) loss_fwd_bwd_kernel<CN><<<grid, kLossThreads, 0, st>>>(loc_p, conf_p, obj_p, loc_t, conf_t, obj_t, rank, num_neg, num_priors, sums3, dloc, dconf, dobj_cls, dobj_obj)
+  switch (num_fg_classes) {
+    case 20: CTX_LOSS(20); break;              // VOC (num_classes 21)
+    case 60: CTX_LOSS(60); break;              // COCO source classes
+    case 15: CTX_LOSS(15); break;
+    case 5: CTX_LOSS(5); break;
+    default: set_error("ctx_loss_forward_backward: %d foreground classes not instantiated (5, 15, 20, 60)", num_fg_classes); return CTX_ERR_UNSUPPORTED;
+  }
+#undef CTX_LOSS
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
+
+// ---- stand-alone box algebra : utils/box_utils.py:5-14 (point_form), :50-68 (jaccard), :135-156 (encode) ----------------
+// The same device functions the match kernel uses, exposed for callers of the reference's helper API.
+namespace ctx {
+__global__ void __launch_bounds__(256) point_form_kernel(const float4* __restrict__ boxes, int n, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = point_form(boxes[i]);
+}
+__global__ void __launch_bounds__(256) jaccard_kernel(const float4* __restrict__ a, int A, const float4* __restrict__ b, int B, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)A * B) return;
+  const float4 t = a[i / B], p = b[i % B];
+  out[i] = jaccard_one(t, __fmul_rn(__fsub_rn(t.z, t.x), __fsub_rn(t.w, t.y)), p);
+}
+__global__ void __launch_bounds__(256) encode_kernel(const float4* __restrict__ matched, const float4* __restrict__ priors, int n, float v0, float v1,
+                                                     float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 m = matched[i], pc = priors[i];
+  float gx = __fsub_rn(__fmul_rn(__fadd_rn(m.x, m.z), 0.5f), pc.x);
+  float gy = __fsub_rn(__fmul_rn(__fadd_rn(m.y, m.w), 0.5f), pc.y);
+  gx = __fdiv_rn(gx, __fmul_rn(v0, pc.z));
+  gy = __fdiv_rn(gy, __fmul_rn(v0, pc.w));
+  out[i] = make_float4(gx, gy, __fdiv_rn(logf(__fdiv_rn(__fsub_rn(m.z, m.x), pc.z)), v1), __fdiv_rn(logf(__fdiv_rn(__fsub_rn(m.w, m.y), pc.w)), v1));
+}
+}  // namespace ctx
+
+extern "C" int ctx_point_form(const float* boxes, int n, float* out, void* stream) {
+  CTX_REQUIRE(n >= 0 && (n == 0 || (boxes && out)), "ctx_point_form: bad arguments");
+  if (n == 0) return CTX_OK;
+  point_form_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)boxes, n, (float4*)out);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+extern "C" int ctx_jaccard(const float* box_a, int na, const float* box_b, int nb, float* out, void* stream) {
+  CTX_REQUIRE(na >= 0 && nb >= 0 && ((long long)na * nb == 0 || (box_a && box_b && out)), "ctx_jaccard: bad arguments");
+  if ((long long)na * nb == 0) return CTX_OK;
+  jaccard_kernel<<<cdiv((long long)na * nb, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)box_a, na, (const float4*)box_b, nb, out);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+extern "C" int ctx_encode(const float* matched, const float* priors, int n, float var0, float var1, float* out, void* stream) {
+  CTX_REQUIRE(n >= 0 && (n == 0 || (matched && priors && out)), "ctx_encode: bad arguments");
+  if (n == 0) return CTX_OK;
+  encode_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)matched, (const float4*)priors, n, var0, var1, (float4*)out);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}

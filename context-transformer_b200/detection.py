@@ -127,6 +127,10 @@ def records_to_all_boxes(records, counts, num_classes):
     import numpy as np
     rec = records.cpu().numpy()
     cnt = counts.cpu().numpy()
+    if int(cnt.max(initial=0)) > int(records.shape[1]):
+        import warnings
+        warnings.warn('DetectPost kept %d detections for an image but the record buffer holds %d rows: the excess (lowest classes '
+                      'last) was dropped — raise max_out' % (int(cnt.max()), int(records.shape[1])))
     B = rec.shape[0]
     all_boxes = [[np.empty((0, 5), dtype=np.float32) for _ in range(B)] for _ in range(num_classes)]
     for i in range(B):

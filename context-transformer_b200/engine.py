@@ -325,9 +325,15 @@ class Engine(object):
                 entry_out[key] = fused.slice(off, bc.out_channels)
                 off += bc.out_channels
 
-        # branch bi runs on lane bi (the block input / fused entry conv was produced on lane 0)
-        off = 0
-        for bi, br in enumerate(branches):
+        # branch bi runs on lane bi (the block input / fused entry conv was produced on the home lane).  The side branches are
+        # emitted FIRST: a lane's fork point is wherever the home lane stands when the lane's first op is recorded, so emitting
+        # branch 0 (home lane) before them would make every side branch wait for branch 0's convs as well.
+        offs, off = [], 0
+        for br in branches:
+            offs.append(off)
+            off += br[-1].out_channels
+        for bi in list(range(1, len(branches))) + [0]:
+            br = branches[bi]
             self._lane(home if bi == 0 else min(bi, 3), wait=(home,))
             t = src
             for li, layer in enumerate(br):
@@ -336,8 +342,7 @@ class Engine(object):
                     t = entry_out[bi]
                     continue
                 t = self._basic_conv('%s.branch%d.%d' % (name, bi, li), layer, t,
-                                     out=cat.slice(off, layer.out_channels) if last else None)
-            off += br[-1].out_channels
+                                     out=cat.slice(offs[bi], layer.out_channels) if last else None)
         self._lane(home, wait=tuple(range(1, min(len(branches), 4))))
         short = entry_out['shortcut'] if 'shortcut' in entry_out else self._basic_conv(name + '.shortcut', m.shortcut, src)
         # relu(ConvLinear(cat) * scale + short): scale folds into the weights, the add + ReLU into the epilogue

@@ -194,6 +194,7 @@ class RFBNet(nn.Module):
         self.size = size
         self.precision = getattr(args, 'precision', 'fp32')
         self.use_cuda_graph = True
+        self.static_outputs = False        # True: forward returns the engine's own output buffers (zero-copy; overwritten by the next call)
         self._engines = {}
         if size == 300:
             self.indicator = 3
@@ -232,17 +233,27 @@ class RFBNet(nn.Module):
         return self.method == 'ours' and self.phase == 2
 
     # ---- inference: compiled sm_100a program --------------------------------------------------
+    MAX_ENGINES = 3                        # live compiled programs (one per batch size / precision), least recently used goes first
+
     def invalidate_engine(self):
         self._engines = {}
 
     def engine(self, batch):
+        """The compiled program for this batch size (activations are sized per batch).  A few are kept (the last, smaller
+        batch of a dataset must not evict the main one); a parameter change (``load_state_dict``, ``normalize()``, an
+        optimizer step) drops all of them.  Re-tuning after such a rebuild is free: the per-layer tiling found by
+        measurement is cached per conv geometry inside the library."""
         from .engine import Engine
         dev = torch.device(self.device)
-        key = (batch, self.precision, dev.index if dev.index is not None else torch.cuda.current_device())
-        eng = self._engines.get(key)
-        if eng is None or eng.stale(self):
+        key = (batch, self.precision, dev.index if dev.index is not None else torch.cuda.current_device(), self.use_cuda_graph)
+        eng = self._engines.pop(key, None)
+        if eng is not None and eng.stale(self):
+            self._engines, eng = {}, None
+        if eng is None:
             eng = Engine(self, batch, self.precision, dev, use_graph=self.use_cuda_graph)
-            self._engines = {key: eng}             # one live engine: activations are sized per batch
+        self._engines[key] = eng                   # most recently used last
+        while len(self._engines) > self.MAX_ENGINES:
+            self._engines.pop(next(iter(self._engines)))
         return eng
 
     def forward(self, x, init=False):
@@ -253,7 +264,10 @@ class RFBNet(nn.Module):
         if torch.device(self.device).type != 'cuda':
             raise RuntimeError("RFBNet inference runs only on a CUDA device (sm_100a kernels, no CPU fallback); "
                                "got model.device = %r" % (self.device,))
-        return self.engine(x.size(0)).run(x)           # fp32 [B,3,S,S], or uint8 [B,S,S,3] (on-device BaseTransform)
+        out = self.engine(x.size(0)).run(x)            # fp32 [B,3,S,S], or uint8 [B,S,S,3] (on-device BaseTransform)
+        # like the reference (RFB_Net_vgg.py:246-286) every call returns tensors of its own: the caller may keep them while
+        # the next batch runs.  ``static_outputs = True`` hands out the engine's buffers instead (saves three D2D copies).
+        return out if self.static_outputs else tuple(t.clone() for t in out)
 
     # ---- training / prototype init: autograd expression of the same graph ---------------------
     def _forward_autograd(self, x, init=False):

@@ -230,6 +230,27 @@ size_t ctx_rank_workspace_bytes(int batch, int num_priors);
 int ctx_hard_negative_rank(const float* loss, int batch, int num_priors, int* rank,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* MultiBoxLoss_combined.forward + its backward, layers/modules/multibox_loss_combined.py:76-122 (after match(): loc_t, conf_t,
+ * obj_t from ctx_match_encode).
+ * ctx_loss_mining: mining[B,P] = CE(obj_p, 0) with positives / ignored boxes zeroed (:88-90) — the input of
+ *   ctx_hard_negative_rank — and num_pos_w[B] (fp64) = sum of the mixup weights of the positives (:77; the caller truncates to
+ *   integer and forms num_neg = min(3 num_pos, P - 1), :94).
+ * ctx_loss_forward_backward: sums3 (fp64) = {loss_box_reg, loss_cls, loss_obj} BEFORE the division by N (:119-122), and the
+ *   gradients of those sums: dloc[B,P,4] (of sums3[0]), dconf[B,P,C] and dobj_cls[B,P,2] (of sums3[1]), dobj_obj[B,P,2] (of
+ *   sums3[2]); rows outside pos | neg are zero.  rank[B,P] from ctx_hard_negative_rank, num_neg[B] int64. */
+int ctx_loss_mining(const float* obj_p, const float* conf_t, const unsigned char* obj_t, int batch, int num_priors,
+                    float* mining, double* num_pos_w, void* stream);
+int ctx_loss_forward_backward(const float* loc_p, const float* conf_p, const float* obj_p, const float* loc_t, const float* conf_t,
+                              const unsigned char* obj_t, const int* rank, const long long* num_neg, int batch, int num_priors,
+                              int num_fg_classes, double* sums3, float* dloc, float* dconf, float* dobj_cls, float* dobj_obj,
+                              void* stream);
+
+/* Box algebra helpers of utils/box_utils.py as stand-alone device ops (the match kernel uses the same device functions):
+ * point_form :5-14 (cx,cy,w,h -> corners), jaccard :50-68 (out[na,nb], corner-form boxes, no +1), encode :135-156. */
+int ctx_point_form(const float* boxes, int n, float* out, void* stream);
+int ctx_jaccard(const float* box_a, int na, const float* box_b, int nb, float* out, void* stream);
+int ctx_encode(const float* matched, const float* priors, int n, float var0, float var1, float* out, void* stream);
+
 /* OBJ(Target) prototype initialisation, train.py:252-286 (init_reweight).  feat[B,P,dim] = model(x, init=True) (raw conf
  * features), conf_t[B,P,2] = the match() labels (ctx_match_encode).  Adds every positive prior's L2-normalised feature row
  * to sums[num_fg, dim] (fp64, caller-zeroed before the first batch) and its class to counts[num_fg]; call once per batch.

@@ -158,16 +158,19 @@ def gen_match_loss(r):
     for i in range(B):
         r.box_utils.match(0.5, targets[i][:, :4], priors, [0.1, 0.2], targets[i][:, 4:6], loc_t, conf_t, obj_t, i, overlap)
     g = synth._gen(0, 'losspred')
-    loc_p = torch.randn(B, P, 4, generator=g)
-    conf_p = torch.randn(B, P, 20, generator=g)
-    obj_p = torch.randn(B, P, 2, generator=g)
+    loc_p = torch.randn(B, P, 4, generator=g).requires_grad_()
+    conf_p = torch.randn(B, P, 20, generator=g).requires_grad_()
+    obj_p = torch.randn(B, P, 2, generator=g).requires_grad_()
     crit = r.MultiBoxLoss_combined(21, 0.5, True, 0, True, 3, 0.5, False)
     losses = crit((loc_p, conf_p, obj_p), priors, targets)
+    # gradients of the reference module's own autograd graph; distinct weights per term so that each gradient path is pinned
+    (1.0 * losses['loss_box_reg'] + 2.0 * losses['loss_cls'] + 3.0 * losses['loss_obj']).backward()
     pos = conf_t[:, :, 0] != 0
     out = dict(loc_t_pos=loc_t[pos].numpy(), pos_index=pos.nonzero().numpy().astype(np.int32),
                conf_t=conf_t.numpy(), obj_t=obj_t.numpy(), overlap=overlap.numpy()[:, ::ROW_STRIDE],
                loc_t_sum=checksum(loc_t), targets=np.array([t.numpy() for t in targets], dtype=object),
-               loss=np.array([float(losses['loss_box_reg']), float(losses['loss_cls']), float(losses['loss_obj'])]))
+               loss=np.array([float(losses['loss_box_reg']), float(losses['loss_cls']), float(losses['loss_obj'])]),
+               grad_weights=np.array([1.0, 2.0, 3.0]), grad_loc=loc_p.grad.numpy(), grad_conf=conf_p.grad.numpy(), grad_obj=obj_p.grad.numpy())
     np.savez_compressed(os.path.join(GOLD, 'match_loss.npz'), **out)
 
 

@@ -422,6 +422,28 @@ def test_forward_other_seed_vs_torch_oracle_and_cuda_graph():
         assert (got.cpu() - w).abs().max() < 1e-4
 
 
+def test_forward_returns_fresh_tensors_unless_static_outputs():
+    """Like the reference (RFB_Net_vgg.py:246-286) every forward returns tensors of its own; ``static_outputs`` is the
+    zero-copy opt-in.  A smaller last batch must not evict the main engine (tile autotune + graph capture cost seconds)."""
+    net = _build(NET_CASES[2], 'bf16')
+    x1, x2 = synth.seeded_input(2, 300, seed=1).cuda(), synth.seeded_input(2, 300, seed=2).cuda()
+    a = net(x1)
+    keep = [t.clone() for t in a]
+    b = net(x2)
+    torch.cuda.synchronize()
+    for ta, tk, tb in zip(a, keep, b):
+        assert ta.data_ptr() != tb.data_ptr() and torch.equal(ta, tk) and not torch.equal(ta, tb)
+    eng = net.engine(2)
+    net(synth.seeded_input(1, 300, seed=3).cuda())             # another batch size: a second engine, the first one stays
+    assert net.engine(2) is eng
+    net.static_outputs = True
+    c = net(x1)
+    d = net(x2)
+    assert all(tc.data_ptr() == td.data_ptr() for tc, td in zip(c, d))
+    torch.cuda.synchronize()
+    assert all(torch.equal(tk, t) for tk, t in zip([t.clone() for t in b], d))
+
+
 def test_graph_lanes_and_autotuned_tiles_are_bit_identical(monkeypatch):
     """The captured graph runs RFB branches / heads on parallel lanes and every conv under its measured-best tiling; neither
     may change a single bit against the serial, default-tiled program."""

@@ -297,6 +297,9 @@ def test_hard_negative_rank(P):
 
 
 def test_multibox_loss_vs_golden_and_oracle(golden):
+    """Fused loss forward + backward (ctx_loss_mining / ctx_hard_negative_rank / ctx_loss_forward_backward) against the
+    reference module's own values AND its autograd gradients (tests/golden/match_loss.npz: d(1*box + 2*cls + 3*obj) / d
+    loc, conf, obj from /root/reference/layers/modules/multibox_loss_combined.py run on CPU)."""
     g = golden('match_loss.npz')
     priors = ctx.PriorBox(ctx.VOC_300).forward()
     targets = [torch.from_numpy(np.asarray(t, dtype=np.float32)) for t in g['targets']]
@@ -309,8 +312,31 @@ def test_multibox_loss_vs_golden_and_oracle(golden):
     out = crit((loc_p, conf_p, obj_p), priors.to(DEV), targets)
     got = np.array([float(out['loss_box_reg']), float(out['loss_cls']), float(out['loss_obj'])])
     assert np.allclose(got, g['loss'], rtol=2e-5)
-    sum(out.values()).backward()
-    assert loc_p.grad is not None and float(conf_p.grad.abs().sum()) > 0 and float(obj_p.grad.abs().sum()) > 0
+    wl, wc, wo = (float(v) for v in g['grad_weights'])
+    (wl * out['loss_box_reg'] + wc * out['loss_cls'] + wo * out['loss_obj']).backward()
+    for name, t in (('grad_loc', loc_p), ('grad_conf', conf_p), ('grad_obj', obj_p)):
+        want = g[name]
+        gt = t.grad.cpu().numpy()
+        assert np.array_equal((gt != 0).any(-1), (want != 0).any(-1)), name    # exactly the reference's pos | neg rows
+        assert np.allclose(gt, want, rtol=2e-5, atol=1e-8), (name, np.abs(gt - want).max())
+    # targets already on the device (no host round trip), same result
+    out2 = crit((loc_p.detach(), conf_p.detach(), obj_p.detach()), priors.to(DEV), [t.to(DEV) for t in targets])
+    assert all(float(out2[k]) == float(out[k]) for k in out)
+
+
+def test_box_algebra_helpers_vs_oracle():
+    """point_form / jaccard / encode as stand-alone device ops against the numpy oracle (utils/box_utils.py:5-68, 135-156)."""
+    from oracle import np_oracle
+    g = synth._gen(5, 'boxalg')
+    pri = ctx.PriorBox(ctx.VOC_300).forward()[::7].contiguous()
+    xy = torch.rand(9, 2, generator=g) * 0.5
+    tr = torch.cat([xy, xy + 0.1 + 0.4 * torch.rand(9, 2, generator=g)], 1)
+    pf = ctx.point_form(pri.to(DEV)).cpu().numpy()
+    assert np.array_equal(pf, np_oracle.point_form(pri.numpy()))
+    assert np.allclose(ctx.jaccard(tr.to(DEV), torch.from_numpy(pf).to(DEV)).cpu().numpy(), np_oracle.jaccard(tr.numpy(), pf), rtol=0, atol=1e-7)
+    matched = tr[torch.randint(0, 9, (pri.size(0),), generator=g)]
+    assert np.allclose(ctx.encode(matched.to(DEV), pri.to(DEV), [0.1, 0.2]).cpu().numpy(), np_oracle.encode(matched.numpy(), pri.numpy(), (0.1, 0.2)),
+                       rtol=2e-5, atol=1e-6)
 
 
 def test_init_reweight_vs_golden_and_oracle(golden):
