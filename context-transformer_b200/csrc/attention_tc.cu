@@ -15,12 +15,14 @@
 //                prologue: load the conf row, split hi/lo, stage it as an A operand; after the projection
 //                MMA (Q = conf (theta+I)^T, 12 UMMAs) read Q from TMEM, add the bias, split hi/lo and stage
 //                it as the A operand of the logits MMAs.
-//                pass A: row maximum of the hi-only logits Qh Kh^T (4 UMMAs M128 N128 / tile) -> softmax reference.
-//                pass B: exact logits (12 UMMAs / tile), p = ex2(s*log2e - ref) against that FIXED reference
-//                (the O accumulator in TMEM never needs a running-maximum rescale, so PV of tile j overlaps
-//                the exponentials of tile j+1); P is written as the fp16 A operand of the PV MMA.
+//                key loop: logits (4 UMMAs / tile, 12 in split mode), p = ex2(s*log2e - ref) against a reference that
+//                only moves when a tile's maximum exceeds it by more than 2^AT_TAU (online softmax with LAZY rescale:
+//                the first half tile sets it; a later jump rescales the row's O / l accumulator in TMEM and the half
+//                tile of P already staged — a handful of times per row, so PV of tile j still overlaps the
+//                exponentials of tile j+1 and no separate maximum pass over the keys exists); P is written as the
+//                fp16 A operand of the PV MMA.
 //                epilogue: O/l, z = conf + O*Wz, z/||z||, OBJ_Target*scale [, fc_base(conf)+conf], class softmax.
-//     warp 8     TMA producer: theta weights once, then {Kh} (pass A) / {Kh, Kl, V^T} (pass B) tiles.
+//     warp 8     TMA producer: theta weights once, then {Kh, V^T[, Kl]} tiles.
 //     warp 9     TMEM allocator + MMA issuer (one elected lane); tcgen05.commit drives every hand-off mbarrier.
 #include "tc_common.cuh"
 
@@ -37,6 +39,7 @@ constexpr int AT_TILE_K = AT_BK * AT_DP * 2;      // 16 KB: 128 keys x 64 featur
 constexpr int AT_TILE_W = AT_DP * AT_DP * 2;      // 8 KB: 64 x 64 (theta' half, V^T key block)
 constexpr int AT_STAGE_SPLIT = 3 * AT_TILE_K, AT_STAGE_FAST = 2 * AT_TILE_K;   // stage layout: Kh | Vt[2] | Kl
 constexpr float AT_LOG2E = 1.4426950408889634f;
+constexpr float AT_TAU = 12.0f;   // a row's softmax reference follows the running maximum only in jumps of > 2^12 (fp16 P stays < 65504)
 
 // ---- K / V projection (fp32 CUDA cores) -> fp16 operands --------------------------------------------
 // rows: B*Pk_pad keys (rows >= Pk of an image are zero).  Khl: [2][B*Pk_pad][64]; Vt: [B][64][Pk_pad].
@@ -157,7 +160,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, q0 = blockIdx.x * (AT_QT * AT_BQ);
   const int T = p.ntiles;
-  const int nA0 = (T + 1) >> 1;                          // uses of S buffer 0 during pass A (phase offset for pass B)
 
   if (warp == 8 && lane == 0) { tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); }
   if (warp == 9) {
@@ -166,7 +168,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       for (int t = 0; t < AT_QT; ++t) {
         mbar_init(x_full + 8 * t, 4); mbar_init(xq_done + 8 * t, 1); mbar_init(q_ready + 8 * t, 4);
         mbar_init(p_full + 8 * t, 4); mbar_init(pv_done + 8 * t, 1);
-        for (int sb = 0; sb < 2; ++sb) { mbar_init(s_full + 8 * (2 * t + sb), 1); mbar_init(s_empty + 8 * (2 * t + sb), 4); }
+        for (int sb = 0; sb < 2; ++sb) { mbar_init(s_full + 8 * (2 * t + sb), 1); mbar_init(s_empty + 8 * (2 * t + sb), 4); }   // (three of the four are used)
         mbar_init(xin_full + 8 * t, 1);
       }
       for (int s = 0; s < 3; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
@@ -182,8 +184,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
-  // TMEM columns: S of q-tile t at 128 t (128 keys) ; O of q-tile t at 256 + 64 t
-  const uint32_t tO = tmem + 256;
+  // TMEM columns: three rotating S buffers (128 keys each) at 0 / 128 / 256 (the projection of q-tile t lands in buffer t);
+  // O of q-tile t at 384 + 64 t
+  const uint32_t tO = tmem + 384;
 
   if (warp == 8) {
     // ================= TMA producer =================
@@ -200,19 +203,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       tma_load_2d(wstage + AT_TILE_W, &tm_w, 0, AT_DP, w_full);   // theta' lo
     }
     __syncwarp();
-    for (int u = 0, s = 0, ph = 1; u < 2 * T; ++u) {             // ring slot / EMPTY parity tracked incrementally (no division)
-      const int j = u < T ? u : u - T;
-      if (u == NST - 1) { mbar_wait(xq_done, 0); mbar_wait(xq_done + 8, 0); }
+    for (int j = 0, s = 0, ph = 1; j < T; ++j) {                // ring slot / EMPTY parity tracked incrementally (no division)
+      if (j == NST - 1) { mbar_wait(xq_done, 0); mbar_wait(xq_done + 8, 0); }     // theta' (last ring stage) has been consumed
       mbar_wait(kv_empty + 8 * s, ph);
       if (elect_one()) {
         const uint32_t dst = sKV + s * STAGE;
-        mbar_arrive_expect_tx(kv_full + 8 * s, u < T ? AT_TILE_K : STAGE);
+        mbar_arrive_expect_tx(kv_full + 8 * s, STAGE);
         tma_load_2d(dst, &tm_k, 0, b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
-        if (u >= T) {
-          tma_load_2d(dst + AT_TILE_K, &tm_v, j * AT_BK, b * AT_DP, kv_full + 8 * s);
-          tma_load_2d(dst + AT_TILE_K + AT_TILE_W, &tm_v, j * AT_BK + 64, b * AT_DP, kv_full + 8 * s);
-          if (p.split) tma_load_2d(dst + 2 * AT_TILE_K, &tm_k, 0, (int)p.k_rows + b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
-        }
+        tma_load_2d(dst + AT_TILE_K, &tm_v, j * AT_BK, b * AT_DP, kv_full + 8 * s);
+        tma_load_2d(dst + AT_TILE_K + AT_TILE_W, &tm_v, j * AT_BK + 64, b * AT_DP, kv_full + 8 * s);
+        if (p.split) tma_load_2d(dst + 2 * AT_TILE_K, &tm_k, 0, (int)p.k_rows + b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
       }
       __syncwarp();
       if (++s == NST) { s = 0; ph ^= 1; }
@@ -241,77 +241,57 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       }
       __syncwarp();
     }
-    // ---- pass A: S = Qh Kh^T only — good to ~|q||k| 2^-10, enough for a softmax reference maximum
-    int s = 0, ph = 0, s_prev = 0;                               // ring slot / FULL parity of the key tile being consumed
-    for (int u = 0; u < T; ++u) {
-      mbar_wait(kv_full + 8 * s, ph);
-      for (int t = 0; t < AT_QT; ++t) {
-        if (u == 0) mbar_wait(q_ready + 8 * t, 0);
-        // pass A ping-pongs S_t between its own columns and the (still unused) O / spare columns: u even -> 128 t,
-        // u odd -> 256 + 128 t; a buffer is free once the softmax warps have read tile u-2
-        mbar_wait(s_empty + 8 * (2 * t + (u & 1)), ((u >> 1) & 1) ^ 1);
+    // ---- key loop over "uses" u = 2 j + t (key tile j, q-tile t): logits S_u (4 / 12 UMMAs) into S buffer u % 3, and — two uses
+    // later, once the softmax warps have turned S_u into P — O_t += P V (8 UMMAs).  Three S buffers rotate between the two
+    // q-tiles, so the logits of a q-tile's NEXT key tile are already in TMEM when its softmax warps finish the current one
+    // (with one buffer per q-tile they idled for an MMA round trip per tile).
+    int sq = 0, phq = 0, sp = 0;                                 // ring slot / FULL parity on the QK side; ring slot on the PV side
+    int buf = 0, bpar = 0;                                       // S buffer u % 3 and parity of its (u / 3)-th use
+    for (int u = 0; u < 2 * T + 2; ++u) {
+      if (u < 2 * T) {
+        const int t = u & 1, j = u >> 1;
+        if (t == 0) { mbar_wait(kv_full + 8 * sq, phq); if (lane == 0) AT_DBG(j * 16 + 0); }
+        if (j == 0) mbar_wait(q_ready + 8 * t, 0);
+        mbar_wait(s_empty + 8 * buf, bpar ^ 1);
         tc_fence_after();
+        if (lane == 0) AT_DBG(j * 16 + 1 + t);
         if (elect_one()) {
-          const uint64_t kh = dKV + (uint64_t)((s * STAGE) >> 4), qh = dQ + (uint64_t)((2 * t * AT_TILE_Q) >> 4);
-          const uint32_t d = tmem + t * AT_BK + (u & 1) * 256;
+          const uint64_t kh = dKV + (uint64_t)((sq * STAGE) >> 4), kl = kh + (uint64_t)((2 * AT_TILE_K) >> 4);
+          const uint64_t qh = dQ + (uint64_t)((2 * t * AT_TILE_Q) >> 4), ql = qh + (uint64_t)(AT_TILE_Q >> 4);
+          const uint32_t d = tmem + buf * AT_BK;
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(d, qh + 2 * k, kh + 2 * k, idesc_s, k ? 1u : 0u);
-          umma_commit(s_full + 8 * (2 * t + (u & 1)));
-          if (t == AT_QT - 1) umma_commit(kv_empty + 8 * s);
+          if (p.split) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d, ql + 2 * k, kh + 2 * k, idesc_s, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d, qh + 2 * k, kl + 2 * k, idesc_s, 1u);
+          }
+          umma_commit(s_full + 8 * buf);
         }
         __syncwarp();
+        if (t == AT_QT - 1 && ++sq == NST) { sq = 0; phq ^= 1; }
+        if (++buf == 3) { buf = 0; bpar ^= 1; }
       }
-      if (++s == NST) { s = 0; ph ^= 1; }
-    }
-    // ---- pass B: exact logits (12 UMMAs per q-tile and key tile) and O += P V (8 UMMAs)
-    for (int j = 0; j <= T; ++j) {
-      const int s_cur = s;
-      if (j < T) {
-        mbar_wait(kv_full + 8 * s, ph);
-        if (lane == 0) AT_DBG(j * 16 + 0);
-        for (int t = 0; t < AT_QT; ++t) {
-          mbar_wait(s_empty + 8 * (2 * t), ((nA0 + j) & 1) ^ 1);       // pass B uses S buffer 0 only (buffer 1 became O)
-          tc_fence_after();
-          if (lane == 0) AT_DBG(j * 16 + 1 + t);
-          if (elect_one()) {
-            const uint64_t kh = dKV + (uint64_t)((s * STAGE) >> 4), kl = kh + (uint64_t)((2 * AT_TILE_K) >> 4);
-            const uint64_t qh = dQ + (uint64_t)((2 * t * AT_TILE_Q) >> 4), ql = qh + (uint64_t)(AT_TILE_Q >> 4);
-            const uint32_t d = tmem + t * AT_BK;
+      if (u >= 2) {
+        const int uu = u - 2, t = uu & 1, jj = uu >> 1;
+        if (lane == 0 && t == 0) AT_DBG(jj * 16 + 3);
+        mbar_wait(p_full + 8 * t, jj & 1);
+        tc_fence_after();
+        if (lane == 0) AT_DBG(jj * 16 + 4 + t);
+        if (elect_one()) {
+          const uint64_t vt = dKV + (uint64_t)((sp * STAGE + AT_TILE_K) >> 4), pp = dP + (uint64_t)((t * 2 * AT_TILE_Q) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d, qh + 2 * k, kh + 2 * k, idesc_s, k ? 1u : 0u);
-            if (p.split) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d, ql + 2 * k, kh + 2 * k, idesc_s, 1u);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d, qh + 2 * k, kl + 2 * k, idesc_s, 1u);
-            }
-            umma_commit(s_full + 8 * (2 * t));
-          }
-          __syncwarp();
+          for (int k = 0; k < 8; ++k)      // keys 0-63: P / Vt block 0, keys 64-127: block 1
+            umma_f16(tO + t * AT_DP, pp + (uint64_t)((k >> 2) * (AT_TILE_Q >> 4)) + 2 * (k & 3),
+                     vt + (uint64_t)((k >> 2) * (AT_TILE_W >> 4)) + 2 * (k & 3), idesc_d, (jj | k) ? 1u : 0u);
+          umma_commit(pv_done + 8 * t);
+          if (t == AT_QT - 1) umma_commit(kv_empty + 8 * sp);
         }
+        __syncwarp();
+        if (lane == 0 && t == 1) AT_DBG(jj * 16 + 6);
+        if (t == AT_QT - 1 && ++sp == NST) sp = 0;
       }
-      if (j < T && ++s == NST) { s = 0; ph ^= 1; }
-      if (j > 0) {
-        const int jj = j - 1, s = s_prev;
-        for (int t = 0; t < AT_QT; ++t) {
-          if (lane == 0 && t == 0) AT_DBG(jj * 16 + 3);
-          mbar_wait(p_full + 8 * t, jj & 1);
-          tc_fence_after();
-          if (lane == 0) AT_DBG(jj * 16 + 4 + t);
-          if (elect_one()) {
-            const uint64_t vt = dKV + (uint64_t)((s * STAGE + AT_TILE_K) >> 4), pp = dP + (uint64_t)((t * 2 * AT_TILE_Q) >> 4);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)      // keys 0-63: P / Vt block 0, keys 64-127: block 1
-              umma_f16(tO + t * AT_DP, pp + (uint64_t)((k >> 2) * (AT_TILE_Q >> 4)) + 2 * (k & 3),
-                       vt + (uint64_t)((k >> 2) * (AT_TILE_W >> 4)) + 2 * (k & 3), idesc_d, (jj | k) ? 1u : 0u);
-            umma_commit(pv_done + 8 * t);
-            if (t == AT_QT - 1) umma_commit(kv_empty + 8 * s);
-          }
-          __syncwarp();
-          if (lane == 0 && t == 1) AT_DBG(jj * 16 + 6);
-        }
-      }
-      s_prev = s_cur;
     }
   } else {
     // ================= softmax warps (4 per q-tile) + epilogue =================
@@ -353,52 +333,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     }
 
     if (warp == 0 && lane == 0) AT_DBG(504);
-    // ---- pass A: approximate row maximum over all keys
-    float ref = -INFINITY;
-    for (int u = 0; u < T; ++u) {
-      const int sb = u & 1;
-      mbar_wait(s_full + 8 * (2 * t + sb), (u >> 1) & 1);
-      tc_fence_after();
-      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains for ILP
-#pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {
-        tmem_ld64(tS + sb * 256 + hb * 64, v);
-        if (hb == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_empty + 8 * (2 * t + sb));
-        }
-        const int nvalid = p.Pk - u * AT_BK - hb * 64;         // keys of this half that exist
-        if (nvalid < 64) {                                     // ragged tail only
-#pragma unroll
-          for (int c = 0; c < 64; ++c)
-            if (c >= nvalid) v[c] = 0xff800000u;               // -inf
-        }
-#pragma unroll
-        for (int c = 0; c < 64; c += 4) {
-          m4[0] = fmaxf(m4[0], __uint_as_float(v[c])); m4[1] = fmaxf(m4[1], __uint_as_float(v[c + 1]));
-          m4[2] = fmaxf(m4[2], __uint_as_float(v[c + 2])); m4[3] = fmaxf(m4[3], __uint_as_float(v[c + 3]));
-        }
-      }
-      ref = fmaxf(ref, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-    }
-    if (warp == 0 && lane == 0) AT_DBG(505);
-    // ---- pass B: p = exp(s - ref) against the fixed reference
-    const float ref2 = ref * AT_LOG2E;
+    // ---- key loop: p = 2^(s log2e - ref2); ref2 (per row, log2 units) trails the running maximum in jumps of > AT_TAU
+    float ref2 = 0.f;
+    const uint32_t tOrow = tO + lane_sel + t * AT_DP;
     for (int j = 0; j < T; ++j) {
-      const int u = T + j;
       if (warp == 0 && lane == 0) AT_DBG(j * 16 + 7);
-      mbar_wait(s_full + 8 * (2 * t), (nA0 + j) & 1);
+      const int u = 2 * j + t, ub = u % 3;                     // this q-tile's use of S buffer u % 3 (see the MMA issuer)
+      const uint32_t tSu = tmem + lane_sel + ub * AT_BK;
+      mbar_wait(s_full + 8 * ub, (u / 3) & 1);
       tc_fence_after();
       if (warp == 0 && lane == 0) AT_DBG(j * 16 + 8);
 #pragma unroll
       for (int hb = 0; hb < 2; ++hb) {
-        tmem_ld64(tS + hb * 64, v);
+        tmem_ld64(tSu + hb * 64, v);
         if (warp == 0 && lane == 0) AT_DBG(j * 16 + 9 + 3 * hb);
         if (hb == 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(s_empty + 8 * (2 * t));
+          if (lane == 0) mbar_arrive(s_empty + 8 * ub);
         }
         const int nvalid = p.Pk - j * AT_BK - hb * 64;
         if (nvalid < 64) {
@@ -406,15 +358,61 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
           for (int c = 0; c < 64; ++c)
             if (c >= nvalid) v[c] = 0xff800000u;               // -inf -> ex2 gives exactly 0
         }
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains for ILP
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
+        for (int c = 0; c < 64; c += 8) {
+          m4[0] = fmaxf(m4[0], fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 1])));
+          m4[1] = fmaxf(m4[1], fmaxf(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])));
+          m4[2] = fmaxf(m4[2], fmaxf(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])));
+          m4[3] = fmaxf(m4[3], fmaxf(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7])));
+        }
+        const float m2 = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * AT_LOG2E;
+        if (hb == 0 && j > 0) mbar_wait(pv_done + 8 * t, (j - 1) & 1);   // PV_{j-1} has finished reading P_t (and writing O_t)
+        if (j == 0 && hb == 0) {
+          ref2 = m2;                                           // first half tile: the reference starts at its maximum
+        } else {
+          const bool jump = m2 > ref2 + AT_TAU;
+          if (__any_sync(0xffffffffu, jump)) {
+            // rare: move the reference of the rows that jumped and rescale what they have accumulated under the old one
+            const float nref = jump ? m2 : ref2;
+            const float f = fast_exp2(ref2 - nref);            // 1 for rows that stay
+            ref2 = nref;
+            if (j > 0) {                                       // O_t / l (TMEM): all MMAs that wrote it are complete (pv_done above)
+              uint32_t o[32];
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                tmem_ld32(tOrow + hh * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+                tmem_st32(tOrow + hh * 32, o);
+              }
+              tmem_st_wait();
+            }
+            if (hb == 1) {                                     // the first half of this tile's P is already staged: scale it in place
+              const __half2 f2 = __float2half2_rn(f);
+              const uint32_t prow0 = sPt + r * 128;
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch) {
+                uint32_t w0, w1, w2, w3;
+                const uint32_t a = prow0 + ((ch ^ (r & 7)) << 4);
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a) : "memory");
+                __half2 h0 = __hmul2(*reinterpret_cast<__half2*>(&w0), f2), h1 = __hmul2(*reinterpret_cast<__half2*>(&w1), f2);
+                __half2 h2 = __hmul2(*reinterpret_cast<__half2*>(&w2), f2), h3 = __hmul2(*reinterpret_cast<__half2*>(&w3), f2);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
+                             "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {       // (ex2.approx.f16x2 is no faster: it issues one MUFU.EX2.F16 per half — checked in SASS)
           const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * e]), AT_LOG2E, -ref2));
           const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * e + 1]), AT_LOG2E, -ref2));
           __half2 hh = __floats2half2_rn(p0, p1);
           v[e] = *reinterpret_cast<uint32_t*>(&hh);
         }
         if (warp == 0 && lane == 0) AT_DBG(j * 16 + 10 + 3 * hb);
-        if (hb == 0 && j > 0) mbar_wait(pv_done + 8 * t, (j - 1) & 1);   // PV_{j-1} has finished reading P_t
         if (warp == 0 && lane == 0) AT_DBG(j * 16 + 11 + 3 * hb);
         const uint32_t prow = sPt + hb * AT_TILE_Q + r * 128;
 #pragma unroll
@@ -423,6 +421,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
                        "r"(v[4 * ch + 1]), "r"(v[4 * ch + 2]), "r"(v[4 * ch + 3]) : "memory");
       }
       fence_proxy_async();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full + 8 * t);
     }
@@ -477,6 +476,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         z[d] = x[d] + (__uint_as_float(v[d]) * inv_l) * s_wz[d];
         nrm = fmaf(z[d], z[d], nrm);
       }
+      if (warp == 0 && lane == 0) AT_DBG(510);
       const float inv_n = 1.0f / sqrtf(nrm);
 #pragma unroll
       for (int d = 0; d < D; ++d) z[d] *= inv_n;
@@ -513,6 +513,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
 #pragma unroll
           for (int c = 0; c < NN; ++c) nov[c] = fmaf(s_obj[c * D + d], z[d], nov[c]);
       }
+      if (warp == 0 && lane == 0) AT_DBG(511);
 #pragma unroll
       for (int c = 0; c < NN; ++c) nov[c] *= p.scale;
       if (p.apply_softmax) {
@@ -533,7 +534,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
 #pragma unroll
       for (int c = 0; c < NN; ++c) orow_s[off + c] = nov[c];
     }
+    if (warp == 0 && lane == 0) AT_DBG(512);
     asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
+    if (warp == 0 && lane == 0) AT_DBG(513);
     {   // the q-tile's output rows are one contiguous block: coalesced copy
       const int rows = min(AT_BQ, p.P - (q0 + t * AT_BQ));
       float* oblk = p.out + ((size_t)b * p.P + q0 + t * AT_BQ) * n_out;

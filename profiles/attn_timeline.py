@@ -13,8 +13,8 @@ buf = torch.zeros(1024, dtype=torch.int64, device='cuda')
 _lib.lib().ctx_debug_set_attention_timeline(buf.data_ptr())
 net(x); torch.cuda.synchronize()
 _lib.lib().ctx_debug_set_attention_timeline(None)
-ph = buf.cpu()[500:510]
-print('phases (start, xload, xstore, xq_done, q_ready/passA, passB, passB end, epi weights, O loaded, end):', [int(x - ph[0]) for x in ph])
+ph = buf.cpu()[500:514]
+print('phases (start, xload, xstore, xq_done, q_ready/passA, passB, passB end, epi weights, O loaded, end, z done, classifier done, softmax done, after barrier):', [int(x - ph[0]) for x in ph])
 t = buf.cpu()[:512].view(32, 16)
 names = ['mma:kv_full', 'mma:s_emptyA', 'mma:s_emptyB(QK_A issued)', 'mma:QK_B issued', 'mma:p_fullA', 'mma:p_fullB(PV_A issued)', 'mma:PV_B issued',
          'smA:top', 'smA:s_full', 'smA:ld0', 'smA:exp0', 'smA:pv_done', 'smA:ld1', 'smA:exp1', 'smA:st1']
