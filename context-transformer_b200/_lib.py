@@ -94,6 +94,7 @@ SIGNATURES = {
     'ctx_maxpool2d_nhwc': (_I, [C.POINTER(CtxPoolParams), _P]),
     'ctx_nchw_to_nhwc': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'ctx_base_transform': (_I, [_P, _P, _I, _I, _I, C.POINTER(C.c_float), _P]),
+    'ctx_base_transform_resize': (_I, [_P, _I, _I, _P, _I, C.POINTER(C.c_float), _P]),
     'ctx_nchw_to_patch27': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'ctx_prog_add_nchw_to_patch27': (_I, [_P, _P, _P, _I, _I, _I, _I]),
     'ctx_attention_workspace_bytes': (_SZ, [C.POINTER(CtxAttnParams)]),

@@ -270,6 +270,50 @@ u8hwc_to_f32chw_kernel(const uint8_t* __restrict__ img, float* __restrict__ out,
   }
 }
 
+// BaseTransform WITH the resize (data/data_augment.py:257-261): cv2.resize(img, (S, S), INTER_LINEAR) on the 8-bit image,
+// then float - mean, HWC -> CHW.  OpenCV's 8-bit bilinear resize is fixed-point (imgproc/resize.cpp: resizeGeneric_ with
+// HResizeLinear<uchar,int,short,2048> and VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>; the IPP variant is not
+// used for 8-bit linear unless IPP "not exact" mode is switched on), and it is restated here operation for operation:
+//   scale = 1 / (dst / src) in double;  f = (float)((d + 0.5) * scale - 0.5);  s = floor(f);  f -= s  (float)
+//   columns: s < 0 -> f = 0, s = 0;  s >= src_w - 1 -> f = 0, s = src_w - 1;  rows: s and s + 1 clipped to the image
+//   taps a1 = cvRound(f * 2048), a0 = cvRound((1.f - f) * 2048)  (round half to even), horizontal pass in int32,
+//   vertical pass  (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2.
+// No fused multiply-adds in the coordinate arithmetic (x86 builds of OpenCV do not contract).  One thread per output pixel.
+__device__ __forceinline__ void cv_linear_tap(int d, double scale, int src, bool clamp_edges, int& s, int& a0, int& a1) {
+  float f = (float)__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
+  s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  if (clamp_edges) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= src - 1) { f = 0.f; s = src - 1; }
+  }
+  a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+__global__ void __launch_bounds__(256)
+resize_base_transform_kernel(const uint8_t* __restrict__ img, int sh, int sw, float* __restrict__ out, int S, float m0, float m1, float m2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * S) return;
+  const int dy = i / S, dx = i - dy * S;
+  const double scale_x = 1.0 / ((double)S / (double)sw), scale_y = 1.0 / ((double)S / (double)sh);
+  int sx, a0, a1, sy, b0, b1;
+  cv_linear_tap(dx, scale_x, sw, true, sx, a0, a1);
+  cv_linear_tap(dy, scale_y, sh, false, sy, b0, b1);
+  const int y0 = min(max(sy, 0), sh - 1), y1 = min(max(sy + 1, 0), sh - 1);
+  const bool one_tap = sx + 1 >= sw;                          // dx >= xmax: D = S[sx] * 2048
+  const uint8_t* p00 = img + ((long long)y0 * sw + sx) * 3;
+  const uint8_t* p10 = img + ((long long)y1 * sw + sx) * 3;
+  const float mean[3] = {m0, m1, m2};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int r0 = one_tap ? (int)p00[c] * 2048 : (int)p00[c] * a0 + (int)p00[c + 3] * a1;
+    const int r1 = one_tap ? (int)p10[c] * 2048 : (int)p10[c] * a0 + (int)p10[c + 3] * a1;
+    const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+    out[(long long)c * S * S + i] = (float)(v & 255) - mean[c];
+  }
+}
+
 // softmax over the last dimension (output activation, RFB_Net_vgg.py:279-285); one thread per row
 __global__ void __launch_bounds__(256)
 softmax_lastdim_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int cols) {
@@ -418,6 +462,13 @@ int base_transform_launch(const unsigned char* img, float* out, int N, int H, in
   return CTX_OK;
 }
 
+int resize_base_transform_launch(const unsigned char* img, int sh, int sw, float* out, int S, const float* means3, cudaStream_t st) {
+  CTX_REQUIRE(img && out && means3 && sh > 0 && sw > 0 && S > 0, "base_transform_resize: bad arguments");
+  resize_base_transform_kernel<<<cdiv((long long)S * S, 256), 256, 0, st>>>(img, sh, sw, out, S, means3[0], means3[1], means3[2]);
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
 int patch27_launch(const float* in, void* out, int N, int H, int W, int dtype, cudaStream_t st) {
   CTX_REQUIRE(in && out && N > 0 && H > 0 && W > 0, "patch27: bad arguments");
   CTX_REQUIRE(dtype == CTX_BF16 || dtype == CTX_F16, "patch27: 16-bit output only");
@@ -444,6 +495,9 @@ extern "C" int ctx_conv2d_simt(const CtxConvParams* p, void* stream) { return ct
 extern "C" int ctx_maxpool2d_nhwc(const CtxPoolParams* p, void* stream) { return ctx::maxpool_launch(p, (cudaStream_t)stream); }
 extern "C" int ctx_nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, int out_dtype, void* stream) {
   return ctx::nchw_to_nhwc_launch(in, out, N, C, H, W, out_dtype, (cudaStream_t)stream);
+}
+extern "C" int ctx_base_transform_resize(const unsigned char* img_hwc, int src_h, int src_w, float* out_chw, int size, const float* means3, void* stream) {
+  return ctx::resize_base_transform_launch(img_hwc, src_h, src_w, out_chw, size, means3, (cudaStream_t)stream);
 }
 extern "C" int ctx_base_transform(const unsigned char* img_hwc, float* out_chw, int N, int H, int W, const float* means3, void* stream) {
   return ctx::base_transform_launch(img_hwc, out_chw, N, H, W, means3, (cudaStream_t)stream);

@@ -169,28 +169,96 @@ class DetectionCollector(object):
             pickle.dump(self.all_boxes, f, pickle.HIGHEST_PROTOCOL)
         return det_file
 
+    # ---- the datasets' result files, written straight from the collected records --------------------------------------
+    def write_voc_results(self, image_ids, class_names, filedir, filename='comp4_det_test_{:s}.txt'):
+        """The per-class text files of ``VOCDetection._write_voc_results_file`` (data/voc0712.py:360-376): one line
+        ``<image id> <score .3f> <x1+1 .1f> <y1+1 .1f> <x2+1 .1f> <y2+1 .1f>`` per detection, images in dataset order.
+        ``image_ids``: the dataset's ``ids`` (``(root, id)`` pairs as upstream, or plain id strings); ``class_names``:
+        ``VOC_CLASSES[split][:16 or 21]`` including ``'__background__'``.  Returns the list of files written."""
+        import os
+        os.makedirs(filedir, exist_ok=True)
+        if len(image_ids) != self.num_images:
+            raise ValueError('%d image ids for %d collected images' % (len(image_ids), self.num_images))
+        written = []
+        for cls_ind, cls in enumerate(class_names):
+            if cls == '__background__':
+                continue
+            path = os.path.join(filedir, filename.format(cls))
+            with open(path, 'wt') as f:
+                for im_ind, index in enumerate(image_ids):
+                    index = index[1] if isinstance(index, (tuple, list)) else index
+                    dets = self.all_boxes[cls_ind][im_ind]
+                    for k in range(len(dets)):
+                        f.write('{:s} {:.3f} {:.1f} {:.1f} {:.1f} {:.1f}\n'.format(index, dets[k, -1], dets[k, 0] + 1, dets[k, 1] + 1,
+                                                                                 dets[k, 2] + 1, dets[k, 3] + 1))
+            written.append(path)
+        return written
+
+    def coco_results(self, img_ids, class_names, class_to_coco_cat_id):
+        """The result list of ``COCODetection._write_coco_results_file`` (data/coco.py:242-274): per class (1-based, in
+        ``class_names`` order) and image, ``{'image_id', 'category_id', 'bbox': [x, y, w + 1, h + 1], 'score'}`` in float64."""
+        import numpy as np
+        if len(img_ids) != self.num_images:
+            raise ValueError('%d image ids for %d collected images' % (len(img_ids), self.num_images))
+        results = []
+        for cls_ind, cls in enumerate(class_names, 1):
+            cat_id = class_to_coco_cat_id[cls]
+            for im_ind, index in enumerate(img_ids):
+                dets = np.asarray(self.all_boxes[cls_ind][im_ind], dtype=np.float64)
+                if dets.size == 0:
+                    continue
+                xs, ys = dets[:, 0], dets[:, 1]
+                ws, hs = dets[:, 2] - xs + 1, dets[:, 3] - ys + 1
+                results.extend([{'image_id': index, 'category_id': cat_id, 'bbox': [xs[k], ys[k], ws[k], hs[k]], 'score': dets[k, -1]}
+                                for k in range(dets.shape[0])])
+        return results
+
+    def write_coco_results(self, res_file, img_ids, class_names, class_to_coco_cat_id):
+        import json
+        with open(res_file, 'w') as fid:
+            json.dump(self.coco_results(img_ids, class_names, class_to_coco_cat_id), fid)
+            fid.flush()
+        return res_file
+
 
 class BaseTransform(object):
-    """Mirror of reference ``data/data_augment.py:224-266`` for the inference path: ``transform(img)`` -> fp32 ``[3,S,S]``.
-    The mean subtraction and the HWC -> CHW change run on the GPU (``ctx_base_transform``); images must already have the
-    network's size — the reference's ``cv2.resize`` (a fixed-point bilinear kernel) is not reimplemented because it cannot be
-    pinned without cv2 in the build image, so other sizes raise instead of silently differing.  Batches:
-    ``transform.batch(imgs_u8[B,S,S,3])`` -> ``[B,3,S,S]`` on the device; or pass the uint8 batch straight to ``net(...)``."""
+    """Mirror of reference ``data/data_augment.py:224-266`` for the inference path: ``transform(img)`` -> fp32 ``[3,S,S]``
+    on the device.  The whole transform runs on the GPU: the 8-bit bilinear resize (``cv2.resize(.., INTER_LINEAR)``: OpenCV's
+    fixed-point kernel restated operation for operation in ``ctx_base_transform_resize``), the mean subtraction and the
+    HWC -> CHW change; a uint8 image crosses PCIe instead of an fp32 one.  Batches of images that already have the network's
+    size: ``transform.batch(imgs_u8[B,S,S,3])`` -> ``[B,3,S,S]``, or pass the uint8 batch straight to ``net(...)``; lists of
+    images of any sizes: ``transform.batch([img0, img1, ...])``."""
 
     def __init__(self, resize, rgb_means, swap=(2, 0, 1), device='cuda'):
         if tuple(swap) != (2, 0, 1):
             raise ValueError('BaseTransform: only the reference swap (2, 0, 1) is supported')
         self.resize, self.means, self.swap, self.device = int(resize), tuple(float(m) for m in rgb_means), tuple(swap), device
 
+    def _one(self, img, out):
+        import ctypes as C
+        import torch
+        t = torch.as_tensor(img)
+        if t.dtype != torch.uint8 or t.dim() != 3 or t.size(2) != 3:
+            raise ValueError('BaseTransform expects a uint8 [H,W,3] image (cv2.imread layout)')
+        t = _lib.require_cuda(t.to(self.device, non_blocking=True).contiguous(), 'img')
+        means = (C.c_float * 3)(*self.means)
+        with torch.cuda.device(t.device):
+            _lib.check(_lib.lib().ctx_base_transform_resize(t.data_ptr(), t.size(0), t.size(1), out.data_ptr(), self.resize, means,
+                                                            _lib.current_stream_ptr()), 'ctx_base_transform_resize')
+
     def batch(self, imgs):
         import ctypes as C
         import torch
+        if isinstance(imgs, (list, tuple)):                       # images of any sizes: one resize launch each
+            out = torch.empty(len(imgs), 3, self.resize, self.resize, device=self.device)
+            for i, im in enumerate(imgs):
+                self._one(im, out[i])
+            return out
         t = torch.as_tensor(imgs)
         if t.dtype != torch.uint8 or t.dim() != 4 or t.size(3) != 3:
-            raise ValueError('BaseTransform.batch expects uint8 [B,H,W,3]')
+            raise ValueError('BaseTransform.batch expects uint8 [B,H,W,3] or a list of uint8 [H,W,3] images')
         if t.size(1) != self.resize or t.size(2) != self.resize:
-            raise NotImplementedError('BaseTransform: image size %dx%d != %d — resize on the host (cv2.resize) first; the on-device '
-                                      'path covers mean subtraction and layout only' % (t.size(1), t.size(2), self.resize))
+            return self.batch([t[i] for i in range(t.size(0))])
         t = t.to(self.device).contiguous()
         _lib.require_cuda(t, 'imgs')
         out = torch.empty(t.size(0), 3, self.resize, self.resize, device=t.device)
@@ -204,4 +272,6 @@ class BaseTransform(object):
         import torch
         if target is not None:
             raise NotImplementedError('BaseTransform with targets is the training-time path (host side, data_augment.py:249-256)')
-        return self.batch(torch.as_tensor(img).unsqueeze(0))[0]
+        out = torch.empty(3, self.resize, self.resize, device=self.device)
+        self._one(img, out)
+        return out

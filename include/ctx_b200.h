@@ -158,9 +158,12 @@ int ctx_maxpool2d_nhwc(const CtxPoolParams* p, void* stream);
 int ctx_nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, int out_dtype, void* stream);
 /* BaseTransform (data/data_augment.py:224-266) for images that already have the network's size (cv2.resize to the same size
  * is a copy): img[N,H,W,3] uint8 (cv2 channel order) -> x[N,3,H,W] fp32 = float(img) - means[c].  means3 is a HOST pointer to
- * three floats ((104,117,123), test.py:87).  The bilinear resize itself is not reimplemented (cv2's fixed-point kernel
- * cannot be pinned without cv2 in the build image). */
+ * three floats ((104,117,123), test.py:87).  Other sizes: ctx_base_transform_resize. */
 int ctx_base_transform(const unsigned char* img_hwc, float* out_chw, int N, int H, int W, const float* means3, void* stream);
+/* BaseTransform with the resize (data/data_augment.py:257-261): img[src_h,src_w,3] uint8 -> cv2.resize(.., (size, size),
+ * INTER_LINEAR) -> float - means -> out[3,size,size].  OpenCV's 8-bit bilinear kernel (fixed point, 11-bit coefficients,
+ * imgproc/resize.cpp) restated operation for operation; one image per call (test.py:122-126 transforms one image at a time). */
+int ctx_base_transform_resize(const unsigned char* img_hwc, int src_h, int src_w, float* out_chw, int size, const float* means3, void* stream);
 /* x[N,3,H,W] fp32 -> 3x3/pad-1 patches [N,H,W,64] 16-bit (27 values, channel = (ky*3+kx)*3+ci, + 37 zeros): turns the
  * Cin = 3 stem conv (vgg() base.0, RFB_Net_vgg.py:331) into a K = 64 tensor-core GEMM */
 int ctx_nchw_to_patch27(const float* in, void* out, int N, int H, int W, int out_dtype, void* stream);

@@ -89,6 +89,116 @@ def gen_autocast(r):
     print('autocast bf16 vs fp32 (reference, seeded state): max', d['max_abs'], 'mean', d['mean_abs'], 'argmax agreement', d['argmax_agreement'])
 
 
+RESIZE_CASES = [((375, 500), 300, 0), ((500, 333), 300, 1), ((281, 500), 512, 2), ((64, 48), 300, 3), ((600, 600), 300, 4), ((300, 300), 300, 5),
+                ((1, 7), 300, 6), ((720, 1280), 512, 7)]          # (source H, W), network size, seed
+
+
+def resize_image(hw, seed):
+    """Seeded uint8 test image: smooth gradients + noise (exercises both the interpolation and the rounding)."""
+    g = np.random.default_rng(1000 + seed)
+    h, w = hw
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([(xx * 255.0 / max(w - 1, 1)), (yy * 255.0 / max(h - 1, 1)), ((xx + yy) % 256)], -1)
+    return np.clip(base + g.normal(0, 40, (h, w, 3)), 0, 255).astype(np.uint8)
+
+
+def gen_resize(r):
+    """The reference's own BaseTransform (data/data_augment.py:224-266; it calls cv2.resize(.., INTER_LINEAR)) on seeded images."""
+    import importlib.util
+    saved = list(sys.path)
+    sys.path.insert(0, ref_import.REF_ROOT)
+    try:
+        spec = importlib.util.spec_from_file_location('ref_data_augment', os.path.join(ref_import.REF_ROOT, 'data', 'data_augment.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path[:] = saved
+    out = {}
+    for hw, size, seed in RESIZE_CASES:
+        t = mod.BaseTransform(size, (104, 117, 123))(resize_image(hw, seed)).numpy()       # [3, S, S] float32
+        key = '%dx%d_%d' % (hw[0], hw[1], size)
+        out['rows_' + key] = t[:, ::17, :].copy()                                              # every 17th row, all columns
+        out['sum_' + key] = checksum(t)
+    np.savez_compressed(os.path.join(GOLD, 'resize.npz'), **out)
+    print('resize golden:', sorted(k for k in out if k.startswith('sum_')))
+
+
+def _reference_functions(path, names, namespace):
+    """Compile the named function definitions straight out of a reference source file (read at generation time, never
+    stored in this repo) into ``namespace`` — for reference modules that cannot be imported whole here (``data/`` pulls in
+    matplotlib and the compiled COCO mask extension)."""
+    import ast
+    tree = ast.parse(open(path).read())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            mod = ast.Module(body=[node], type_ignores=[])
+            exec(compile(mod, path, 'exec'), namespace)
+    return namespace
+
+
+class _Dets(np.ndarray):
+    """ndarray whose ``== []`` is False instead of a broadcast error: the reference's writers test ``if dets == []`` on
+    arrays (numpy 1.x semantics)."""
+    def __eq__(self, other):
+        if isinstance(other, list):
+            return False
+        return np.ndarray.__eq__(self, other)
+
+
+def writer_inputs(golden_post):
+    """all_boxes[class][image] in the reference's structure, from the post-processing golden (2 images, 21 classes)."""
+    num_images, num_classes = 2, 21
+    all_boxes = [[[] for _ in range(num_images)] for _ in range(num_classes)]
+    for b in range(num_images):
+        rec = golden_post['records_gt_%d' % b]
+        for j in range(1, num_classes):
+            rows = rec[rec[:, 5] == j][:, :5].astype(np.float32)
+            if len(rows):
+                all_boxes[j][b] = rows
+    ids = [('/data/VOCdevkit/VOC2007', '000001'), ('/data/VOCdevkit/VOC2007', '004242')]
+    return all_boxes, ids
+
+
+def gen_writers(r):
+    """VOCDetection._write_voc_results_file (data/voc0712.py:360-376) and COCODetection._coco_results_one_category
+    (data/coco.py:242-259) EXECUTED from the reference's source on the detections of the post-processing golden."""
+    import tempfile
+    import types as _t
+    post = np.load(os.path.join(GOLD, 'post_voc300.npz'), allow_pickle=True)
+    all_boxes, ids = writer_inputs(post)
+    wrapped = [[(b.view(_Dets) if isinstance(b, np.ndarray) else b) for b in cls] for cls in all_boxes]
+    ns = {'os': os, 'np': np, 'print': lambda *a, **k: None}
+    src = open(os.path.join(ref_import.REF_ROOT, 'data', 'voc0712.py')).read()
+    vc = {}
+    exec(src[src.index('VOC_CLASSES = dict()'):src.index('# for making bounding boxes pretty')], vc)
+    ns['VOC_CLASSES'] = vc['VOC_CLASSES']
+    _reference_functions(os.path.join(ref_import.REF_ROOT, 'data', 'voc0712.py'), ('_write_voc_results_file', '_get_voc_results_file_template'), ns)
+    tmp = tempfile.mkdtemp(prefix='ctx_voc_')
+    fake = _t.SimpleNamespace(split=0, phase=2, ids=ids, root=tmp, _year='2007')
+    fake._get_voc_results_file_template = lambda: ns['_get_voc_results_file_template'](fake)
+    ns['_write_voc_results_file'](fake, wrapped)
+    out = {}
+    d = os.path.join(tmp, 'results', 'VOC2007', 'Main')
+    for fn in sorted(os.listdir(d)):
+        out['voc_' + fn] = np.array(open(os.path.join(d, fn)).read())
+    cns = {'np': np}
+    np.float = float                       # removed in numpy 1.24; the reference calls dets.astype(np.float)
+    try:
+        _reference_functions(os.path.join(ref_import.REF_ROOT, 'data', 'coco.py'), ('_coco_results_one_category',), cns)
+        fake_c = _t.SimpleNamespace(img_ids=[139, 285])
+        res = []
+        for cls_ind in range(1, 21):
+            res.extend(cns['_coco_results_one_category'](fake_c, wrapped[cls_ind], 100 + cls_ind))
+    finally:
+        del np.float
+    out['coco_image_id'] = np.array([x['image_id'] for x in res])
+    out['coco_category_id'] = np.array([x['category_id'] for x in res])
+    out['coco_bbox'] = np.array([x['bbox'] for x in res], dtype=np.float64)
+    out['coco_score'] = np.array([x['score'] for x in res], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, 'writers.npz'), **out)
+    print('writers golden: %d VOC files, %d COCO results' % (len([k for k in out if k.startswith('voc_')]), len(res)))
+
+
 def gen_post(r):
     """Detect.forward + the numpy loop of test.py:133-161 with the reference's own NMS routines."""
     priors = r.PriorBox(r.cfg.VOC_300).forward()
@@ -219,7 +329,7 @@ def gen_reweight(r):
 def main():
     os.makedirs(GOLD, exist_ok=True)
     r = ref_import.load()
-    which = sys.argv[1:] or ['priors', 'nms', 'post', 'match', 'net', 'reweight', 'autocast']
+    which = sys.argv[1:] or ['priors', 'nms', 'post', 'match', 'net', 'reweight', 'autocast', 'resize', 'writers']
     if 'priors' in which:
         gen_priors(r)
     if 'nms' in which:
@@ -234,6 +344,10 @@ def main():
         gen_net(r)
     if 'autocast' in which:
         gen_autocast(r)
+    if 'resize' in which:
+        gen_resize(r)
+    if 'writers' in which:
+        gen_writers(r)
 
 
 if __name__ == '__main__':

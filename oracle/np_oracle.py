@@ -357,3 +357,51 @@ def base_transform_same_size(img_u8, means=(104, 117, 123)):
     img = img_u8.astype(F)
     img -= np.asarray(means, F)
     return img.transpose(2, 0, 1)
+
+
+# --------------------------------------------------------------------------------------------
+# BaseTransform with the resize — data/data_augment.py:257-261: cv2.resize(img, (S, S), INTER_LINEAR) on uint8.
+# Restatement of OpenCV's 8-bit bilinear algorithm (modules/imgproc/src/resize.cpp: cv::resize coordinate / coefficient set-up,
+# HResizeLinear<uchar,int,short,INTER_RESIZE_COEF_SCALE = 2048>, VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>).
+# PINNED: bit-exact against cv2.resize (opencv-python-headless 4.13, the build image's) on up- and down-scaling, odd sizes,
+# 1x1 .. 1920x1080 sources (tests/test_oracle_golden.py, live) and against tests/golden/resize.npz, which oracle/gen_golden.py
+# produces by running the REFERENCE's own BaseTransform class (data/data_augment.py:224-266, loaded from /root/reference).
+# --------------------------------------------------------------------------------------------
+def _cv_taps(dst, src, clamp_edges):
+    """(s[dst], a0[dst], a1[dst]) of cv::resize for INTER_LINEAR, fixed point."""
+    scale = 1.0 / (float(dst) / float(src))                       # double: inv_scale = dsize / ssize, scale = 1. / inv_scale
+    d = np.arange(dst, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)              # (float)((dx + 0.5) * scale_x - 0.5)
+    s = np.floor(f).astype(np.int64)                              # cvFloor
+    f = (f - s.astype(np.float32)).astype(np.float32)             # fx -= sx  (float)
+    if clamp_edges:
+        lo = s < 0
+        f[lo], s[lo] = 0.0, 0
+        hi = s >= src - 1
+        f[hi], s[hi] = 0.0, src - 1
+    a0 = np.rint((np.float32(1.0) - f) * np.float32(2048.0)).astype(np.int64)     # saturate_cast<short>(cvRound(..)): half to even
+    a1 = np.rint(f * np.float32(2048.0)).astype(np.int64)
+    return s, a0, a1
+
+
+def cv_resize_linear_u8(img, size):
+    """img [H,W,3] uint8 -> [size,size,3] uint8, cv2.resize(img, (size, size), interpolation=cv2.INTER_LINEAR)."""
+    img = np.asarray(img, dtype=np.uint8)
+    sh, sw = img.shape[:2]
+    sx, a0, a1 = _cv_taps(size, sw, True)
+    sy, b0, b1 = _cv_taps(size, sh, False)
+    src = img.astype(np.int64)
+    one = sx + 1 >= sw                                            # dx >= xmax: D = S[sx] * ONE
+    sx1 = np.minimum(sx + 1, sw - 1)
+    rows = np.where(one[None, :, None], src[:, sx] * 2048, src[:, sx] * a0[None, :, None] + src[:, sx1] * a1[None, :, None])   # [H, size, 3] int
+    y0, y1 = np.clip(sy, 0, sh - 1), np.clip(sy + 1, 0, sh - 1)
+    r0, r1 = rows[y0], rows[y1]
+    v = (((b0[:, None, None] * (r0 >> 4)) >> 16) + ((b1[:, None, None] * (r1 >> 4)) >> 16) + 2) >> 2
+    return (v & 255).astype(np.uint8)
+
+
+def base_transform(img_u8, size, means=(104, 117, 123)):
+    """data_augment.py:257-261: resize -> astype(float32) -> -= means -> transpose(2, 0, 1)."""
+    img = cv_resize_linear_u8(img_u8, size).astype(F)
+    img -= np.asarray(means, F)
+    return img.transpose(2, 0, 1)

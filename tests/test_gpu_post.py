@@ -381,3 +381,22 @@ def test_init_reweight_vs_golden_and_oracle(golden):
     assert np.array_equal(acc.counts.cpu().numpy(), g['counts'])
     with pytest.raises(_lib.CtxError):
         ctx.PrototypeAccumulator(20, 60, 'cpu')
+
+
+def test_base_transform_with_resize_bit_exact(golden):
+    """On-device BaseTransform incl. the cv2-style 8-bit bilinear resize (ctx_base_transform_resize) — bit-exact against the
+    numpy oracle and the golden of the reference's own BaseTransform class, for the mixed image sizes a VOC loop sees."""
+    from oracle.gen_golden import RESIZE_CASES, resize_image
+    g = golden('resize.npz')
+    for hw, size, seed in RESIZE_CASES:
+        img = resize_image(hw, seed)
+        tr = ctx.BaseTransform(size, (104, 117, 123))
+        got = tr(torch.from_numpy(img)).cpu().numpy()
+        key = '%dx%d_%d' % (hw[0], hw[1], size)
+        assert np.array_equal(got, np_oracle.base_transform(img, size)), key
+        assert np.array_equal(got[:, ::17, :], g['rows_' + key]), key
+    # a list of images of different sizes -> one batch for the network
+    imgs = [torch.from_numpy(resize_image(hw, seed)) for hw, size, seed in RESIZE_CASES[:3]]
+    batch = ctx.BaseTransform(300, (104, 117, 123)).batch(imgs).cpu().numpy()
+    for i, (hw, size, seed) in enumerate(RESIZE_CASES[:3]):
+        assert np.array_equal(batch[i], np_oracle.base_transform(resize_image(hw, seed), 300))

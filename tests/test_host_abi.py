@@ -199,3 +199,37 @@ def test_detection_collector_builds_the_reference_result_structure(tmp_path):
     import pytest
     with pytest.raises(IndexError):
         col.add(4, rec, cnt)
+
+
+def test_result_writers_match_the_reference_writers(golden, tmp_path):
+    """f-2: the VOC per-class text files and the COCO result list, written from the gathered [B, K, 6] records through
+    DetectionCollector, against tests/golden/writers.npz — produced by EXECUTING the reference's own writer functions
+    (data/voc0712.py:360-376, data/coco.py:242-259; oracle/gen_golden.py gen_writers) on the same detections."""
+    import json
+    from oracle.gen_golden import writer_inputs
+    g, post = golden('writers.npz'), golden('post_voc300.npz')
+    _, ids = writer_inputs(post)
+    K = 256
+    rec = torch.zeros(2, K, 6)
+    cnt = torch.zeros(2, dtype=torch.int32)
+    for b in range(2):
+        r = torch.from_numpy(post['records_gt_%d' % b])
+        rec[b, :len(r)] = r
+        cnt[b] = len(r)
+    col = ctx.DetectionCollector(num_images=2, num_classes=21).add(0, rec, cnt)
+    voc_classes = ('__background__', 'aeroplane', 'bicycle', 'bird', 'boat', 'bottle', 'bus', 'car', 'cat', 'chair', 'cow', 'diningtable',
+                   'dog', 'horse', 'motorbike', 'person', 'pottedplant', 'sheep', 'sofa', 'train', 'tvmonitor')
+    files = col.write_voc_results(ids, voc_classes, str(tmp_path / 'Main'))
+    assert len(files) == 20
+    n_lines = 0
+    for f in files:
+        text = open(f).read()
+        assert text == str(g['voc_' + f.split('/')[-1]]), f
+        n_lines += text.count('\n')
+    assert n_lines == int(cnt.sum())
+    names = voc_classes[1:]
+    res = col.coco_results([139, 285], names, {n: 101 + i for i, n in enumerate(names)})
+    assert [x['image_id'] for x in res] == g['coco_image_id'].tolist() and [x['category_id'] for x in res] == g['coco_category_id'].tolist()
+    assert np.array_equal(np.array([x['bbox'] for x in res]), g['coco_bbox']) and np.array_equal(np.array([x['score'] for x in res]), g['coco_score'])
+    out = col.write_coco_results(str(tmp_path / 'res.json'), [139, 285], names, {n: 101 + i for i, n in enumerate(names)})
+    assert len(json.load(open(out))) == len(res)

@@ -144,3 +144,26 @@ def test_init_reweight_prototypes_match_reference(golden):
     assert np.allclose(got, g['weight'], rtol=0, atol=2e-6, equal_nan=True)
     inc = np_oracle.init_reweight_prototypes([f.numpy() for f in feats], labels, 21, 'incre')
     assert inc.shape == (5, 60) and np.allclose(inc, g['weight_incre'], rtol=0, atol=2e-6, equal_nan=True)
+
+
+def test_base_transform_resize_oracle_vs_reference_golden(golden):
+    """oracle/np_oracle.base_transform (OpenCV's fixed-point 8-bit bilinear resize restated) against the output of the
+    REFERENCE's own BaseTransform class (data/data_augment.py:224-266) on seeded images — tests/golden/resize.npz."""
+    from oracle.gen_golden import RESIZE_CASES, resize_image
+    g = golden('resize.npz')
+    for hw, size, seed in RESIZE_CASES:
+        key = '%dx%d_%d' % (hw[0], hw[1], size)
+        t = np_oracle.base_transform(resize_image(hw, seed), size)
+        assert t.shape == (3, size, size) and t.dtype == np.float32
+        assert np.array_equal(t[:, ::17, :], g['rows_' + key]), key
+        assert np.array_equal(checksum(t), g['sum_' + key]), key
+
+
+def test_resize_oracle_vs_live_cv2():
+    """... and against cv2.resize itself where cv2 is importable: up / down scaling, odd sizes, 1-pixel sources."""
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(7)
+    for (h, w) in [(375, 500), (500, 375), (333, 500), (300, 300), (600, 600), (100, 130), (1, 1), (2, 3), (480, 640), (299, 301), (37, 901)]:
+        for size in (300, 512):
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            assert np.array_equal(np_oracle.cv_resize_linear_u8(img, size), cv2.resize(img, (size, size), interpolation=cv2.INTER_LINEAR)), (h, w, size)
