@@ -344,6 +344,234 @@ __device__ int block_soft_nms(float4* box, float* sc, int* tag, int* tmp, int n,
 }
 
 // ------------------------------------------------------------------------------------------------
+// cpu_soft_nms for lists of <= kSoftSmall candidates: the same algorithm and arithmetic as block_soft_nms above, with the
+// whole state (box / score / prior per position) in SHARED memory, a small CTA (128 threads: block barriers cost tens of
+// ns instead of the ~0.3 us of 512 threads going through global memory) and the swap-with-last compaction done by ONE warp
+// from the short list of positions removed in this iteration (ballots instead of two block-wide scans).  The outer loop
+// is inherently sequential (one iteration per surviving box), so the time of a class is iterations x latency: this cuts
+// the latency of an iteration ~6x.  Longer lists keep the generic kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSoftSmall = 2048;
+constexpr int kSoftThreads = 128;     // lists <= kSoftSplit; longer ones (<= kSoftSmall) get kSoftThreadsBig: the decay pass is (N / threads) deep
+constexpr int kSoftThreadsBig = 256;
+constexpr int kSoftSplit = 384;
+struct SoftSmem {
+  uint64_t keys[kSoftSmall];
+  float4 box[kSoftSmall];
+  float sc[kSoftSmall];
+  float area[kSoftSmall];              // (x2 - x1 + 1)(y2 - y1 + 1) of the box at each position, evaluated once (it travels with the box)
+  int tag[kSoftSmall];
+  int removed[kSoftSmall];             // positions removed in the current iteration (unordered)
+  int holes[32];
+  float best[16];
+  int bpos[16];
+  int nrem, maxpos;
+  int scan[40];
+};
+
+// first maximum (value, position) of two candidates: larger value wins, ties go to the smaller position
+__device__ __forceinline__ void first_max(float& best, int& bpos, float ov, int op) {
+  if (op != 0x7fffffff && (bpos == 0x7fffffff || ov > best || (ov == best && op < bpos))) { best = ov; bpos = op; }
+}
+
+__device__ int block_soft_nms_small(SoftSmem& sm, int n, float sigma, float Nt, float threshold, unsigned method, int T) {
+  // T = participating threads (the first T of the CTA; the others have exited)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  float4* box = sm.box; float* sc = sm.sc; int* tag = sm.tag; float* ar = sm.area;
+  int N = n;
+  // partial first-maxima of this thread's strided positions in [lo, N) -> sm.best / sm.bpos per warp
+  auto scan_max = [&](int lo) {
+    float best = -INFINITY; int bpos = 0x7fffffff;
+    for (int pos = lo + tid; pos < N; pos += T) {
+      const float v = sc[pos];
+      if (bpos == 0x7fffffff || best < v) { best = v; bpos = pos; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first_max(best, bpos, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bpos, o));
+    if (lane == 0) { sm.best[warp] = best; sm.bpos[warp] = bpos; }
+  };
+  // thread 0: combine the warps' partial maxima over [i, N) and bring the winner to position i (the reference starts
+  // from maxscore = boxes[i,4] and only moves on a strictly larger score)
+  auto select = [&](int i) {
+    if (warp == 0) {
+      float best = lane < nw ? sm.best[lane] : -INFINITY;
+      int bpos = lane < nw ? sm.bpos[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) first_max(best, bpos, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bpos, o));
+      if (lane == 0) {
+        if (i < N) {
+          const int mp = (bpos != 0x7fffffff && sc[i] < best) ? bpos : i;
+          if (mp != i) {
+            const float4 tb = box[i]; box[i] = box[mp]; box[mp] = tb;
+            const float ts = sc[i]; sc[i] = sc[mp]; sc[mp] = ts;
+            const int tt = tag[i]; tag[i] = tag[mp]; tag[mp] = tt;
+            const float ta = ar[i]; ar[i] = ar[mp]; ar[mp] = ta;
+          }
+        }
+        sm.nrem = 0;
+      }
+    }
+  };
+  scan_max(0);
+  __syncthreads();
+  select(0);
+  __syncthreads();
+  for (int i = 0; i < N; ++i) {
+    // decay (i, N) against box i; removed positions are appended to sm.removed; the partial first-maxima of the UPDATED
+    // scores over (i, N) — the next iteration's selection — are gathered in the same pass
+    const float4 t = box[i];
+    float best = -INFINITY; int bpos = 0x7fffffff;
+    // one position: overlap test first (the reference computes the candidate's area before it, which has no effect when
+    // the boxes are disjoint): iw = (float)((double)(min - max) + 1.0) > 0  <=>  min - max > -1 exactly
+    // Arithmetic as cpu_nms.pyx:117-143 evaluates it (Cython promotes "+ 1" to double and rounds the assignment to float):
+    // iw = (float)((double)dw + 1.0) equals the single-precision sum exactly (a correctly rounded sum of two floats is
+    // immune to double rounding, 53 >= 2 * 24 + 2); the box areas are compound double expressions and come from sm.area.
+    const double t_area = ((double)__fsub_rn(t.z, t.x) + 1.0) * ((double)__fsub_rn(t.w, t.y) + 1.0);
+    auto decay_one = [&](int pos, const float4 b, float v) {
+      const float dw = __fsub_rn(fminf(t.z, b.z), fmaxf(t.x, b.x)), dh = __fsub_rn(fminf(t.w, b.w), fmaxf(t.y, b.y));
+      if (dw > -1.0f && dh > -1.0f) {
+        const float iw = __fadd_rn(dw, 1.0f), ih = __fadd_rn(dh, 1.0f);
+        if (iw > 0.f && ih > 0.f) {
+          const float iwh = __fmul_rn(iw, ih);
+          const float ua = (float)((t_area + (double)ar[pos]) - (double)iwh);
+          const float ov = __fdiv_rn(iwh, ua);
+          float weight;
+          if (method == 1) weight = ov > Nt ? __fsub_rn(1.0f, ov) : 1.0f;
+          else if (method == 2) weight = (float)exp((double)__fdiv_rn(-__fmul_rn(ov, ov), sigma));
+          else weight = ov > Nt ? 0.0f : 1.0f;
+          v = __fmul_rn(weight, v);
+          sc[pos] = v;
+          if (v < threshold) sm.removed[atomicAdd(&sm.nrem, 1)] = pos;
+        }
+      }
+      if (bpos == 0x7fffffff || best < v) { best = v; bpos = pos; }
+    };
+    int pos = i + 1 + tid;
+    for (; pos + 3 * T < N; pos += 4 * T) {                    // four independent loads in flight: the pass is latency bound
+      const float4 b0 = box[pos], b1 = box[pos + T], b2 = box[pos + 2 * T], b3 = box[pos + 3 * T];
+      const float v0 = sc[pos], v1 = sc[pos + T], v2 = sc[pos + 2 * T], v3 = sc[pos + 3 * T];
+      decay_one(pos, b0, v0); decay_one(pos + T, b1, v1); decay_one(pos + 2 * T, b2, v2); decay_one(pos + 3 * T, b3, v3);
+    }
+    for (; pos < N; pos += T) decay_one(pos, box[pos], sc[pos]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first_max(best, bpos, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bpos, o));
+    if (lane == 0) { sm.best[warp] = best; sm.bpos[warp] = bpos; }
+    __syncthreads();
+    const int nrem = sm.nrem;
+    if (nrem > 0) {
+      // swap-with-last compaction: holes (removed positions < Nf, ascending) are filled by the survivors at positions
+      // >= Nf taken in descending position order.  Positions move, so the maxima gathered above are recomputed afterwards.
+      const int Nf = N - nrem;
+      if (nrem <= 32) {
+        if (warp == 0) {
+          const int pr = lane < nrem ? sm.removed[lane] : 0x7fffffff;
+          int rank = 0;                                 // rank of this lane's removed position among the holes
+          bool taken = false;                           // is position N - 1 - lane (a filler candidate) itself removed?
+          const int q = N - 1 - lane;
+          for (int k = 0; k < nrem; ++k) {
+            const int pk = __shfl_sync(0xffffffffu, pr, k);
+            rank += (pk < pr && pk < Nf) ? 1 : 0;
+            taken = taken || pk == q;
+          }
+          if (pr < Nf) sm.holes[rank] = pr;
+          __syncwarp();
+          const bool filler = lane < nrem && !taken;    // q >= Nf by construction
+          const unsigned fm = __ballot_sync(0xffffffffu, filler);
+          if (filler) {
+            const int dst = sm.holes[__popc(fm & ((1u << lane) - 1u))];
+            box[dst] = box[q]; sc[dst] = sc[q]; tag[dst] = tag[q]; ar[dst] = ar[q];
+          }
+        }
+      } else {
+        // many removals at once (rare): flags + two block-wide scans, as in the generic kernel
+        int* flag = reinterpret_cast<int*>(sm.keys);            // the sort buffer is free by now: [0, N) flags, [N, 2N) holes
+        for (int pos = i + 1 + tid; pos < N; pos += T) flag[pos] = 0;
+        __syncthreads();
+        for (int k = tid; k < nrem; k += T) flag[sm.removed[k]] = 1;
+        __syncthreads();
+        int running = 0;
+        for (int base = i + 1; base < N; base += T) {
+          const int pos = base + tid;
+          const int rem = (pos < N) ? flag[pos] : 0;
+          int tot;
+          const int R = running + block_exclusive_scan_n(rem, sm.scan, &tot, nw);
+          running += tot;
+          if (pos < N && rem && pos < Nf) flag[N + R] = pos;
+        }
+        __syncthreads();
+        running = 0;
+        for (int base = i + 1; base < N; base += T) {
+          const int pos = base + tid;
+          const int rem = (pos < N) ? flag[pos] : 0;
+          int tot;
+          const int R = running + block_exclusive_scan_n(rem, sm.scan, &tot, nw);
+          running += tot;
+          if (pos < N && pos >= Nf && !rem) {
+            const int dst = flag[N + (N - 1 - pos) - (nrem - R)];
+            box[dst] = box[pos]; sc[dst] = sc[pos]; tag[dst] = tag[pos]; ar[dst] = ar[pos];
+          }
+        }
+      }
+      N = Nf;
+      __syncthreads();
+      scan_max(i + 1);
+      __syncthreads();
+    }
+    select(i + 1);
+    __syncthreads();
+  }
+  return N;
+}
+
+__global__ void __launch_bounds__(kSoftThreadsBig)
+class_soft_nms_small_kernel(const float* __restrict__ conf, const float* __restrict__ obj, const float4* boxes_px,
+                            const int* __restrict__ cand_count, const uint64_t* cand_keys, int key_stride, int P, int C,
+                            float thresh, int method, float sigma, float soft_threshold,
+                            float4* spill, int* kept_prior, float* kept_score, int* kept_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SoftSmem& sm = *reinterpret_cast<SoftSmem*>(smem_raw);
+  const int j = blockIdx.x, b = blockIdx.y;
+  const size_t row = (size_t)b * C + j;
+  const int n = cand_count[row];
+  if (n > kSoftSmall) return;                                   // the generic kernel takes long lists
+  if (n == 0) { if (threadIdx.x == 0) kept_count[row] = 0; return; }
+  // short lists run on the first kSoftThreads threads only (cheaper barriers and reductions); the rest of the CTA leaves
+  const int T = n > kSoftSplit ? kSoftThreadsBig : kSoftThreads;
+  if ((int)threadIdx.x >= T) return;
+  const float4* bpx = boxes_px + (size_t)b * P;
+  // candidate order = ascending prior index (np.where order, test.py:143): sort keys (0xFFFFFFFF - prior) descending
+  const uint64_t* gk = cand_keys + row * key_stride;
+  int npad = 2;
+  while (npad < n) npad <<= 1;
+  for (int i = threadIdx.x; i < npad; i += T) sm.keys[i] = i < n ? (uint64_t)(0xFFFFFFFFu - key_index(gk[i])) + 1ull : 0ull;
+  __syncthreads();
+  for (int k = 2; k <= npad; k <<= 1)
+    for (int jj = k >> 1; jj > 0; jj >>= 1) {
+      for (int t = threadIdx.x; t < (npad >> 1); t += T) {
+        const int i = 2 * t - (t & (jj - 1));
+        cmpxchg_desc(sm.keys, i, i + jj, (i & k) == 0);
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += T) {
+    const int p = (int)(0xFFFFFFFFu - (uint32_t)(sm.keys[i] - 1ull));
+    const size_t bp = (size_t)b * P + p;
+    const float4 bx = bpx[p];
+    sm.box[i] = bx;
+    sm.area[i] = (float)(((double)__fsub_rn(bx.z, bx.x) + 1.0) * ((double)__fsub_rn(bx.w, bx.y) + 1.0));
+    sm.sc[i] = __fmul_rn(obj[bp * 2 + 1], conf[bp * C + j]);
+    sm.tag[i] = p;
+  }
+  __syncthreads();
+  const int N = block_soft_nms_small(sm, n, sigma, thresh, soft_threshold, method == 3 ? 0u : (unsigned)method, T);
+  float4* my_spill = spill + row * P;
+  int* my_prior = kept_prior + row * P;
+  float* my_score = kept_score + row * P;
+  for (int i = threadIdx.x; i < N; i += T) { my_spill[i] = sm.box[i]; my_score[i] = sm.sc[i]; my_prior[i] = sm.tag[i]; }
+  if (threadIdx.x == 0) kept_count[row] = N;
+}
+
+// ------------------------------------------------------------------------------------------------
 // one CTA per (class, image): sort candidates, run NMS, emit the kept (prior, score) list
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNmsThreads)
@@ -375,6 +603,7 @@ class_nms_kernel(const float* __restrict__ conf, const float* __restrict__ obj, 
     }
     if (threadIdx.x == 0) kept_count[row] = nk;
   } else {
+    if (n <= kSoftSmall) return;              // class_soft_nms_small_kernel handles short lists
     // soft-NMS runs in candidate order = ascending prior index (np.where order, test.py:143):
     // rewrite keys so that the descending sort yields ascending prior index.
     for (int i = threadIdx.x; i < n; i += blockDim.x) gkeys[i] = (uint64_t)(0xFFFFFFFFu - key_index(gkeys[i]));
@@ -580,6 +809,13 @@ extern "C" int ctx_detect_postprocess(const float* loc, const float* conf, const
                                                        w.cand_keys, w.key_stride);
   CTX_LAUNCH_CHECK();
   CTX_CUDA_TRY(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem)));
+  if (p->nms_method != 0) {
+    CTX_CUDA_TRY(cudaFuncSetAttribute(class_soft_nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SoftSmem)));
+    class_soft_nms_small_kernel<<<dim3(C, B), kSoftThreadsBig, sizeof(SoftSmem), st>>>(
+        conf, obj, w.boxes_px, w.cand_count, w.cand_keys, w.key_stride, P, C, p->nms_thresh, p->nms_method, p->soft_sigma,
+        p->soft_threshold, w.spill, w.kept_prior, w.kept_score, w.kept_count);
+    CTX_LAUNCH_CHECK();
+  }
   class_nms_kernel<<<dim3(C, B), kNmsThreads, sizeof(NmsSmem), st>>>(
       conf, obj, w.boxes_px, w.cand_count, w.cand_keys, w.key_stride, P, C, p->nms_thresh, p->suppress_on_equal,
       p->nms_method, p->soft_sigma, p->soft_threshold, w.spill, w.kept_prior, w.kept_score, w.kept_count, w.soft_tmp);

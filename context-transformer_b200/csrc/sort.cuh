@@ -17,8 +17,13 @@ __device__ __forceinline__ uint32_t key_index(uint64_t k) { return 0xFFFFFFFFu -
 
 // block-wide exclusive scan of one int per thread; returns exclusive prefix, *total = block sum.
 // scratch: >= 33 ints of shared memory.  All threads of the block must call.
+__device__ __forceinline__ int block_exclusive_scan_n(int v, int* scratch, int* total, int nwarp);
 __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  return block_exclusive_scan_n(v, scratch, total, (blockDim.x + 31) >> 5);
+}
+// same, for the first `nwarp` warps of a CTA whose other warps have exited
+__device__ __forceinline__ int block_exclusive_scan_n(int v, int* scratch, int* total, int nwarp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
