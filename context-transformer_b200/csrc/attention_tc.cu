@@ -47,7 +47,7 @@ template <int D>
 __global__ void __launch_bounds__(128)
 proj_kv_kernel(const float* __restrict__ pooled, const float* __restrict__ phi_w, const float* __restrict__ phi_b,
                const float* __restrict__ g_w, const float* __restrict__ g_b, int B, int Pk, int Pk_pad,
-               __half* __restrict__ khl, __half* __restrict__ vt) {
+               __half* __restrict__ khl, __half* __restrict__ vt, __half* __restrict__ vt_lo) {
   __shared__ float s_phi[D * D], s_g[D * D], s_pb[D], s_gb[D];
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) { s_phi[i] = phi_w[i]; s_g[i] = g_w[i]; }
   for (int i = threadIdx.x; i < D; i += blockDim.x) { s_pb[i] = phi_b[i]; s_gb[i] = g_b[i]; }
@@ -78,7 +78,9 @@ proj_kv_kernel(const float* __restrict__ pooled, const float* __restrict__ phi_w
       h[e] = __float2half_rn(k);
       l[e] = __float2half_rn(k - __half2float(h[e]));
       if (o == D) v = valid ? 1.f : 0.f;                     // "ones" feature: the PV MMA then accumulates sum_j p_j in O[:, D]
-      vt[((long long)b * AT_DP + o) * Pk_pad + j] = __float2half_rn(v);
+      const __half vh = __float2half_rn(v);
+      vt[((long long)b * AT_DP + o) * Pk_pad + j] = vh;
+      if (vt_lo) vt_lo[((long long)b * AT_DP + o) * Pk_pad + j] = __float2half_rn(v - __half2float(vh));
     }
     *reinterpret_cast<uint4*>(hi + o0) = *reinterpret_cast<uint4*>(h);
     *reinterpret_cast<uint4*>(lo + o0) = *reinterpret_cast<uint4*>(l);
@@ -103,6 +105,7 @@ struct AttnTcParams {
   int num_novel, incre, apply_softmax;
   int bulk_x;                       // conf blocks are 16-byte aligned / sized: staged with 1-D bulk copies
   int split;                        // 1: logits = Qh Kh^T + Ql Kh^T + Qh Kl^T (fp32-grade); 0: Qh Kh^T only (fp16-grade, 3x fewer MMAs)
+  int precise;                      // 1 (implies split): 64-key tiles, P and V as fp16 hi/lo pairs too: O = Pl Vh + Ph Vl + Ph Vh (fp32-grade output)
   long long k_rows;                 // B*Pk_pad (row offset of the "lo" half of K)
   const float* conf;                // [B,P,D] fp32: projection input and residual x
   const float *theta_b, *Wz, *obj_w, *fc_w, *fc_b;
@@ -142,7 +145,7 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
 template <int D, int NN>       // feature dim, novel classes (rows of OBJ_Target)
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_k,
-                    const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p) {
+                    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_vl, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // [QhA QlA QhB QlB] 64 KB (epilogue: classifier weights per q-tile)
@@ -150,8 +153,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   // ring 96 KB: 2 x {Kh 16, Vt 2 x 8, Kl 16} or 3 x {Kh, Vt} (prologue: the last stage holds theta' hi/lo)
   const uint32_t sQ = base, sP = sQ + 4 * AT_TILE_Q, sKV = sP + 4 * AT_TILE_Q;
   const uint32_t bars = sKV + AT_RING;
-  const int NST = p.split ? 2 : 3;                       // ring depth
-  const uint32_t STAGE = p.split ? AT_STAGE_SPLIT : AT_STAGE_FAST;
+  // precise mode: 64-key tiles, stage = {Kh 8, Kl 8, Vh^T 8, Vl^T 8} KB, three stages
+  const int KT = p.precise ? 64 : AT_BK;                 // keys per tile
+  const int NST = p.precise ? 3 : (p.split ? 2 : 3);     // ring depth
+  const uint32_t STAGE = p.precise ? 4u * AT_TILE_W : (p.split ? AT_STAGE_SPLIT : AT_STAGE_FAST);
   const uint32_t w_full = bars, x_full = bars + 8, xq_done = bars + 24, q_ready = bars + 40, kv_full = bars + 56,
                  kv_empty = kv_full + 8 * 3, s_full = kv_empty + 8 * 3, s_empty = s_full + 32,
                  p_full = s_empty + 32, pv_done = p_full + 16, tmem_slot = pv_done + 16, xin_full = tmem_slot + 8;
@@ -161,7 +166,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   const int b = blockIdx.y, q0 = blockIdx.x * (AT_QT * AT_BQ);
   const int T = p.ntiles;
 
-  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); }
+  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); if (p.precise) tma_prefetch_desc(&tm_vl); }
   if (warp == 9) {
     if (lane == 0) {
       mbar_init(w_full, 1);
@@ -209,17 +214,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       if (elect_one()) {
         const uint32_t dst = sKV + s * STAGE;
         mbar_arrive_expect_tx(kv_full + 8 * s, STAGE);
-        tma_load_2d(dst, &tm_k, 0, b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
-        tma_load_2d(dst + AT_TILE_K, &tm_v, j * AT_BK, b * AT_DP, kv_full + 8 * s);
-        tma_load_2d(dst + AT_TILE_K + AT_TILE_W, &tm_v, j * AT_BK + 64, b * AT_DP, kv_full + 8 * s);
-        if (p.split) tma_load_2d(dst + 2 * AT_TILE_K, &tm_k, 0, (int)p.k_rows + b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
+        if (p.precise) {                                        // (tm_k is encoded with 64-row boxes in this mode)
+          tma_load_2d(dst, &tm_k, 0, b * p.Pk_pad + j * 64, kv_full + 8 * s);
+          tma_load_2d(dst + AT_TILE_W, &tm_k, 0, (int)p.k_rows + b * p.Pk_pad + j * 64, kv_full + 8 * s);
+          tma_load_2d(dst + 2 * AT_TILE_W, &tm_v, j * 64, b * AT_DP, kv_full + 8 * s);
+          tma_load_2d(dst + 3 * AT_TILE_W, &tm_vl, j * 64, b * AT_DP, kv_full + 8 * s);
+        } else {
+          tma_load_2d(dst, &tm_k, 0, b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
+          tma_load_2d(dst + AT_TILE_K, &tm_v, j * AT_BK, b * AT_DP, kv_full + 8 * s);
+          tma_load_2d(dst + AT_TILE_K + AT_TILE_W, &tm_v, j * AT_BK + 64, b * AT_DP, kv_full + 8 * s);
+          if (p.split) tma_load_2d(dst + 2 * AT_TILE_K, &tm_k, 0, (int)p.k_rows + b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
+        }
       }
       __syncwarp();
       if (++s == NST) { s = 0; ph ^= 1; }
     }
   } else if (warp == 9) {
     // ================= MMA issuer ================= (whole warp converged, one elected lane issues)
-    const uint32_t idesc_s = make_idesc_f16(false, AT_BQ, AT_BK);    // logits: M128 x N128 keys
+    const uint32_t idesc_s = make_idesc_f16(false, AT_BQ, KT);       // logits: M128 x N = keys per tile
     const uint32_t idesc_d = make_idesc_f16(false, AT_BQ, AT_DP);    // projection / PV: M128 x N64 features
     const uint64_t dQ = make_sw128_desc(sQ), dP = make_sw128_desc(sP), dKV = make_sw128_desc(sKV);
     // ---- projection: Q_t = conf_t (theta + I)^T, hi/lo split, into the first 64 columns of S_t
@@ -256,7 +268,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         tc_fence_after();
         if (lane == 0) AT_DBG(j * 16 + 1 + t);
         if (elect_one()) {
-          const uint64_t kh = dKV + (uint64_t)((sq * STAGE) >> 4), kl = kh + (uint64_t)((2 * AT_TILE_K) >> 4);
+          const uint64_t kh = dKV + (uint64_t)((sq * STAGE) >> 4), kl = kh + (uint64_t)((p.precise ? AT_TILE_W : 2 * AT_TILE_K) >> 4);
           const uint64_t qh = dQ + (uint64_t)((2 * t * AT_TILE_Q) >> 4), ql = qh + (uint64_t)(AT_TILE_Q >> 4);
           const uint32_t d = tmem + buf * AT_BK;
 #pragma unroll
@@ -280,7 +292,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         tc_fence_after();
         if (lane == 0) AT_DBG(jj * 16 + 4 + t);
         if (elect_one()) {
-          const uint64_t vt = dKV + (uint64_t)((sp * STAGE + AT_TILE_K) >> 4), pp = dP + (uint64_t)((t * 2 * AT_TILE_Q) >> 4);
+          const uint64_t vt = dKV + (uint64_t)((sp * STAGE + (p.precise ? 2 * AT_TILE_W : AT_TILE_K)) >> 4), pp = dP + (uint64_t)((t * 2 * AT_TILE_Q) >> 4);
+          if (p.precise) {                 // 64 keys: O += Pl Vh + Ph Vl + Ph Vh (small terms first)
+            const uint64_t pl = pp + (uint64_t)(AT_TILE_Q >> 4), vl = vt + (uint64_t)(AT_TILE_W >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tO + t * AT_DP, pl + 2 * k, vt + 2 * k, idesc_d, (jj | k) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tO + t * AT_DP, pp + 2 * k, vl + 2 * k, idesc_d, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tO + t * AT_DP, pp + 2 * k, vt + 2 * k, idesc_d, 1u);
+          } else
 #pragma unroll
           for (int k = 0; k < 8; ++k)      // keys 0-63: P / Vt block 0, keys 64-127: block 1
             umma_f16(tO + t * AT_DP, pp + (uint64_t)((k >> 2) * (AT_TILE_Q >> 4)) + 2 * (k & 3),
@@ -343,16 +364,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       mbar_wait(s_full + 8 * ub, (u / 3) & 1);
       tc_fence_after();
       if (warp == 0 && lane == 0) AT_DBG(j * 16 + 8);
-#pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {
+      const int NH = p.precise ? 1 : 2;                          // 64-key halves per tile
+      for (int hb = 0; hb < NH; ++hb) {
         tmem_ld64(tSu + hb * 64, v);
         if (warp == 0 && lane == 0) AT_DBG(j * 16 + 9 + 3 * hb);
-        if (hb == 1) {
+        if (hb == NH - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(s_empty + 8 * ub);
         }
-        const int nvalid = p.Pk - j * AT_BK - hb * 64;
+        const int nvalid = p.Pk - j * KT - hb * 64;
         if (nvalid < 64) {
 #pragma unroll
           for (int c = 0; c < 64; ++c)
@@ -404,6 +425,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
               }
             }
           }
+        }
+        if (p.precise) {                     // P as fp16 hi / lo pairs: the two K-blocks of P_t hold Ph and Pl of the same 64 keys
+#pragma unroll
+          for (int c = 0; c < 64; ++c) v[c] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(v[c]), AT_LOG2E, -ref2)));
+          store_split_row(sPt, sPt + AT_TILE_Q, r, *reinterpret_cast<const float(*)[64]>(&v[0]));
+          continue;
         }
 #pragma unroll
         for (int e = 0; e < 32; ++e) {       // (ex2.approx.f16x2 is no faster: it issues one MUFU.EX2.F16 per half — checked in SASS)
@@ -560,8 +587,8 @@ static size_t attn_tc_smem(int D, int num_novel, int incre) {
 
 size_t attention_tc_workspace_bytes(int B, int P, int Pk) {
   const size_t Pk_pad = (size_t)(Pk + AT_BK - 1) / AT_BK * AT_BK;
-  (void)P;
-  return align_up((size_t)2 * B * Pk_pad * AT_DP * 2, 1024) + align_up((size_t)B * AT_DP * Pk_pad * 2, 1024) +
+  (void)P;                                  // K hi/lo, V^T hi, V^T lo (precise mode), theta' hi/lo
+  return align_up((size_t)2 * B * Pk_pad * AT_DP * 2, 1024) + 2 * align_up((size_t)B * AT_DP * Pk_pad * 2, 1024) +
          align_up((size_t)2 * AT_DP * AT_DP * 2, 1024);
 }
 
@@ -582,22 +609,27 @@ static int attention_tc_launch_t(const CtxAttnParams* a, cudaStream_t st) {
   char* ws = (char*)a->workspace;
   __half* khl = (__half*)ws;
   __half* vt = (__half*)(ws + align_up((size_t)2 * B * Pk_pad * AT_DP * 2, 1024));
-  __half* wq = (__half*)((char*)vt + align_up((size_t)B * AT_DP * Pk_pad * 2, 1024));
+  __half* vt_lo = (__half*)((char*)vt + align_up((size_t)B * AT_DP * Pk_pad * 2, 1024));
+  __half* wq = (__half*)((char*)vt_lo + align_up((size_t)B * AT_DP * Pk_pad * 2, 1024));
+  const bool precise = a->use_tensor_cores == 3;
+  const int KT = precise ? 64 : AT_BK;
   const long long k_rows = (long long)B * Pk_pad;
   prep_wq_kernel<<<cdiv(AT_DP * AT_DP, 256), 256, 0, st>>>(a->theta_w, D, wq);
   CTX_LAUNCH_CHECK();
-  proj_kv_kernel<D><<<cdiv(k_rows, 128), 128, 0, st>>>(a->pooled, a->phi_w, a->phi_b, a->g_w, a->g_b, B, Pk, Pk_pad, khl, vt);
+  proj_kv_kernel<D><<<cdiv(k_rows, 128), 128, 0, st>>>(a->pooled, a->phi_w, a->phi_b, a->g_w, a->g_b, B, Pk, Pk_pad, khl, vt, precise ? vt_lo : nullptr);
   CTX_LAUNCH_CHECK();
-  CUtensorMap tw, tk, tv;
+  CUtensorMap tw, tk, tv, tvl;
   int rc = encode_2d_sw128(&tw, wq, false, 2ull * AT_DP, AT_DP, AT_DP);
-  if (!rc) rc = encode_2d_sw128(&tk, khl, false, 2ull * k_rows, AT_DP, AT_BK);
+  if (!rc) rc = encode_2d_sw128(&tk, khl, false, 2ull * k_rows, AT_DP, (unsigned)KT);
   if (!rc) rc = encode_2d_sw128(&tv, vt, false, (unsigned long long)B * AT_DP, (unsigned long long)Pk_pad, AT_DP);   // box: 64 keys x 64 features
+  if (!rc) rc = encode_2d_sw128(&tvl, precise ? vt_lo : vt, false, (unsigned long long)B * AT_DP, (unsigned long long)Pk_pad, AT_DP);
   if (rc) return rc;
   AttnTcParams p;
-  p.B = B; p.P = P; p.Pk = Pk; p.Pk_pad = Pk_pad; p.ntiles = Pk_pad / AT_BK;
+  p.B = B; p.P = P; p.Pk = Pk; p.Pk_pad = Pk_pad; p.ntiles = Pk_pad / KT;
+  p.precise = precise;
   p.num_novel = a->num_novel; p.incre = a->incre; p.apply_softmax = a->apply_softmax;
   p.k_rows = k_rows;
-  p.split = a->use_tensor_cores == 2;
+  p.split = a->use_tensor_cores >= 2;
   p.bulk_x = ((uintptr_t)a->conf % 16 == 0) && ((size_t)P * D * 4 % 16 == 0) && ((size_t)AT_BQ * D * 4 % 16 == 0) &&
              ((size_t)(P % AT_BQ) * D * 4 % 16 == 0);
   p.conf = a->conf; p.theta_b = a->theta_b; p.Wz = a->Wz; p.obj_w = a->obj_target_w; p.fc_w = a->fc_base_w; p.fc_b = a->fc_base_b;
@@ -605,7 +637,7 @@ static int attention_tc_launch_t(const CtxAttnParams* a, cudaStream_t st) {
   p.dbg = g_attn_dbg;
   const size_t smem = attn_tc_smem(D, a->num_novel, a->incre);
   CTX_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<D, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_tc_kernel<D, NN><<<dim3(cdiv(P, AT_QT * AT_BQ), B), AT_THREADS, smem, st>>>(tw, tk, tv, p);
+  attention_tc_kernel<D, NN><<<dim3(cdiv(P, AT_QT * AT_BQ), B), AT_THREADS, smem, st>>>(tw, tk, tv, tvl, p);
   CTX_LAUNCH_CHECK();
   return CTX_OK;
 }

@@ -489,8 +489,8 @@ class Engine(object):
             ap.Wz = f32(net.Wz)
             ap.obj_target_w = f32(net.OBJ_Target.weight)
             ap.scale = float(net.scale.detach().float().cpu().item())
-            # 0: fp32 CUDA cores; 1: tcgen05, fp16 logits; 2: tcgen05, fp16 hi/lo split logits
-            ap.use_tensor_cores = {'fp32': 0, 'fp32x3': 0}.get(self.precision, 1)
+            # 0: fp32 CUDA cores; 1: tcgen05, fp16 logits; 2: tcgen05, fp16 hi/lo split logits; 3: + hi/lo split P and V
+            ap.use_tensor_cores = {'fp32': 0, 'fp32x3': 3}.get(self.precision, 1)
             if os.environ.get('CTX_ATTN_MODE'):                  # development aid: force a Context-Transformer kernel variant
                 ap.use_tensor_cores = int(os.environ['CTX_ATTN_MODE'])
             ws_bytes = self.L.ctx_attention_workspace_bytes(C.byref(ap))

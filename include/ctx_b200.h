@@ -181,8 +181,10 @@ typedef struct CtxAttnParams {
   const float* Wz;                             /* [dim] */
   const float* obj_target_w;                   /* [num_novel, dim] */
   float scale;
-  int use_tensor_cores;                        /* 0: fp32 CUDA-core kernel (1e-4 parity mode); 1: tcgen05 kernel, fp16 logits
-                                                * (|dconf| ~6e-3 max / 2e-5 mean); 2: tcgen05 kernel, fp16 hi/lo split logits (4e-5) */
+  int use_tensor_cores;                        /* 0: fp32 CUDA-core kernel; 1: tcgen05 kernel, fp16 logits (|dconf| ~6e-3 max /
+                                                * 2e-5 mean: the 16-bit engine modes); 2: tcgen05, fp16 hi/lo split logits (4e-5);
+                                                * 3: tcgen05, hi/lo split logits AND hi/lo split P and V (fp32-grade output: the
+                                                * 'fp32x3' engine mode, 1e-4 parity bar) */
   void* workspace;                             /* ctx_attention_workspace_bytes(p) bytes, 1024-byte aligned */
   size_t workspace_bytes;
   float* out;                                  /* [B,P, incre ? dim+num_novel : num_novel] */

@@ -341,7 +341,7 @@ def test_attention_kernel_vs_torch(setting, d, n_novel):
     dv = lambda t: t.to(DEV).contiguous()
     t_ = [dv(t) for t in (conf, pool, tw, tb, pw, pb, gw, gb, fw, fb, Wz, ot)]
     n_out = want.size(-1)
-    for apply_softmax, use_tc in ((0, 0), (1, 0), (0, 1), (1, 1), (0, 2), (1, 2)):
+    for apply_softmax, use_tc in ((0, 0), (1, 0), (0, 1), (1, 1), (0, 2), (1, 2), (0, 3), (1, 3)):
         out = torch.empty(B, P, n_out, device=DEV)
         ap = _lib.CtxAttnParams()
         ap.batch, ap.num_priors, ap.num_pooled, ap.dim = B, P, Pk, d
@@ -359,6 +359,8 @@ def test_attention_kernel_vs_torch(setting, d, n_novel):
         # logit error): an order looser, used by the 16-bit engine modes whose conv stack is no more accurate than that.
         if not use_tc:
             tol = dict(rtol=1e-4, atol=2e-5)
+        elif use_tc == 3:                   # hi/lo split Q, K, P and V: fp32-grade (the 'fp32x3' engine mode)
+            tol = dict(rtol=0, atol=5e-6) if apply_softmax else dict(rtol=0, atol=4e-5)
         elif use_tc == 2:
             tol = dict(rtol=0, atol=2e-4) if apply_softmax else dict(rtol=0, atol=2e-3)
         else:
