@@ -434,20 +434,20 @@ def measure(w, steps, warmup, world, rank, full=True, layers_path=None, quick=Fa
 
     # ---- per-kernel pass: CUDA events around every op of the program ---------------------------
     # Large ops (> 5 GFLOP): L2 flushed, one launch per event pair, min of 3.  Small ops: a lone launch between two events is
-    # dominated by launch latency (~15-20 us) that does not exist inside the captured graph, so 10 back-to-back launches
+    # dominated by launch latency (~15-20 us) that does not exist inside the captured graph, so 20 back-to-back launches —
+    # issued by ONE native call (a Python -> ctypes call per launch costs ~8 us of host time, more than these kernels run) —
     # share one event pair and the average launch duration is reported (their inputs are L2-resident in the step as well).
     reps = 3
     per_op = []
     eng.load_input(w.x_dev)
     for i, (name, kind, flops, shape) in enumerate(eng.layers):
         ts = []
-        burst = 1 if flops > 5e9 else 10
+        burst = 1 if flops > 5e9 else 20
         for _ in range(reps):
             flush.zero_() if flops > 5e9 else None
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            for _k in range(burst):
-                eng.run_range(i, i + 1)
+            eng.run_range(i, i + 1, burst)
             b.record()
             b.synchronize()
             ts.append(a.elapsed_time(b) / burst)

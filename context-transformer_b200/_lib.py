@@ -115,6 +115,7 @@ SIGNATURES = {
     'ctx_prog_run': (_I, [_P, _P]),
     'ctx_prog_instantiate_graph': (_I, [_P, _P]),
     'ctx_prog_run_range': (_I, [_P, _I, _I, _P]),
+    'ctx_prog_run_range_repeat': (_I, [_P, _I, _I, _I, _P]),
     'ctx_prog_destroy': (None, [_P]),
     'ctx_match_encode': (_I, [_P, _P, _I, _P, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     'ctx_rank_workspace_bytes': (_SZ, [_I, _I]),

@@ -19,8 +19,8 @@
 // the heads, 1e-4 absolute on loc values of ~50).  Model: an instruction that brings the partial sum to s loses 3.4e-8 s on
 // average (half an ulp, averaged over the mantissa), so a chain of m equal blocks loses 3.4e-8 (m + 1) / 2 of its sum (m = 4
 // for a full 64-channel K-step, fewer for a channel tail); the residual bias measured with it is within +-2.5e-8.
-// The epilogue undoes the expected loss: sum * (1 + trunc_comp) is formed in fp64 and rounded ONCE to fp32 together with
-// the scale and the bias — an unbiased estimate of the exact sum instead of a biased one.
+// The epilogue undoes the expected loss: sum * (1 + trunc_comp) * scale + bias is rounded ONCE (error-free fp32 arithmetic,
+// see finish()) — an unbiased estimate of the exact sum instead of a biased one.
 //
 // Kernel (448 threads, persistent, one CTA per SM, 128 pixels x BN <= 128 channels per tile):
 //   warps 0-3  A producers in modes GATHER (16-byte cp.async im2col, both planes) and STEM (raw fp32 NCHW image -> 27-value
@@ -280,9 +280,12 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     uint32_t chain = 0, s = 0;
     for (int tile = group0; tile < p.num_tiles; tile += ngroups) {
       const int mt = tile / p.n_tiles_n, n0 = (tile - mt * p.n_tiles_n) * BN;
-      const int cbase = n0 + h * 64;                         // first channel of this warp's 64 columns
+      // the two warps of a TMEM lane quarter split the tile's columns: 64 + rest for wide tiles, 32 + rest for tiles <= 64 wide
+      // (so that all eight warps share the flush and the epilogue of the narrow stem / conv1_2 tiles)
+      const int cs = BN <= 64 ? 32 : 64;
+      const int cbase = n0 + h * cs;                         // first channel of this warp's columns
       const int c_end = min(p.Cout, n0 + BN);
-      const bool active = h * 64 < BN && cbase < c_end;      // warp-uniform
+      const bool active = h * cs < BN && cbase < c_end;      // warp-uniform
       float acc[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
@@ -293,21 +296,29 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         if (releaser && lane == 0) mbar_arrive(empty0 + 8 * s);
         if (++s == (uint32_t)S) s = 0;
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + buf * (uint32_t)X3_ACC_COLS + (uint32_t)(h * 64) + ((uint32_t)(q * 32) << 16);
+        const uint32_t taddr = tmem_base + buf * (uint32_t)X3_ACC_COLS + (uint32_t)(h * cs) + ((uint32_t)(q * 32) << 16);
+        const bool second = active && cs == 64;
         if (active) {
           tmem_ld32(taddr, v);
           tmem_ld_wait();
+          if (second) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i]);
-          tmem_ld32(taddr + 32u, v);
-          tmem_ld_wait();
+            for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i]);
+            tmem_ld32(taddr + 32u, v);
+            tmem_ld_wait();
+          }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acce0 + 8 * buf);
         if (active) {
+          if (second) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[32 + i] += __uint_as_float(v[i]);
+            for (int i = 0; i < 32; ++i) acc[32 + i] += __uint_as_float(v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i]);
+          }
         }
       }
       if (!active) continue;
@@ -316,9 +327,18 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       if (!row_ok) continue;
       const long long m_lin = (long long)n_img * p.Ho * p.Wo + pix;
       const int relu_cend = p.relu ? p.relu_cend : 0;
-      const double comp = 1.0 + (double)p.trunc_comp;
-      // (sum * (1 + comp)) * scale + bias with one rounding
-      auto finish = [&](float a, int c) { return (float)fma((double)a * comp, (double)s_scale[c], (double)s_bias[c]); };
+      // sum * (1 + comp) * scale + bias rounded ONCE, in fp32 only (fp64 conversions run on the quarter-rate XU pipe: with them
+      // the stem's epilogue ran that pipe at 120 % — ncu): scale is a power of two, so a = sum * scale is exact; the compensation
+      // t = a * comp is far below an ulp of the result and rides on the rounding error of a + bias (TwoSum), which is added back
+      // before the final rounding.
+      const float comp = p.trunc_comp;
+      auto finish = [&](float acc_v, int c) {
+        const float a = __fmul_rn(acc_v, s_scale[c]), b = s_bias[c];
+        const float s = __fadd_rn(a, b);
+        const float bb = __fsub_rn(s, a);
+        const float err = __fadd_rn(__fsub_rn(a, __fsub_rn(s, bb)), __fsub_rn(b, bb));
+        return __fadd_rn(s, __fadd_rn(err, __fmul_rn(a, comp)));
+      };
       if (p.fast_out) {
         // one 16-bit output tensor: hi / lo planes, 8 channels (16 bytes) per store
         const CtxOutSeg& sg = p.segs.seg[0];
@@ -330,7 +350,7 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 #pragma unroll
         for (int g8 = 0; g8 < 8; ++g8) {
           const int c = cbase + g8 * 8;
-          if (c < c_end) {
+          if (g8 * 8 < cs && c < c_end) {
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = finish(acc[g8 * 8 + j], c + j);
@@ -355,7 +375,7 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
           const int c = cbase + j;
-          if (c < c_end) {
+          if (j < cs && c < c_end) {
             float f = finish(acc[j], c);
             if (c < relu_cend) f = fmaxf(f, 0.f);
             int sgi = 0;
@@ -370,7 +390,7 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 #pragma unroll
         for (int g4 = 0; g4 < 16; ++g4) {
           const int c = cbase + g4 * 4;
-          if (c < c_end) {
+          if (g4 * 4 < cs && c < c_end) {
             float4 f = make_float4(finish(acc[g4 * 4 + 0], c + 0), finish(acc[g4 * 4 + 1], c + 1), finish(acc[g4 * 4 + 2], c + 2), finish(acc[g4 * 4 + 3], c + 3));
             if (c < relu_cend) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
             int sgi = 0;

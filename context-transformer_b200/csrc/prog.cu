@@ -313,6 +313,20 @@ extern "C" int ctx_prog_run_range(void* prog, int first, int last, void* stream)
   return CTX_OK;
 }
 
+// the same range `reps` times back to back from native code: per-kernel timing of small ops without the host language's
+// per-call overhead (a Python -> ctypes call costs ~8 us, more than most of the late-pyramid kernels run)
+extern "C" int ctx_prog_run_range_repeat(void* prog, int first, int last, int reps, void* stream) {
+  CTX_REQUIRE(prog, "ctx_prog_run_range_repeat: null handle");
+  Prog* pr = (Prog*)prog;
+  CTX_REQUIRE(first >= 0 && last <= (int)pr->ops.size() && first <= last && reps >= 0, "ctx_prog_run_range_repeat: bad range [%d,%d) x %d", first, last, reps);
+  for (int r = 0; r < reps; ++r)
+    for (int i = first; i < last; ++i) {
+      int rc = run_op(pr->ops[i], (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+  return CTX_OK;
+}
+
 extern "C" int ctx_prog_instantiate_graph(void* prog, void* stream) {
   CTX_REQUIRE(prog, "ctx_prog_instantiate_graph: null handle");
   Prog* pr = (Prog*)prog;

@@ -570,7 +570,7 @@ class Engine(object):
         _lib.check(self.L.ctx_prog_conv_config(self.prog, op_index, info), 'ctx_prog_conv_config')
         return list(info)
 
-    def run_range(self, first, last):
+    def run_range(self, first, last, reps=1):
         with torch.cuda.device(self.dev):
             st = torch.cuda.current_stream(self.dev)
-            _lib.check(self.L.ctx_prog_run_range(self.prog, first, last, C.c_void_p(st.cuda_stream)), 'ctx_prog_run_range')
+            _lib.check(self.L.ctx_prog_run_range_repeat(self.prog, first, last, reps, C.c_void_p(st.cuda_stream)), 'ctx_prog_run_range')

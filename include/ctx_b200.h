@@ -220,6 +220,8 @@ int ctx_prog_run(void* prog, void* stream);
 int ctx_prog_instantiate_graph(void* prog, void* stream);
 /* run ops [first, last) — used by bench.py/ncu to time one layer class */
 int ctx_prog_run_range(void* prog, int first, int last, void* stream);
+/* the same range `reps` times back to back (per-kernel timing of small ops without a host-language call per launch) */
+int ctx_prog_run_range_repeat(void* prog, int first, int last, int reps, void* stream);
 void ctx_prog_destroy(void* prog);
 
 /* ---- training targets : utils/box_utils.py:83-156, multibox_loss_combined.py:88-96 ----------- */
