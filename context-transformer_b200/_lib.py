@@ -91,6 +91,9 @@ SIGNATURES = {
     'ctx_conv2d_x3_plan_info': (_I, [_P, C.POINTER(_I)]),
     'ctx_conv2d_x3_plan_destroy': (None, [_P]),
     'ctx_prog_add_conv_x3': (_I, [_P, C.POINTER(CtxConvParams)]),
+    'ctx_conv2d_stem2_supported': (_I, [C.POINTER(CtxConvParams)]),
+    'ctx_conv2d_stem2_plan_create': (_I, [C.POINTER(CtxConvParams), _P, _P, _P, C.POINTER(_P)]),
+    'ctx_prog_add_conv_stem2': (_I, [_P, C.POINTER(CtxConvParams), _P, _P, _P]),
     'ctx_maxpool2d_nhwc': (_I, [C.POINTER(CtxPoolParams), _P]),
     'ctx_nchw_to_nhwc': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     'ctx_base_transform': (_I, [_P, _P, _I, _I, _I, C.POINTER(C.c_float), _P]),

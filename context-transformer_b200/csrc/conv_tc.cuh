@@ -11,7 +11,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_THREADS = 448;        // 4 producer + TMA + MMA + 2 x 4 epilogue warps
 constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;     // 16 KB
-constexpr int A_GATHER = 0, A_TMA = 1, A_STEM = 2, A_HALO = 3;
+constexpr int A_GATHER = 0, A_TMA = 1, A_STEM = 2, A_HALO = 3, A_STEM2 = 4;      // A_STEM2: conv_stem2.cu (conv1_1 fused into conv1_2)
 constexpr int HALO_THREADS = 352;      // patch TMA + weight TMA + MMA + 2 x 4 epilogue warps
 
 struct TcParams {
@@ -45,11 +45,23 @@ struct TcParams {
   void* out_lo;
   const float* out_scale;
   float trunc_comp;            // expected relative loss of one chain to the tensor core's truncating adder (see conv_x3.cu)
+  const float* bias1;          // A_STEM2: bias of the fused first conv (conv1_1), 64 floats
 };
+
+// A planned tensor-core conv: the TMA descriptors (pointers baked in), the kernel parameters and the launch shape.
+struct TcPlan {
+  CUtensorMap tmap_w, tmap_a;
+  CUtensorMap tmap_raw, tmap_w1;         // A_STEM2: raw fp32 NCHW input patches, conv1_1 weights
+  TcParams p;
+  int stages;
+  int grid;
+  size_t smem;
+};
+int launch_stem2(const TcPlan* pl, cudaStream_t st);      // conv_stem2.cu
 
 // output pixel (image, linear pixel index, validity) of row r of M-tile mt
 __device__ __forceinline__ bool tile_row_pixel(const TcParams& p, int mt, int r, int& n_img, int& pix) {
-  if ((p.a_mode == A_TMA && !p.flat) || p.a_mode == A_HALO) {
+  if ((p.a_mode == A_TMA && !p.flat) || p.a_mode == A_HALO || p.a_mode == A_STEM2) {
     const int per_img = p.tiles_x * p.tiles_y;
     n_img = mt / per_img;
     const int t = mt - n_img * per_img;

@@ -1,0 +1,332 @@
+// conv_tc_epilogue.cuh — epilogue warps of the tensor-core conv kernels (conv_tc.cu: conv_tc_kernel / conv_halo_kernel;
+// conv_stem2.cu: the fused conv1_1 + conv1_2 kernel): TMEM accumulator -> bias / residual / ReLU / 2x2 max-pool -> NHWC stores.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace ctx {
+
+// ---------------------------------------------------------------------------------------------------
+// Lean epilogue for the common case (one 16-bit output segment, 8-channel aligned: TcParams::fast_out), specialised at
+// compile time on fused pooling / residual / bulk-copy output so that the per-chunk code is branch-free: on the layers
+// with little K (the stem, conv1_2) the epilogue warps, not the MMAs, set the pace (ncu source view: ~320 warp
+// instructions per 32-column chunk in the generic path below, most of them flag tests and 64-bit index arithmetic).
+template <int CL, bool POOL, bool RES, bool BULK>
+__device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const float* s_bias, uint32_t tmem_base, uint32_t accf0, uint32_t acce0,
+                                                   int warp, int lane, uint32_t eset, int rank, int group0, int ngroups, uint32_t stage_smem) {
+  const int q = warp & 3;
+  const int BN = p.bn, Cout = p.Cout, relu_cend = p.relu ? p.relu_cend : 0;     // ReLU on channels < relu_cend (multiple of 8)
+  const int r = q * 32 + lane;
+  const bool bf16 = p.is_bf16 != 0;
+  uint16_t* const seg_ptr = reinterpret_cast<uint16_t*>(p.segs.seg[0].ptr) + p.segs.seg[0].ch_offset;
+  const long long img_stride = p.segs.seg[0].img_stride;
+  const int pix_stride = p.segs.seg[0].pix_stride;
+  const uint32_t stage_row = stage_smem + (uint32_t)(lane * Cout) * 2u;
+  uint32_t lt = eset;
+  for (int tile = group0 + (int)eset * ngroups; tile < p.num_tiles; tile += 2 * ngroups, lt += 2) {
+    const uint32_t buf = lt & 1;
+    const int mg = tile / p.n_tiles_n, n0 = (tile - mg * p.n_tiles_n) * BN, mt = mg * CL + rank;
+    int n_img, pix;
+    bool row_ok;
+    if (BULK) {            // pixel-linear tile of a dense map: the batch is one long pixel row (no per-tile division)
+      n_img = 0; pix = mt * TC_BM + r; row_ok = pix < p.M;
+    } else {
+      row_ok = tile_row_pixel(p, mt, r, n_img, pix);
+    }
+    long long opix = pix;
+    bool store = row_ok;
+    if (POOL) {            // row r = pixel (r / TW, r % TW) of the patch: 2 x 2 partners are lanes ^1 and ^TW; even/even lane stores
+      const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
+      opix = (long long)(oy >> 1) * (p.Wo >> 1) + (ox >> 1);
+      store = row_ok && !(lane & (1 | p.TW));
+    }
+    uint16_t* const out = seg_ptr + (long long)n_img * img_stride + opix * pix_stride;
+    const uint16_t* res = nullptr;
+    if (RES) res = reinterpret_cast<const uint16_t*>(p.residual) + ((long long)n_img * p.Ho * p.Wo + pix) * p.res_cstride + p.res_coffset;
+    const int c_end = min(Cout, n0 + BN);
+    // Transposed stores (plain case): a thread owns one output row, so its 16-byte pieces of a 32-column chunk would go out
+    // as four requests touching 32 half-written sectors each.  The four lanes of a quad exchange pieces (4 x 4 transpose, 16
+    // shuffles per chunk) so that a request writes, per row, the 64 contiguous bytes of the chunk from four adjacent lanes:
+    // whole 32-byte sectors, half as many of them.
+    constexpr bool TR = !POOL && !BULK;
+    unsigned long long outq[4] = {0ull, 0ull, 0ull, 0ull};
+    unsigned okbits = 0u;
+    if (TR) {
+      okbits = __ballot_sync(0xffffffffu, row_ok);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) outq[k] = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)out, (lane & ~3) + k);
+    }
+    // residual (RFB shortcut): the 64 bytes a thread needs per 32-column chunk are fetched one chunk ahead — the first
+    // chunk before the accumulator is even complete — so their latency hides behind the MMAs / the previous chunk
+    // (ncu what-if: without this the ConvLinear layers spent 70 % of their time waiting on these loads)
+    uint4 rnext[4];
+    auto load_res = [&](int c0) {
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        const int c = c0 + gq * 8;
+        rnext[gq] = (row_ok && c < c_end) ? __ldg(reinterpret_cast<const uint4*>(res + c)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    if (RES) load_res(n0);
+    mbar_wait(accf0 + 8 * buf, (lt >> 1) & 1);
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.acc_stride + ((uint32_t)(q * 32) << 16);
+    if (BULK) {                                                   // the previous tile's bulk store has read the staging rows
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int c0 = n0; c0 < c_end; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_d + (uint32_t)(c0 - n0), v);
+      uint4 rcur[4];
+      if (RES) {
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) rcur[gq] = rnext[gq];
+        if (c0 + 32 < c_end) load_res(c0 + 32);
+      }
+      tmem_ld_wait();
+      if (BULK && !row_ok) continue;
+      uint4 o[4];
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        const int c = c0 + gq * 8;
+        o[gq] = make_uint4(0u, 0u, 0u, 0u);
+        if (c < c_end) {
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
+          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
+          float f[8] = {__uint_as_float(v[gq * 8 + 0]) + b0.x, __uint_as_float(v[gq * 8 + 1]) + b0.y,
+                        __uint_as_float(v[gq * 8 + 2]) + b0.z, __uint_as_float(v[gq * 8 + 3]) + b0.w,
+                        __uint_as_float(v[gq * 8 + 4]) + b1.x, __uint_as_float(v[gq * 8 + 5]) + b1.y,
+                        __uint_as_float(v[gq * 8 + 6]) + b1.z, __uint_as_float(v[gq * 8 + 7]) + b1.w};
+          if (RES) {
+            if (row_ok) {
+              const uint4 rv = rcur[gq];
+              const float2 r0 = unpack2(rv.x, bf16), r1 = unpack2(rv.y, bf16), r2 = unpack2(rv.z, bf16), r3 = unpack2(rv.w, bf16);
+              f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y; f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+            }
+          }
+          if (c < relu_cend) {                                      // warp-uniform
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+          }
+          if (POOL) {                                               // max is exact in any precision: pool the fp32 values
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 1));
+              f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], p.TW));
+            }
+          }
+          o[gq] = make_uint4(pack2(f[0], f[1], bf16), pack2(f[2], f[3], bf16), pack2(f[4], f[5], bf16), pack2(f[6], f[7], bf16));
+          if (!TR && store) {
+            if (BULK)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (uint32_t)c * 2u), "r"(o[gq].x), "r"(o[gq].y), "r"(o[gq].z),
+                           "r"(o[gq].w) : "memory");
+            else
+              *reinterpret_cast<uint4*>(out + c) = o[gq];
+          }
+        }
+      }
+      if (TR) {
+        // 4 x 4 transpose of the 16-byte pieces inside each quad: afterwards lane j of the quad holds piece j of rows 0..3
+        const bool hi2 = (lane & 2) != 0, hi1 = (lane & 1) != 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          uint4 t = hi2 ? o[k] : o[k + 2];
+          t.x = __shfl_xor_sync(0xffffffffu, t.x, 2); t.y = __shfl_xor_sync(0xffffffffu, t.y, 2);
+          t.z = __shfl_xor_sync(0xffffffffu, t.z, 2); t.w = __shfl_xor_sync(0xffffffffu, t.w, 2);
+          if (hi2) o[k] = t; else o[k + 2] = t;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k += 2) {
+          uint4 t = hi1 ? o[k] : o[k + 1];
+          t.x = __shfl_xor_sync(0xffffffffu, t.x, 1); t.y = __shfl_xor_sync(0xffffffffu, t.y, 1);
+          t.z = __shfl_xor_sync(0xffffffffu, t.z, 1); t.w = __shfl_xor_sync(0xffffffffu, t.w, 1);
+          if (hi1) o[k] = t; else o[k + 1] = t;
+        }
+        const int c = c0 + (lane & 3) * 8;
+        if (c < c_end) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if ((okbits >> ((lane & ~3) + k)) & 1u) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>((uintptr_t)outq[k]) + c) = o[k];
+        }
+      }
+    }
+    if (BULK) {
+      // rows of this warp are 32 consecutive pixels of a dense NHWC map: one contiguous block (valid rows are a prefix)
+      const uint32_t nrow = (uint32_t)__popc(__ballot_sync(0xffffffffu, row_ok));
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && nrow) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out), "r"(stage_smem), "r"(nrow * (uint32_t)Cout * 2u) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (CL == 2 && rank == 1) mbar_arrive_remote(acce0 + 8 * buf, 0);     // the leader's MMA owns the accumulator hand-off
+      else mbar_arrive(acce0 + 8 * buf);
+    }
+  }
+  if (BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Epilogue role (shared by the kernels below): epilogue set `eset` (four warps, one per TMEM lane quarter) drains
+// accumulator `eset` = local tiles eset, eset + 2, ...: tcgen05.ld, + bias (BatchNorm folded) [+ residual] [ReLU]
+// [2x2 max-pool], convert, vectorised NHWC store(s).
+template <int CL>
+__device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_bias, uint32_t tmem_base, uint32_t accf0, uint32_t acce0,
+                                              int warp, int lane, uint32_t eset, int rank, int group0, int ngroups, uint32_t stage_smem = 0u) {
+    if (p.fast_out) {
+#define CTX_EPI_FAST(POOL, RES, BULK) epilogue_fast_role<CL, POOL, RES, BULK>(p, s_bias, tmem_base, accf0, acce0, warp, lane, eset, rank, group0, ngroups, stage_smem)
+      const bool res = p.residual != nullptr;
+      if (p.bulk_out) { if (res) CTX_EPI_FAST(false, true, true); else CTX_EPI_FAST(false, false, true); }
+      else if (p.pool2) CTX_EPI_FAST(true, false, false);           // fused pooling never has a residual (tc_supported)
+      else if (res) CTX_EPI_FAST(false, true, false);
+      else CTX_EPI_FAST(false, false, false);
+#undef CTX_EPI_FAST
+      return;
+    }
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int BN = p.bn;
+    const int r = q * 32 + lane;
+    const bool bf16 = p.is_bf16 != 0;
+    uint32_t lt = eset;
+    for (int tile = group0 + (int)eset * ngroups; tile < p.num_tiles; tile += 2 * ngroups, lt += 2) {
+      const uint32_t buf = lt & 1;
+      const int mg = tile / p.n_tiles_n, n0 = (tile - mg * p.n_tiles_n) * BN, mt = mg * CL + rank;
+      int n_img, pix;
+      const bool row_ok = tile_row_pixel(p, mt, r, n_img, pix);
+      const long long m_lin = (long long)n_img * p.Ho * p.Wo + pix;
+      mbar_wait(accf0 + 8 * buf, (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.acc_stride + ((uint32_t)(q * 32) << 16);
+      if (p.bulk_out) {                                             // the previous tile's bulk store has read the staging rows
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int cb = 0; cb * 32 < BN; ++cb) {
+        const int c0 = n0 + cb * 32;
+        if (c0 >= p.Cout) break;                                   // warp-uniform
+        const int lim = BN - cb * 32;                              // columns of this chunk that belong to the tile
+        uint32_t v[32];
+        tmem_ld32(tmem_d + (uint32_t)(cb * 32), v);
+        tmem_ld_wait();
+        if (!row_ok && !p.pool2) continue;
+        if (p.fast_out) {
+          const CtxOutSeg& sg = p.segs.seg[0];
+          // pool2: row r of the tile is pixel (r / TW, r % TW) of a TW x 128/TW patch, TW = 16 or 8, so the 2 x 2 window
+          // partners are lanes ^1 (x) and ^TW (y) of the same warp; the even/even lane stores the pooled pixel
+          long long opix = pix;
+          bool store = row_ok;
+          if (p.pool2) {
+            const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
+            opix = (long long)(oy >> 1) * (p.Wo >> 1) + (ox >> 1);
+            store = row_ok && !(lane & (1 | p.TW));
+          }
+          uint16_t* out = reinterpret_cast<uint16_t*>(sg.ptr) + (long long)n_img * sg.img_stride + opix * sg.pix_stride + sg.ch_offset;
+          const uint16_t* res = (p.residual && row_ok) ? reinterpret_cast<const uint16_t*>(p.residual) + m_lin * p.res_cstride + p.res_coffset : nullptr;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            const int c = c0 + gq * 8;
+            if (c < p.Cout && gq * 8 < lim) {
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
+              float f[8] = {__uint_as_float(v[gq * 8 + 0]) + b0.x, __uint_as_float(v[gq * 8 + 1]) + b0.y,
+                            __uint_as_float(v[gq * 8 + 2]) + b0.z, __uint_as_float(v[gq * 8 + 3]) + b0.w,
+                            __uint_as_float(v[gq * 8 + 4]) + b1.x, __uint_as_float(v[gq * 8 + 5]) + b1.y,
+                            __uint_as_float(v[gq * 8 + 6]) + b1.z, __uint_as_float(v[gq * 8 + 7]) + b1.w};
+              if (res) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(res + c);
+                const float2 r0 = unpack2(rv.x, bf16), r1 = unpack2(rv.y, bf16), r2 = unpack2(rv.z, bf16), r3 = unpack2(rv.w, bf16);
+                f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y; f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+              }
+              if (p.relu && c < p.relu_cend) {           // relu_cend is a multiple of 8 on this path
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+              }
+              if (p.pool2) {                             // max is exact in any precision: pool the fp32 values
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 1));
+                  f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], p.TW));
+                }
+              }
+              if (store) {
+                uint4 o;
+                o.x = pack2(f[0], f[1], bf16); o.y = pack2(f[2], f[3], bf16); o.z = pack2(f[4], f[5], bf16); o.w = pack2(f[6], f[7], bf16);
+                if (p.bulk_out)
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_smem + (uint32_t)(lane * p.Cout + c) * 2u), "r"(o.x), "r"(o.y),
+                               "r"(o.z), "r"(o.w) : "memory");
+                else
+                  *reinterpret_cast<uint4*>(out + c) = o;
+              }
+            }
+          }
+        } else if (!row_ok) {
+          continue;
+        } else if (p.vec_f32) {
+          // fp32 segments whose boundaries, strides and offsets are multiples of 4 channels (the fused heads)
+#pragma unroll
+          for (int gq = 0; gq < 8; ++gq) {
+            const int c = c0 + gq * 4;
+            if (c < p.Cout && gq * 4 < lim) {
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
+              float4 f = make_float4(__uint_as_float(v[gq * 4 + 0]) + b0.x, __uint_as_float(v[gq * 4 + 1]) + b0.y,
+                                     __uint_as_float(v[gq * 4 + 2]) + b0.z, __uint_as_float(v[gq * 4 + 3]) + b0.w);
+              if (p.relu && c < p.relu_cend) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f); }
+              int sgi = 0;
+              if (p.segs.nseg > 1 && c >= p.segs.seg[1].c_begin) sgi = 1;
+              if (p.segs.nseg > 2 && c >= p.segs.seg[2].c_begin) sgi = 2;
+              const CtxOutSeg& sg = p.segs.seg[sgi];
+              float* out = reinterpret_cast<float*>(sg.ptr) + (long long)n_img * sg.img_stride + (long long)pix * sg.pix_stride +
+                           sg.ch_offset + (c - sg.c_begin);
+              *reinterpret_cast<float4*>(out) = f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = c0 + j;
+            if (c < p.Cout && j < lim) {
+              float f = __uint_as_float(v[j]) + s_bias[c];
+              if (p.residual) f += load_as(p.residual, m_lin * p.res_cstride + p.res_coffset + c, p.res_dtype);
+              if (p.relu && c < p.relu_cend) f = fmaxf(f, 0.f);
+#pragma unroll
+              for (int sgi = 0; sgi < 3; ++sgi) {
+                if (sgi < p.segs.nseg && c >= p.segs.seg[sgi].c_begin && c < p.segs.seg[sgi].c_end) {
+                  const CtxOutSeg& sg = p.segs.seg[sgi];
+                  store_as(sg.ptr, (long long)n_img * sg.img_stride + (long long)pix * sg.pix_stride + sg.ch_offset + (c - sg.c_begin),
+                           sg.dtype, f);
+                }
+              }
+            }
+          }
+        }
+      }
+      if (p.bulk_out) {
+        // rows of this warp are 32 consecutive pixels of a dense NHWC map: one contiguous block (valid rows are a prefix)
+        const uint32_t nrow = (uint32_t)__popc(__ballot_sync(0xffffffffu, row_ok));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && nrow) {
+          const CtxOutSeg& sg = p.segs.seg[0];
+          uint16_t* dst = reinterpret_cast<uint16_t*>(sg.ptr) + (long long)n_img * sg.img_stride + (long long)pix * sg.pix_stride + sg.ch_offset;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(stage_smem), "r"(nrow * (uint32_t)p.Cout * 2u)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CL == 2 && rank == 1) mbar_arrive_remote(acce0 + 8 * buf, 0);     // the leader's MMA owns the accumulator hand-off
+        else mbar_arrive(acce0 + 8 * buf);
+      }
+    }
+    if (p.bulk_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+}  // namespace ctx

@@ -34,6 +34,7 @@ struct Op {
   CtxAttnParams attn;
   void* tc_plan = nullptr;
   void* x3_plan = nullptr;
+  bool fixed_plan = false;       // the tensor-core plan has no alternative tilings (fused conv1_1 + conv1_2)
   struct { const float* in; void* out; int N, C, H, W, dtype; } cvt;
   struct { const float* in; float* out; long long rows; int cols; } sm;
 };
@@ -128,6 +129,16 @@ extern "C" int ctx_prog_add_conv_tc(void* prog, const CtxConvParams* p) {
   CTX_REQUIRE(p, "ctx_prog_add_conv_tc: null params");
   Op op{}; op.kind = OP_CONV_TC; op.conv = *p;
   int rc = ctx_conv2d_tc_plan_create(p, &op.tc_plan);
+  if (rc) return rc;
+  push_op(pr, op);
+  return CTX_OK;
+}
+
+extern "C" int ctx_prog_add_conv_stem2(void* prog, const CtxConvParams* p, const float* stem_in, const void* stem_weight, const float* stem_bias) {
+  PROG_OR_FAIL(prog);
+  CTX_REQUIRE(p, "ctx_prog_add_conv_stem2: null params");
+  Op op{}; op.kind = OP_CONV_TC; op.conv = *p; op.fixed_plan = true;
+  int rc = ctx_conv2d_stem2_plan_create(p, stem_in, stem_weight, stem_bias, &op.tc_plan);
   if (rc) return rc;
   push_op(pr, op);
   return CTX_OK;
@@ -235,7 +246,7 @@ extern "C" int ctx_prog_autotune(void* prog, void* stream, int reps) {
   };
   for (Op& op : pr->ops) {
     ++op_index;
-    if (op.kind != OP_CONV_TC || op.conv.in_nchw) continue;
+    if (op.kind != OP_CONV_TC || op.conv.in_nchw || op.fixed_plan) continue;
     const TuneKey tkey = tune_key(op.conv);
     {
       std::lock_guard<std::mutex> lock(tune_mutex());

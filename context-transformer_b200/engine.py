@@ -151,9 +151,13 @@ class Engine(object):
         return w, b
 
     def _emit_conv(self, name, src, w, b, stride, pad, dil, relu, segs=None, out=None, residual=None, relu_channels=0,
-                   algo_flops=None, in_nchw=False, pool2=False):
+                   algo_flops=None, in_nchw=False, pool2=False, stem=None):
         """w: folded fp32 [Cout,Cin,KH,KW]; b: fp32 [Cout].  segs: list of (tensor, c_begin, c_end, img_stride,
-        pix_stride, ch_offset) for multi-destination epilogues; otherwise writes ``out`` (a View) or a new one."""
+        pix_stride, ch_offset) for multi-destination epilogues; otherwise writes ``out`` (a View) or a new one.
+        ``stem`` = (raw input View, w1, b1): this is conv1_2 and conv1_1 (3 -> 64, folded fp32 weights ``w1`` / bias ``b1``) is
+        evaluated inside the same kernel from the raw fp32 NCHW input (csrc/conv_stem2.cu); ``src`` then only carries the
+        geometry of the activation between the two convs, which never exists in HBM.  Returns None when the fused kernel does
+        not take the geometry."""
         Cout, Cin, KH, KW = w.shape
         assert Cin == src.C, (name, Cin, src.C)
         ph, pw = pad
@@ -195,11 +199,30 @@ class Engine(object):
         if getattr(self, 'trace', None) is not None:
             self.trace.append(dict(name=name, src=src, w=w, b=b, stride=stride, pad=(ph, pw), dil=dil, relu=bool(relu),
                                    relu_channels=int(relu_channels), residual=residual, segs=segs, out=result, pool2=bool(pool2),
-                                   in_nchw=bool(in_nchw), op=self.L.ctx_prog_num_ops(self.prog)))
+                                   in_nchw=bool(in_nchw), op=self.L.ctx_prog_num_ops(self.prog),
+                                   stem=None if stem is None else dict(w=stem[1], b=stem[2])))
         flops = algo_flops if algo_flops is not None else 2.0 * src.N * Ho * Wo * Cout * Cin * KH * KW
         if self.split:
             return self._emit_conv_x3(name, p, src, w, residual, segs, result, flops, in_nchw, pool2)
         use_tc = self.precision != 'fp32' and self.L.ctx_conv2d_tc_supported(C.byref(p)) == 1
+        if stem is not None:
+            x_raw, w1, b1 = stem
+            if not use_tc or self.L.ctx_conv2d_stem2_supported(C.byref(p)) != 1:
+                if getattr(self, 'trace', None) is not None:
+                    self.trace.pop()
+                return None
+            wt1 = torch.zeros(64, 64, dtype=self.act_dtype, device=self.dev)            # k = (ky*3 + kx)*3 + ci, as the STEM mode
+            wt1[:, :27] = w1.permute(0, 2, 3, 1).reshape(64, 27).to(self.act_dtype)
+            wt = torch.zeros((Cout + 15) // 16 * 16, KH * KW, 64, dtype=self.act_dtype, device=self.dev)
+            wt[:Cout] = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin).to(self.act_dtype)
+            bias1 = b1.contiguous()
+            self.keep += [wt1, wt, bias1]
+            p.weight = wt.data_ptr()
+            _lib.check(self.L.ctx_prog_add_conv_stem2(self.prog, C.byref(p), x_raw.buf.data_ptr(), wt1.data_ptr(), bias1.data_ptr()),
+                       'ctx_prog_add_conv_stem2(%s)' % name)
+            flops += 2.0 * src.N * src.H * src.W * 64 * 27
+            self.layers.append((name, 'conv_tc', flops, (src.N, src.H, src.W, Cin, Cout, KH, KW, stride, dil)))
+            return result
         if pool2 and not use_tc:
             return None                     # caller falls back to conv + separate pool
         if in_nchw and not use_tc:
@@ -348,6 +371,26 @@ class Engine(object):
         # relu(ConvLinear(cat) * scale + short): scale folds into the weights, the add + ReLU into the epilogue
         return self._basic_conv(name + '.ConvLinear', m.ConvLinear, cat, residual=short, relu=True, scale=float(m.scale))
 
+    def _stem_pair(self, net, x_raw, w1, b1, relu1, hi):
+        """conv1_1 -> ReLU -> conv1_2 -> ReLU [-> MaxPool2d(2,2)] (vgg() base.0 .. base.4, RFB_Net_vgg.py:323-343) as one kernel
+        in the 16-bit modes: returns (output view, index of the next base module) or None.  CTX_STEM2=0 keeps the two convs apart."""
+        if self.precision not in _TC16 or os.environ.get('CTX_STEM2', '1') == '0' or not relu1 or hi < 4:
+            return None
+        m = net.base[2]
+        if not (isinstance(m, nn.Conv2d) and isinstance(net.base[3], nn.ReLU) and w1.size(0) == 64 and m.in_channels == 64 and m.out_channels <= 64
+                and m.kernel_size == (3, 3) and m.stride == (1, 1) and m.padding == (1, 1) and m.dilation == (1, 1)):
+            return None
+        w2, b2 = self._fold(m, None)
+        pool = net.base[4] if hi > 4 else None
+        pool2 = (isinstance(pool, nn.MaxPool2d) and pool.kernel_size == 2 and pool.stride == 2 and pool.padding == 0
+                 and x_raw.H % 2 == 0 and x_raw.W % 2 == 0)
+        mid = View(torch.empty(0, dtype=self.act_dtype, device=self.dev), x_raw.N, x_raw.H, x_raw.W, 64)     # geometry only
+        out = self._emit_conv('base.0+base.2' + ('+pool4' if pool2 else ''), mid, w2, b2, 1, (1, 1), 1, True, pool2=pool2,
+                              stem=(x_raw, w1, b1))
+        if out is None:
+            return None
+        return out, (5 if pool2 else 4)
+
     # ------------------------------------------------------------------------------------------
     def _compile(self, net):
         B, S = self.batch, net.size
@@ -375,6 +418,10 @@ class Engine(object):
                     relu = k + 1 < len(net.base) and isinstance(net.base[k + 1], nn.ReLU)
                     w, b = self._fold(m, None)
                     if k == 0 and stem_as_gemm:
+                        fused = self._stem_pair(net, x, w, b, relu, hi)
+                        if fused is not None:
+                            x, k = fused
+                            continue
                         x = self._emit_conv('base.0', x, w, b, 1, (1, 1), 1, relu, in_nchw=True)
                         k += 2 if relu else 1
                         continue

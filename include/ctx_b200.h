@@ -142,6 +142,14 @@ int ctx_conv2d_tc_plan_create_tuned(const CtxConvParams* p, int n_tiles_n, int c
 int ctx_conv2d_tc_plan_info(void* plan, int* info8);
 int ctx_conv2d_tc_plan_run(void* plan, void* stream);
 void ctx_conv2d_tc_plan_destroy(void* plan);
+/* conv1_1 -> ReLU -> conv1_2 -> ReLU [-> MaxPool2d(2,2)] of vgg() (models/RFB_Net_vgg.py:323-343, base.0 .. base.4) in ONE kernel:
+ * the 64-channel full-resolution activation between the two convs never exists in HBM.  `conv12` describes conv1_2 exactly as for
+ * ctx_conv2d_tc_plan_create (3x3 / stride 1 / pad 1, Cin = 64, Cout <= 64, one 16-bit output segment, ReLU, optional pool2); its `in`
+ * is ignored.  stem_in = the raw fp32 NCHW network input [N,3,H,W] (W % 4 == 0), stem_weight = conv1_1 packed as for the in_nchw
+ * stem conv (16-bit [64][64]: 27 values k = (ky*3+kx)*3+ci, then zeros), stem_bias = [64] fp32.  Results are bit-identical to the two
+ * separate tensor-core convs.  The plan is run / destroyed with ctx_conv2d_tc_plan_run / _destroy (info8 A mode 6). */
+int ctx_conv2d_stem2_supported(const CtxConvParams* conv12);
+int ctx_conv2d_stem2_plan_create(const CtxConvParams* conv12, const float* stem_in, const void* stem_weight, const float* stem_bias, void** plan_out);
 /* fp32 emulated on the tensor cores (precision 'fp32x3'): activations and weights are fp16 hi/lo plane pairs (p->split = 1),
  * weights [Cout_pad16][2 planes: hi, lo][KH*KW][Cin_pad64] scaled per output channel by a power of two (p->out_scale undoes it).
  * Per 64-channel K-step of one filter tap the kernel chains lo*Whi + hi*Wlo + hi*Whi (12 tcgen05.mma) into a fresh TMEM
@@ -201,6 +209,7 @@ int ctx_prog_create(void** prog_out);
 int ctx_prog_add_conv_simt(void* prog, const CtxConvParams* p);
 int ctx_prog_add_conv_tc(void* prog, const CtxConvParams* p);
 int ctx_prog_add_conv_x3(void* prog, const CtxConvParams* p);
+int ctx_prog_add_conv_stem2(void* prog, const CtxConvParams* conv12, const float* stem_in, const void* stem_weight, const float* stem_bias);
 int ctx_prog_add_pool(void* prog, const CtxPoolParams* p);
 int ctx_prog_add_nchw_to_nhwc(void* prog, const float* in, void* out, int N, int C, int H, int W, int out_dtype);
 int ctx_prog_add_nchw_to_patch27(void* prog, const float* in, void* out, int N, int H, int W, int out_dtype);

@@ -549,11 +549,20 @@ def test_every_conv_of_the_compiled_net_vs_torch(case, precision):
     dt = eng.act_dtype
     half_ulp = {torch.bfloat16: 2.0 ** -8, torch.float16: 2.0 ** -11}[dt]
     worst16, worst32, n16, n32 = 0.0, 0.0, 0, 0
-    assert len(eng.trace) > 60
+    assert len(eng.trace) >= 60
     for t in eng.trace:
         src = t['src']
+        slack = 3e-5
         if t['in_nchw']:
             x = eng.x_in if precision == 'fp32x3' else eng.x_in.to(dt).float()
+        elif t.get('stem') is not None:
+            # conv1_1 evaluated inside the conv1_2 kernel (csrc/conv_stem2.cu): the activation between them is not in HBM, so it
+            # is recomputed here (16-bit operands, rounded to 16 bits as the kernel does).  A value within fp32 summation error of
+            # a rounding boundary may round the other way in the kernel — one 16-bit ulp on one of 576 inputs — hence the wider
+            # slack; test_fused_stem_pair_is_bit_identical pins the fused kernel bit for bit against the two separate convs.
+            x1 = F.conv2d(eng.x_in.to(dt).double(), t['stem']['w'].to(dt).double(), t['stem']['b'].double(), 1, 1)
+            x = F.relu(x1).float().to(dt).float()
+            slack = 3e-4
         else:
             x = src.tensor().float().permute(0, 3, 1, 2)
         w = t['w'] if precision == 'fp32x3' else t['w'].to(dt).float()
@@ -574,7 +583,7 @@ def test_every_conv_of_the_compiled_net_vs_torch(case, precision):
                 worst32, n32 = max(worst32, e), n32 + 1
                 assert e < 2e-6, (t['name'], e)
             else:
-                excess = ((got - y).abs() - half_ulp * y.abs() * 1.0001 - 3e-5 * scale).max().item()
+                excess = ((got - y).abs() - half_ulp * y.abs() * 1.0001 - slack * scale).max().item()
                 worst16, n16 = max(worst16, ((got - y).abs().max() / scale).item()), n16 + 1
                 assert excess <= 0, (t['name'], excess, scale)
         else:
@@ -587,6 +596,31 @@ def test_every_conv_of_the_compiled_net_vs_torch(case, precision):
                 assert e < (2e-6 if precision == 'fp32x3' else 2e-5), (t['name'], e)
     print('%s %s: %d convs; 16-bit outputs (%d) worst |err|/scale %.2e (all within half an ulp); fp32-grade outputs (%d) worst %.2e'
           % (tag, precision, len(eng.trace), n16, worst16, n32, worst32))
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+@pytest.mark.parametrize('case', [NET_CASES[0], NET_CASES[3]], ids=[NET_CASES[0][0], NET_CASES[3][0]])
+def test_fused_stem_pair_is_bit_identical(case, precision, monkeypatch):
+    """conv1_1 + conv1_2 (+ 2x2 pool) in one kernel (csrc/conv_stem2.cu, vgg() base.0 .. base.4) against the two separate
+    tensor-core convs: the pooled conv1_2 activation and every network output must agree bit for bit (300x300: partial tiles on
+    the right / bottom edge; 512x512: full tiles)."""
+    tag, method, phase, setting, size, ncls, batch = case
+    net = _build(case, precision)
+    x = synth.seeded_input(3, size, seed=5).cuda()
+    outs = {}
+    for fused in ('1', '0'):
+        monkeypatch.setenv('CTX_STEM2', fused)
+        eng = Engine(net, 3, precision, DEV, use_graph=False, trace=True)
+        names = [l[0] for l in eng.layers]
+        assert ('base.0+base.2+pool4' in names) == (fused == '1'), names[:3]
+        res = [t.clone() for t in eng.run(x)]
+        first = eng.trace[0 if fused == '1' else 1]['out'].tensor().clone()
+        torch.cuda.synchronize()
+        outs[fused] = (first, res)
+    a, b = outs['1'], outs['0']
+    assert a[0].shape == b[0].shape and torch.equal(a[0].view(torch.int16), b[0].view(torch.int16))
+    for u, v in zip(a[1], b[1]):
+        assert torch.equal(u, v)
 
 
 @pytest.mark.parametrize('precision', ['fp32x3', 'bf16', 'fp16'])
@@ -703,8 +737,9 @@ def test_base_transform_on_device_and_uint8_input():
     got = tr.batch(imgs)
     assert got.dtype == torch.float32 and np.array_equal(got.cpu().numpy(), want)
     assert np.array_equal(tr(imgs[1].numpy()).cpu().numpy(), want[1])
-    with pytest.raises(NotImplementedError):
-        tr.batch(torch.zeros(1, 200, 300, 3, dtype=torch.uint8))
+    other = torch.randint(0, 256, (2, 200, 333, 3), generator=g, dtype=torch.uint8)      # another size: resized on the device
+    want_r = np.stack([np_oracle.base_transform(i.numpy(), 300) for i in other])
+    assert np.array_equal(tr.batch(other).cpu().numpy(), want_r)
     net = _build(NET_CASES[0], 'bf16')
     a = [t.clone() for t in net(torch.from_numpy(want).cuda())]
     b = [t.clone() for t in net(imgs.pin_memory())]
