@@ -91,6 +91,7 @@ SIGNATURES = {
     'ctx_conv2d_x3_plan_info': (_I, [_P, C.POINTER(_I)]),
     'ctx_conv2d_x3_plan_destroy': (None, [_P]),
     'ctx_prog_add_conv_x3': (_I, [_P, C.POINTER(CtxConvParams)]),
+    'ctx_debug_set_conv_timeline': (None, [_P]),
     'ctx_conv2d_stem2_supported': (_I, [C.POINTER(CtxConvParams)]),
     'ctx_conv2d_stem2_plan_create': (_I, [C.POINTER(CtxConvParams), _P, _P, _P, C.POINTER(_P)]),
     'ctx_prog_add_conv_stem2': (_I, [_P, C.POINTER(CtxConvParams), _P, _P, _P]),

@@ -46,13 +46,18 @@ struct TcParams {
   const float* out_scale;
   float trunc_comp;            // expected relative loss of one chain to the tensor core's truncating adder (see conv_x3.cu)
   const float* bias1;          // A_STEM2: bias of the fused first conv (conv1_1), 64 floats
+  long long* dbg;              // development aid (ctx_debug_set_conv_timeline): clock64 stamps of CTA 0, [8 roles][64 tiles][6]; NULL = off
 };
+__device__ __forceinline__ void dbg_stamp(const TcParams& p, int role, uint32_t j, int k) {
+  if (p.dbg && blockIdx.x == 0 && j < 64u) p.dbg[(role * 64 + (int)j) * 6 + k] = clock64();
+}
 
 // A planned tensor-core conv: the TMA descriptors (pointers baked in), the kernel parameters and the launch shape.
 struct TcPlan {
   CUtensorMap tmap_w, tmap_a;
   CUtensorMap tmap_raw, tmap_w1;         // A_STEM2: raw fp32 NCHW input patches, conv1_1 weights
   TcParams p;
+  float bias1_host[64], bias2_host[64];  // A_STEM2: the biases of conv1_1 / conv1_2 (passed to the kernel by value)
   int stages;
   int grid;
   size_t smem;

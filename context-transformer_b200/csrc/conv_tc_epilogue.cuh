@@ -10,21 +10,34 @@ namespace ctx {
 // compile time on fused pooling / residual / bulk-copy output so that the per-chunk code is branch-free: on the layers
 // with little K (the stem, conv1_2) the epilogue warps, not the MMAs, set the pace (ncu source view: ~320 warp
 // instructions per 32-column chunk in the generic path below, most of them flag tests and 64-bit index arithmetic).
-template <int CL, bool POOL, bool RES, bool BULK>
+// 16-bit pair maximum (2 x 2 pooling / ReLU on packed values: rounding is monotonic, so max(round(a), round(b)) == round(max(a, b)))
+__device__ __forceinline__ uint32_t max2_packed(uint32_t a, uint32_t b, bool bf16) {
+  if (bf16) {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// DT: operand type known at compile time (1 bf16, 0 fp16) or -1; NBUF: accumulator buffers (and accf / acce barrier pairs) in rotation;
+// CBN > 0: the layer is ONE N tile of exactly CBN channels (chunk loop unrolled: with `s_bias` in kernel-parameter space the bias
+// becomes constant-bank operands of the FADDs)
+template <int CL, bool POOL, bool RES, bool BULK, int DT = -1, int NBUF = 2, int CBN = 0>
 __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const float* s_bias, uint32_t tmem_base, uint32_t accf0, uint32_t acce0,
                                                    int warp, int lane, uint32_t eset, int rank, int group0, int ngroups, uint32_t stage_smem) {
   const int q = warp & 3;
   const int BN = p.bn, Cout = p.Cout, relu_cend = p.relu ? p.relu_cend : 0;     // ReLU on channels < relu_cend (multiple of 8)
   const int r = q * 32 + lane;
-  const bool bf16 = p.is_bf16 != 0;
+  const bool bf16 = DT < 0 ? p.is_bf16 != 0 : DT == 1;
   uint16_t* const seg_ptr = reinterpret_cast<uint16_t*>(p.segs.seg[0].ptr) + p.segs.seg[0].ch_offset;
   const long long img_stride = p.segs.seg[0].img_stride;
   const int pix_stride = p.segs.seg[0].pix_stride;
   const uint32_t stage_row = stage_smem + (uint32_t)(lane * Cout) * 2u;
   uint32_t lt = eset;
   for (int tile = group0 + (int)eset * ngroups; tile < p.num_tiles; tile += 2 * ngroups, lt += 2) {
-    const uint32_t buf = lt & 1;
-    const int mg = tile / p.n_tiles_n, n0 = (tile - mg * p.n_tiles_n) * BN, mt = mg * CL + rank;
+    const uint32_t buf = lt & (uint32_t)(NBUF - 1);
+    const int mg = CBN ? tile : tile / p.n_tiles_n, n0 = CBN ? 0 : (tile - mg * p.n_tiles_n) * BN, mt = mg * CL + rank;
     int n_img, pix;
     bool row_ok;
     if (BULK) {            // pixel-linear tile of a dense map: the batch is one long pixel row (no per-tile division)
@@ -34,15 +47,14 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
     }
     long long opix = pix;
     bool store = row_ok;
-    if (POOL) {            // row r = pixel (r / TW, r % TW) of the patch: 2 x 2 partners are lanes ^1 and ^TW; even/even lane stores
+    if (POOL) {            // row r = pixel (r / TW, r % TW) of the patch: 2 x 2 partners are lanes ^1 and ^TW (all four store a piece)
       const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
       opix = (long long)(oy >> 1) * (p.Wo >> 1) + (ox >> 1);
-      store = row_ok && !(lane & (1 | p.TW));
     }
     uint16_t* const out = seg_ptr + (long long)n_img * img_stride + opix * pix_stride;
     const uint16_t* res = nullptr;
     if (RES) res = reinterpret_cast<const uint16_t*>(p.residual) + ((long long)n_img * p.Ho * p.Wo + pix) * p.res_cstride + p.res_coffset;
-    const int c_end = min(Cout, n0 + BN);
+    const int c_end = CBN ? CBN : min(Cout, n0 + BN);
     // Transposed stores (plain case): a thread owns one output row, so its 16-byte pieces of a 32-column chunk would go out
     // as four requests touching 32 half-written sectors each.  The four lanes of a quad exchange pieces (4 x 4 transpose, 16
     // shuffles per chunk) so that a request writes, per row, the 64 contiguous bytes of the chunk from four adjacent lanes:
@@ -67,15 +79,15 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
       }
     };
     if (RES) load_res(n0);
-    mbar_wait(accf0 + 8 * buf, (lt >> 1) & 1);
+    mbar_wait(accf0 + 8 * buf, (lt / (uint32_t)NBUF) & 1);
     tc_fence_after();
+    if (q == 0 && lane == 0) dbg_stamp(p, 5 + (int)eset, lt, 0);
     const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.acc_stride + ((uint32_t)(q * 32) << 16);
     if (BULK) {                                                   // the previous tile's bulk store has read the staging rows
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
     }
-#pragma unroll 1
-    for (int c0 = n0; c0 < c_end; c0 += 32) {
+    auto chunk = [&](const int c0) {
       uint32_t v[32];
       tmem_ld32(tmem_d + (uint32_t)(c0 - n0), v);
       uint4 rcur[4];
@@ -85,7 +97,8 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
         if (c0 + 32 < c_end) load_res(c0 + 32);
       }
       tmem_ld_wait();
-      if (BULK && !row_ok) continue;
+      if (q == 0 && lane == 0) dbg_stamp(p, 5 + (int)eset, lt, c0 == n0 ? 2 : 4);
+      if (BULK && !row_ok) return;
       uint4 o[4];
 #pragma unroll
       for (int gq = 0; gq < 4; ++gq) {
@@ -105,19 +118,20 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
               f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y; f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
             }
           }
-          if (c < relu_cend) {                                      // warp-uniform
+          if (POOL) {
+            // ReLU and the 2 x 2 maximum on the PACKED values: rounding to 16 bits is monotonic, so this is bit for bit the
+            // fp32 max followed by the conversion
+            // ReLU rides on the conversion (cvt.rn.relu); the window maximum follows below, for the whole chunk, on packed values
+            if (c < relu_cend) o[gq] = make_uint4(pack2_relu(f[0], f[1], bf16), pack2_relu(f[2], f[3], bf16), pack2_relu(f[4], f[5], bf16), pack2_relu(f[6], f[7], bf16));
+            else o[gq] = make_uint4(pack2(f[0], f[1], bf16), pack2(f[2], f[3], bf16), pack2(f[4], f[5], bf16), pack2(f[6], f[7], bf16));
+          } else {
+            if (c < relu_cend) {                                    // warp-uniform
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-          }
-          if (POOL) {                                               // max is exact in any precision: pool the fp32 values
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], 1));
-              f[e] = fmaxf(f[e], __shfl_xor_sync(0xffffffffu, f[e], p.TW));
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
             }
+            o[gq] = make_uint4(pack2(f[0], f[1], bf16), pack2(f[2], f[3], bf16), pack2(f[4], f[5], bf16), pack2(f[6], f[7], bf16));
           }
-          o[gq] = make_uint4(pack2(f[0], f[1], bf16), pack2(f[2], f[3], bf16), pack2(f[4], f[5], bf16), pack2(f[6], f[7], bf16));
-          if (!TR && store) {
+          if (BULK && store) {
             if (BULK)
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (uint32_t)c * 2u), "r"(o[gq].x), "r"(o[gq].y), "r"(o[gq].z),
                            "r"(o[gq].w) : "memory");
@@ -125,6 +139,32 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
               *reinterpret_cast<uint4*>(out + c) = o[gq];
           }
         }
+      }
+      if (POOL) {
+        // 2 x 2 maximum over lanes ^1 (x) and ^TW (y) as a butterfly that HALVES the data at each step: the even-x lane keeps
+        // the first two 8-channel pieces of the chunk and receives its partner's copies of them, the odd-x lane the last two
+        // (8 shuffles); the same between the two rows leaves every lane of the window with ONE fully pooled piece (4 shuffles):
+        // 12 shuffles per chunk instead of 32, and each lane stores one 16-byte piece — four adjacent lanes write the 64
+        // contiguous bytes of the pooled pixel's chunk.  (Shuffles share the shared-memory datapath with the tensor cores'
+        // operand fetch, which is what bounds the 64-channel full-resolution layers.)
+        const bool odd = (lane & 1) != 0, up = (lane & p.TW) != 0;
+        uint4 x2[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint4 send = odd ? o[k] : o[k + 2], keep = odd ? o[k + 2] : o[k];
+          x2[k].x = max2_packed(keep.x, __shfl_xor_sync(0xffffffffu, send.x, 1), bf16);
+          x2[k].y = max2_packed(keep.y, __shfl_xor_sync(0xffffffffu, send.y, 1), bf16);
+          x2[k].z = max2_packed(keep.z, __shfl_xor_sync(0xffffffffu, send.z, 1), bf16);
+          x2[k].w = max2_packed(keep.w, __shfl_xor_sync(0xffffffffu, send.w, 1), bf16);
+        }
+        const uint4 send = up ? x2[0] : x2[1], keep = up ? x2[1] : x2[0];
+        uint4 y1;
+        y1.x = max2_packed(keep.x, __shfl_xor_sync(0xffffffffu, send.x, p.TW), bf16);
+        y1.y = max2_packed(keep.y, __shfl_xor_sync(0xffffffffu, send.y, p.TW), bf16);
+        y1.z = max2_packed(keep.z, __shfl_xor_sync(0xffffffffu, send.z, p.TW), bf16);
+        y1.w = max2_packed(keep.w, __shfl_xor_sync(0xffffffffu, send.w, p.TW), bf16);
+        const int c = c0 + ((odd ? 2 : 0) + (up ? 1 : 0)) * 8;         // the piece this lane ended up with
+        if (row_ok && c < c_end) *reinterpret_cast<uint4*>(out + c) = y1;
       }
       if (TR) {
         // 4 x 4 transpose of the 16-byte pieces inside each quad: afterwards lane j of the quad holds piece j of rows 0..3
@@ -150,6 +190,14 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
             if ((okbits >> ((lane & ~3) + k)) & 1u) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>((uintptr_t)outq[k]) + c) = o[k];
         }
       }
+      if (q == 0 && lane == 0) dbg_stamp(p, 5 + (int)eset, lt, c0 == n0 ? 3 : 5);
+    };
+    if constexpr (CBN > 0) {                                      // tile width known at compile time: chunks unrolled, bias indices constant
+#pragma unroll
+      for (int c0 = 0; c0 < CBN; c0 += 32) chunk(c0);
+    } else {
+#pragma unroll 1
+      for (int c0 = n0; c0 < c_end; c0 += 32) chunk(c0);
     }
     if (BULK) {
       // rows of this warp are 32 consecutive pixels of a dense NHWC map: one contiguous block (valid rows are a prefix)
@@ -166,6 +214,7 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
     if (lane == 0) {
       if (CL == 2 && rank == 1) mbar_arrive_remote(acce0 + 8 * buf, 0);     // the leader's MMA owns the accumulator hand-off
       else mbar_arrive(acce0 + 8 * buf);
+      if (q == 0) dbg_stamp(p, 5 + (int)eset, lt, 1);
     }
   }
   if (BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

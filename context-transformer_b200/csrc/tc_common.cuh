@@ -163,6 +163,14 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, bool bf16) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// pack2(max(a, 0), max(b, 0)) in ONE instruction (cvt.rn.relu: the clamp is applied to the rounded result, which is the same
+// value — rounding is monotonic and keeps the sign)
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b, bool bf16) {
+  uint32_t r;
+  if (bf16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 __device__ __forceinline__ float2 unpack2(uint32_t u, bool bf16) {
   if (bf16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
   return __half22float2(*reinterpret_cast<__half2*>(&u));

@@ -150,6 +150,8 @@ void ctx_conv2d_tc_plan_destroy(void* plan);
  * separate tensor-core convs.  The plan is run / destroyed with ctx_conv2d_tc_plan_run / _destroy (info8 A mode 6). */
 int ctx_conv2d_stem2_supported(const CtxConvParams* conv12);
 int ctx_conv2d_stem2_plan_create(const CtxConvParams* conv12, const float* stem_in, const void* stem_weight, const float* stem_bias, void** plan_out);
+/* development aid: device buffer (>= 8 * 64 * 6 int64) receiving clock64() stamps of CTA 0 of the fused kernel's roles; NULL disables */
+void ctx_debug_set_conv_timeline(void* device_buffer);
 /* fp32 emulated on the tensor cores (precision 'fp32x3'): activations and weights are fp16 hi/lo plane pairs (p->split = 1),
  * weights [Cout_pad16][2 planes: hi, lo][KH*KW][Cin_pad64] scaled per output channel by a power of two (p->out_scale undoes it).
  * Per 64-channel K-step of one filter tap the kernel chains lo*Whi + hi*Wlo + hi*Whi (12 tcgen05.mma) into a fresh TMEM
