@@ -125,11 +125,10 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
             if (c < relu_cend) o[gq] = make_uint4(pack2_relu(f[0], f[1], bf16), pack2_relu(f[2], f[3], bf16), pack2_relu(f[4], f[5], bf16), pack2_relu(f[6], f[7], bf16));
             else o[gq] = make_uint4(pack2(f[0], f[1], bf16), pack2(f[2], f[3], bf16), pack2(f[4], f[5], bf16), pack2(f[6], f[7], bf16));
           } else {
-            if (c < relu_cend) {                                    // warp-uniform
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-            }
-            o[gq] = make_uint4(pack2(f[0], f[1], bf16), pack2(f[2], f[3], bf16), pack2(f[4], f[5], bf16), pack2(f[6], f[7], bf16));
+            if (c < relu_cend)                                      // warp-uniform; ReLU rides on the conversion
+              o[gq] = make_uint4(pack2_relu(f[0], f[1], bf16), pack2_relu(f[2], f[3], bf16), pack2_relu(f[4], f[5], bf16), pack2_relu(f[6], f[7], bf16));
+            else
+              o[gq] = make_uint4(pack2(f[0], f[1], bf16), pack2(f[2], f[3], bf16), pack2(f[4], f[5], bf16), pack2(f[6], f[7], bf16));
           }
           if (BULK && store) {
             if (BULK)
