@@ -19,6 +19,8 @@
 // conv1_2 reads it — the results are bit-identical to conv_tc_kernel (STEM mode) followed by conv_halo_kernel.
 #include "conv_tc_epilogue.cuh"
 
+#include <stdlib.h>
+
 namespace ctx {
 
 constexpr int S2_THREADS = 736;                    // 23 warps
@@ -279,7 +281,8 @@ int launch_stem2(const TcPlan* pl, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const int pdl = [] { const char* e = getenv("CTX_CONV_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+  attr[0].val.programmaticStreamSerializationAllowed = pdl;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   TcParams prm = pl->p;
