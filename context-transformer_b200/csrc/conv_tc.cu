@@ -475,7 +475,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     }
     __syncwarp();
   } else {
-    epilogue_role<1>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 3) >> 2, 0, group0, ngroups);
+    epilogue_role<1, OCC == 1>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 3) >> 2, 0, group0, ngroups);   // (OCC = 2: 80 registers)
   }
 
   tc_fence_before();

@@ -23,7 +23,10 @@ __device__ __forceinline__ uint32_t max2_packed(uint32_t a, uint32_t b, bool bf1
 // DT: operand type known at compile time (1 bf16, 0 fp16) or -1; NBUF: accumulator buffers (and accf / acce barrier pairs) in rotation;
 // CBN > 0: the layer is ONE N tile of exactly CBN channels (chunk loop unrolled: with `s_bias` in kernel-parameter space the bias
 // becomes constant-bank operands of the FADDs)
-template <int CL, bool POOL, bool RES, bool BULK, int DT = -1, int NBUF = 2, int CBN = 0>
+// BPRE: the bias of a 32-column chunk is fetched while the chunk's TMEM load is in flight (the first one before the accumulator
+// is complete): a shared-memory load issued right before its FADDs waits behind the tensor cores' operand fetch, which keeps the
+// shared-memory pipe busy in exactly the layers whose epilogue sets the pace
+template <int CL, bool POOL, bool RES, bool BULK, int DT = -1, int NBUF = 2, int CBN = 0, bool BPRE = false>
 __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const float* s_bias, uint32_t tmem_base, uint32_t accf0, uint32_t acce0,
                                                    int warp, int lane, uint32_t eset, int rank, int group0, int ngroups, uint32_t stage_smem) {
   const int q = warp & 3;
@@ -79,6 +82,12 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
       }
     };
     if (RES) load_res(n0);
+    float4 bnext[8];
+    auto load_bias = [&](int c0) {                                // s_bias is zero-padded to a whole chunk past Cout
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bnext[k] = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * k);
+    };
+    if (BPRE && !CBN) load_bias(n0);
     mbar_wait(accf0 + 8 * buf, (lt / (uint32_t)NBUF) & 1);
     tc_fence_after();
     if (q == 0 && lane == 0) dbg_stamp(p, 5 + (int)eset, lt, 0);
@@ -96,6 +105,7 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
         for (int gq = 0; gq < 4; ++gq) rcur[gq] = rnext[gq];
         if (c0 + 32 < c_end) load_res(c0 + 32);
       }
+      if (BPRE && !CBN && c0 != n0) load_bias(c0);                 // (the first chunk's was issued before the accumulator wait)
       tmem_ld_wait();
       if (q == 0 && lane == 0) dbg_stamp(p, 5 + (int)eset, lt, c0 == n0 ? 2 : 4);
       if (BULK && !row_ok) return;
@@ -105,8 +115,8 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
         const int c = c0 + gq * 8;
         o[gq] = make_uint4(0u, 0u, 0u, 0u);
         if (c < c_end) {
-          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c);
-          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c + 4);
+          const float4 b0 = (BPRE && !CBN) ? bnext[2 * gq] : *reinterpret_cast<const float4*>(s_bias + c);
+          const float4 b1 = (BPRE && !CBN) ? bnext[2 * gq + 1] : *reinterpret_cast<const float4*>(s_bias + c + 4);
           float f[8] = {__uint_as_float(v[gq * 8 + 0]) + b0.x, __uint_as_float(v[gq * 8 + 1]) + b0.y,
                         __uint_as_float(v[gq * 8 + 2]) + b0.z, __uint_as_float(v[gq * 8 + 3]) + b0.w,
                         __uint_as_float(v[gq * 8 + 4]) + b1.x, __uint_as_float(v[gq * 8 + 5]) + b1.y,
@@ -223,11 +233,11 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
 // Epilogue role (shared by the kernels below): epilogue set `eset` (four warps, one per TMEM lane quarter) drains
 // accumulator `eset` = local tiles eset, eset + 2, ...: tcgen05.ld, + bias (BatchNorm folded) [+ residual] [ReLU]
 // [2x2 max-pool], convert, vectorised NHWC store(s).
-template <int CL>
+template <int CL, bool BPRE = true>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_bias, uint32_t tmem_base, uint32_t accf0, uint32_t acce0,
                                               int warp, int lane, uint32_t eset, int rank, int group0, int ngroups, uint32_t stage_smem = 0u) {
     if (p.fast_out) {
-#define CTX_EPI_FAST(POOL, RES, BULK) epilogue_fast_role<CL, POOL, RES, BULK>(p, s_bias, tmem_base, accf0, acce0, warp, lane, eset, rank, group0, ngroups, stage_smem)
+#define CTX_EPI_FAST(POOL, RES, BULK) epilogue_fast_role<CL, POOL, RES, BULK, -1, 2, 0, BPRE>(p, s_bias, tmem_base, accf0, acce0, warp, lane, eset, rank, group0, ngroups, stage_smem)
       const bool res = p.residual != nullptr;
       if (p.bulk_out) { if (res) CTX_EPI_FAST(false, true, true); else CTX_EPI_FAST(false, false, true); }
       else if (p.pool2) CTX_EPI_FAST(true, false, false);           // fused pooling never has a residual (tc_supported)
