@@ -484,6 +484,135 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------
+// HALO mode on CTA pairs (tune a_mode 5): two CTAs of a cluster take two adjacent 8 x 16 tiles and ONE tcgen05.mma.cta_group::2
+// (M = 256) per K = 16 step serves both.  Each CTA keeps HALF of the layer's weight rows resident in its shared memory (the
+// pair instruction reads N / 2 rows of B from each CTA), so
+//   * layers whose weights are too large for one CTA's shared memory (conv2_2: 288 KB) become resident (144 KB per CTA) instead
+//     of streaming every tap through a ring once per tile — that stream, not the math, bounded them (shared-memory write +
+//     read bandwidth), and
+//   * the operand fetch per MMA drops from A + B to A + B / 2 bytes per CTA: for N <= 128 the single-CTA instruction needs the
+//     full 128 B / clk of shared-memory bandwidth, which it has to share with the patch loads and the epilogue.
+// Hand-offs as in conv_tc_kernel<S, 2>: the peer's TMA loads complete on the LEADER's full barriers, the leader's commits are
+// multicast to both CTAs, the peer's epilogue warps arrive on the leader's accumulator-empty barriers.
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int BN = p.bn, SA = p.sa;
+  const uint32_t B_TAP = (uint32_t)(BN / 2) * TC_BK * 2;       // this CTA's half of one tap's weight tile
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base, sB = smem_base + (uint32_t)(SA * p.a_slot);
+  const uint32_t bars = sB + 9u * (uint32_t)p.cin_blocks * B_TAP;
+  const uint32_t fullA0 = bars, emptyA0 = bars + 8 * SA, fullB = bars + 16 * SA, accf0 = fullB + 16, acce0 = accf0 + 16, tmem_slot = acce0 + 16;   // (s_bias stays 16-byte aligned)
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int group0 = blockIdx.x / 2, ngroups = gridDim.x / 2;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_a);
+  if (warp == 1 && lane == 0) tma_prefetch_desc(&tmap_w);
+  if (warp == 2) {
+    if (lane == 0) {
+      for (int s = 0; s < SA; ++s) { mbar_init(fullA0 + 8 * s, 1); mbar_init(emptyA0 + 8 * s, 1); }
+      mbar_init(fullB, 1);
+      for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 8); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2cta(tmem_slot, 512); tmem_relinquish_2cta();
+  }
+  for (int c = threadIdx.x; c < ((p.Cout + 31) & ~31) + 32; c += HALO_THREADS) s_bias[c] = c < p.Cout ? p.bias[c] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // the peer's barriers exist before any remote arrive / multicast commit
+  tc_fence_after();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int per_img = p.tiles_x * p.tiles_y;
+  if (warp == 0) {
+    // ================= patch producer: this CTA's tile (2 g + rank) of every pair =================
+    if (elect_one()) {
+      const uint32_t a_bytes = (uint32_t)(p.PW * p.PH * 128);
+      uint32_t slot = 0, ph = 1, dst = sA;
+      for (int tile = group0; tile < p.num_tiles; tile += ngroups) {
+        const int mt = tile * 2 + rank;                      // (one N tile: tile == pair index); past the last tile: image index >= N reads as zero
+        const int n_img = mt / per_img, t = mt - n_img * per_img;
+        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+        const int x0 = tx * p.TW - p.pad_w, y0 = ty * p.TH - p.pad_h;
+        for (int cc = 0; cc < p.cin_blocks; ++cc) {
+          mbar_wait(emptyA0 + 8 * slot, ph);
+          if (rank == 0) {
+            mbar_arrive_expect_tx(fullA0 + 8 * slot, 2u * a_bytes);     // the leader's barrier counts the bytes landing in both CTAs
+            tma_load_4d(dst, &tmap_a, p.in_coffset + cc * TC_BK, x0, y0, n_img, fullA0 + 8 * slot);
+          } else {
+            tma_load_4d_2cta(dst, &tmap_a, p.in_coffset + cc * TC_BK, x0, y0, n_img, fullA0 + 8 * slot);
+          }
+          dst += (uint32_t)p.a_slot;
+          if (++slot == (uint32_t)SA) { slot = 0; ph ^= 1u; dst = sA; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= weights: rows [rank BN / 2, +BN / 2) of every (channel block, tap), once =================
+    if (elect_one() && group0 < p.num_tiles) {
+      if (rank == 0) mbar_arrive_expect_tx(fullB, 2u * 9u * (uint32_t)p.cin_blocks * B_TAP);
+      for (int cc = 0; cc < p.cin_blocks; ++cc)
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t dst = sB + (uint32_t)(cc * 9 + tap) * B_TAP;
+          if (rank == 0) tma_load_2d(dst, &tmap_w, (tap * p.cin_blocks + cc) * TC_BK, 0, fullB);
+          else tma_load_2d_2cta(dst, &tmap_w, (tap * p.cin_blocks + cc) * TC_BK, BN / 2, fullB);
+        }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = make_idesc_f16(p.is_bf16 != 0, TC_BM * 2, BN);
+      const uint64_t desc_hi = ((uint64_t)1 << 16) | ((uint64_t)((uint32_t)(p.PW * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint64_t bdesc0 = make_sw128_desc(sB), b_tap = (uint64_t)(B_TAP >> 4);
+      const uint32_t row_step = (uint32_t)(p.dil * 128) >> 4, line_step = (uint32_t)((p.PW - 2) * p.dil * 128) >> 4;
+      uint32_t slot = 0, pha = 0, lt = 0, a_lo = (sA >> 4) & 0x3FFFu;
+      if (group0 < p.num_tiles) mbar_wait(fullB, 0);
+      for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++lt) {
+        const uint32_t buf = lt & 1;
+        mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);            // both CTAs' epilogues have drained it
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.acc_stride;
+        for (int cc = 0; cc < p.cin_blocks; ++cc) {
+          mbar_wait(fullA0 + 8 * slot, pha);
+          tc_fence_after();
+          uint32_t a_tap = a_lo;
+          uint64_t bt = bdesc0 + (uint64_t)(cc * 9) * b_tap;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap, bt += b_tap) {
+            const uint64_t ad = desc_hi | (uint64_t)a_tap;
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) umma_f16_2cta(tmem_d, ad + 2 * k, bt + 2 * k, idesc, (cc | tap | k) ? 1u : 0u);
+            a_tap += (tap % 3 == 2) ? line_step : row_step;
+          }
+          umma_commit_2cta(emptyA0 + 8 * slot, (uint16_t)3);
+          a_lo += (uint32_t)p.a_slot >> 4;
+          if (++slot == (uint32_t)SA) { slot = 0; pha ^= 1u; a_lo = (sA >> 4) & 0x3FFFu; }
+        }
+        umma_commit_2cta(accf0 + 8 * buf, (uint16_t)3);
+      }
+    }
+    __syncwarp();
+  } else {
+    epilogue_role<2>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 3) >> 2, rank, group0, ngroups);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // no CTA exits while its peer can still signal it
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_2cta(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------------------------------------------
 static int tc_supported(const CtxConvParams* p) {
   if (!p) return 0;
   if (p->in_nchw)       // stem mode: raw fp32 NCHW input, 3x3 / s1 / p1, 16-bit output
@@ -539,6 +668,26 @@ static int launch_halo(const TcPlan* pl, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   CTX_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_halo_kernel<OCC>, pl->tmap_w, pl->tmap_a, pl->p));
+  CTX_LAUNCH_CHECK();
+  return CTX_OK;
+}
+
+static int launch_halo_pair(const TcPlan* pl, cudaStream_t st) {
+  CTX_CUDA_TRY(cudaFuncSetAttribute(conv_halo_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)pl->grid);
+  cfg.blockDim = dim3(HALO_THREADS);
+  cfg.dynamicSmemBytes = pl->smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  static const int pdl = [] { const char* e = getenv("CTX_CONV_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+  attr[0].val.programmaticStreamSerializationAllowed = pdl;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  CTX_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_halo_pair_kernel, pl->tmap_w, pl->tmap_a, pl->p));
   CTX_LAUNCH_CHECK();
   return CTX_OK;
 }
@@ -614,7 +763,7 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
                        (!p->pool2 || (((p->Ho | p->Wo) & 1) == 0 && p->Cin % 64 == 0));
   t.occ = 1; t.acc_stride = 256;
   t.resident = 0;
-  if ((tune_amode == 2 || tune_amode == 3 || tune_amode == 4) && halo_ok) { t.a_mode = A_HALO; tw = 8; th = 16; }
+  if ((tune_amode == 2 || tune_amode == 3 || tune_amode == 4 || tune_amode == 5) && halo_ok) { t.a_mode = A_HALO; tw = 8; th = 16; }
   else if (p->in_nchw) t.a_mode = A_STEM;
   else if (tune_amode == 0 && !p->pool2) t.a_mode = A_GATHER;
   else if (flat_eligible(p)) { t.a_mode = A_TMA; tw = 128; th = 1; }
@@ -633,6 +782,7 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
     const char* e = getenv("CTX_CONV_CLUSTER");
     const bool want2 = tune_cluster ? tune_cluster == 2 : (e && e[0] == '2');
     t.cluster = (want2 && m_tiles >= 2 && t.bn % 32 == 0 && t.bn >= 128 && t.a_mode != A_HALO) ? 2 : 1;
+    if (t.a_mode == A_HALO && tune_amode == 5) t.cluster = 2;          // CTA pairs with resident half-weights (checked below)
   }
   t.num_tiles = cdiv(m_tiles, t.cluster) * t.n_tiles_n;
   const int stage_bytes = TC_A_STAGE + (t.bn / t.cluster) * TC_BK * 2;
@@ -657,6 +807,16 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
     // barrier wait instead of four (the MMA thread's issue loop is the pace there); an explicit commit group keeps 1 tap
     const int clog_rule = t.clog;
     t.sa = 0;
+    if (tune_amode == 5) {                  // CTA pairs: each CTA keeps half of the weight rows resident (conv_halo_pair_kernel)
+      const size_t wbytes = (size_t)9 * t.cin_blocks * (t.bn / 2) * TC_BK * 2, budget = 232448 - 1024 - bias_bytes - 8 * (2 * 6 + 8) - 64;
+      if (t.n_tiles_n == 1 && t.bn % 32 == 0 && t.bn >= 64 && m_tiles >= 2 && wbytes + 3 * (size_t)t.a_slot <= budget) {
+        t.resident = 1; t.occ = 1; t.acc_stride = 256; t.tps = 1; t.clog = 0;
+        t.sb = 9 * t.cin_blocks;
+        t.sa = (int)std::min<size_t>(6, (budget - wbytes) / t.a_slot);
+      } else {
+        delete pl; set_error("conv_tc: HALO pair mode does not apply (tile %d, %d channel blocks)", t.bn, t.cin_blocks); return CTX_ERR_UNSUPPORTED;
+      }
+    }
     if (tune_amode == 4) {                  // weights resident: the whole layer is one N tile and fits beside >= 3 patches
       const size_t wbytes = (size_t)9 * t.cin_blocks * t.bn * TC_BK * 2, budget = 232448 - 1024 - bias_bytes - 8 * (2 * 6 + 2 * 18 + 4) - 64;
       if (t.n_tiles_n == 1 && t.cin_blocks <= 2 && wbytes + 3 * (size_t)t.a_slot <= budget) {
@@ -686,7 +846,7 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
     if (!t.sa) { delete pl; set_error("conv_tc: HALO mode does not fit shared memory (dilation %d, tile width %d)", p->dil, t.bn); return CTX_ERR_UNSUPPORTED; }
     pl->stages = t.sb;
   }
-  pl->smem = t.a_mode == A_HALO ? (size_t)t.sa * t.a_slot + (size_t)t.sb * t.tps * t.bn * TC_BK * 2 + 8 * (2 * t.sa + 2 * t.sb + 4) + 64 + bias_bytes + 1024 :
+  pl->smem = t.a_mode == A_HALO ? (size_t)t.sa * t.a_slot + (size_t)t.sb * t.tps * (t.bn / t.cluster) * TC_BK * 2 + 8 * (2 * t.sa + 2 * t.sb + 4) + 64 + bias_bytes + 1024 :
              (size_t)pl->stages * stage_bytes + 24 * pl->stages + 64 + 4 * (((size_t)p->Cout + 31) / 32 * 32 + 32) + 1024;
   // bulk-copy epilogue: pixel-linear tiles (stem / gather / flat), the whole pixel in one tile, dense output map, small rows
   if (t.fast_out && (t.a_mode == A_STEM || t.a_mode == A_GATHER || (t.a_mode == A_TMA && t.flat)) && t.n_tiles_n == 1 && t.cluster == 1 &&
@@ -727,7 +887,7 @@ extern "C" int ctx_conv2d_tc_plan_info(void* plan, int* info8) {
   const TcPlan* pl = (const TcPlan*)plan;
   int* info6 = info8;
   info8[6] = pl->p.a_mode == A_HALO && pl->p.tps == 3 ? 3 : 1 << pl->p.clog; info8[7] = pl->p.TW * 1000 + pl->p.TH;
-  info6[0] = pl->p.bn; info6[1] = pl->p.n_tiles_n; info6[2] = pl->p.cluster; info6[3] = pl->p.a_mode == A_STEM2 ? 6 : pl->p.a_mode == A_HALO && pl->p.resident ? 5 : (pl->p.a_mode == A_HALO && pl->p.occ == 2 ? 4 : pl->p.a_mode); info6[4] = pl->stages; info6[5] = pl->grid;
+  info6[0] = pl->p.bn; info6[1] = pl->p.n_tiles_n; info6[2] = pl->p.cluster; info6[3] = pl->p.a_mode == A_STEM2 ? 6 : pl->p.a_mode == A_HALO && pl->p.cluster == 2 ? 7 : pl->p.a_mode == A_HALO && pl->p.resident ? 5 : (pl->p.a_mode == A_HALO && pl->p.occ == 2 ? 4 : pl->p.a_mode); info6[4] = pl->stages; info6[5] = pl->grid;
   return CTX_OK;
 }
 
@@ -736,6 +896,7 @@ extern "C" int ctx_conv2d_tc_plan_run(void* plan, void* stream) {
   const TcPlan* pl = (const TcPlan*)plan;
   cudaStream_t st = (cudaStream_t)stream;
   if (pl->p.a_mode == A_STEM2) return launch_stem2(pl, st);
+  if (pl->p.a_mode == A_HALO && pl->p.cluster == 2) return launch_halo_pair(pl, st);
   if (pl->p.a_mode == A_HALO) return pl->p.occ == 2 ? launch_halo<2>(pl, st) : launch_halo<1>(pl, st);
   if (pl->p.cluster == 2) {
     if (pl->stages == 8) return launch_tc<8, 2>(pl, st);

@@ -292,7 +292,7 @@ extern "C" int ctx_prog_autotune(void* prog, void* stream, int reps) {
     // pass 1: tile width x CTA pairs x A-operand mode, commit group by rule; pass 2: commit group on the winner
     for (int dn = 0; dn < 6 && !rc; ++dn) {
       const int n = dn < 4 ? n0 + dn : n0 * (dn == 4 ? 2 : 3);
-      for (int amode = -1; amode <= 4 && !rc; ++amode)
+      for (int amode = -1; amode <= 5 && !rc; ++amode)
         for (int cl = 1; cl <= 2 && !rc; ++cl)
           if (consider(n, cl, amode, 0)) { best_n = n; best_cl = cl; best_amode = amode; }
     }
