@@ -721,7 +721,7 @@ def main():
     if n_gpus == 1 and not args.no_extra and size == 300 and B == BATCH_PER_GPU:
         del w, eng
         torch.cuda.empty_cache()
-        k = max(5, args.steps // 4)
+        k = max(10, args.steps // 2)           # (the streaming e2e leg keeps two batches in flight: a handful of steps would mostly time its fill and drain)
         configs = {}
         for key, (sz, prec, bb, nk) in (('512_fp16_b16_softnms', (512, 'fp16', 16, 'linear')), ('300_fp32x3_b32', (300, 'fp32x3', 32, 'hard'))):
             if prec == args.precision and sz == size:
