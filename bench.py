@@ -355,7 +355,7 @@ def measure(w, steps, warmup, world, rank, full=True, layers_path=None, quick=Fa
     # CTX_BENCH_WORKERS=2: two replicas of the compiled network (same weights, own activation buffers) on two streams take
     # alternate batches, so that the latency-bound end of one forward (late pyramid levels, Context-Transformer) runs beside
     # the tensor-bound beginning of the next
-    workers = int(os.environ.get('CTX_BENCH_WORKERS', '2'))          # measured: 10.30 k img/s with one replica, 10.62 k with two
+    workers = int(os.environ.get('CTX_BENCH_WORKERS', '1'))          # two replicas: 7.0 .. 10.6 k img/s from run to run (one: 9.8 .. 10.3 k) — two graphs of persistent kernels with static tile lists stall each other whenever they collide; kept as an experiment
     nets, wstreams = [net], [None]
     if workers == 2:
         import copy
