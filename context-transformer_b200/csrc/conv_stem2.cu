@@ -270,6 +270,7 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 }
 
 static long long* g_conv_timeline = nullptr;
+long long* conv_timeline_ptr() { return g_conv_timeline; }
 
 int launch_stem2(const TcPlan* pl, cudaStream_t st) {
   auto kernel = pl->p.is_bf16 ? conv_stem2_kernel<true> : conv_stem2_kernel<false>;

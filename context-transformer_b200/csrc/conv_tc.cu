@@ -332,7 +332,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 // OCC = 2 (tiles <= 128 wide): two CTAs per SM, each with half of TMEM and of shared memory — two MMA-issuing threads per
 // SM, because with narrow tiles the issue rate of ONE thread (~50-90 clk per tcgen05.mma against a tensor-pipe floor of
 // 32 / 64 clk for N = 64 / 128) is what bounds the kernel.
-template <int OCC>
+template <int OCC, int NBUF>      // CTAs per SM; accumulators in rotation (4 for tiles <= 128 wide with the lean epilogue: the epilogue of a
+                                  // tile takes longer than its MMAs there, and with two accumulators the MMA thread waited for it every tile —
+                                  // clock64 timeline, profiles/dev/halo_timeline.py)
 __global__ void __launch_bounds__(HALO_THREADS, OCC)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -342,7 +344,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   const uint32_t sA = smem_base, sB = smem_base + (uint32_t)(SA * p.a_slot);
   const uint32_t bars = sB + (uint32_t)SB * B_STAGE;
   const uint32_t fullA0 = bars, emptyA0 = bars + 8 * SA, fullB0 = bars + 16 * SA, emptyB0 = fullB0 + 8 * SB, accf0 = emptyB0 + 8 * SB,
-                 acce0 = accf0 + 16, tmem_slot = acce0 + 16;
+                 acce0 = accf0 + 8 * NBUF, tmem_slot = acce0 + 8 * NBUF;
   float* s_bias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -355,7 +357,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) { mbar_init(fullA0 + 8 * s, 1); mbar_init(emptyA0 + 8 * s, 1); }
       for (int s = 0; s < SB; ++s) { mbar_init(fullB0 + 8 * s, 1); mbar_init(emptyB0 + 8 * s, 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 4); }
+      for (int b = 0; b < NBUF; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 4); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -385,6 +387,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const int x0 = tx * p.TW - p.pad_w, y0 = ty * p.TH - p.pad_h;
         for (int cc = 0; cc < p.cin_blocks; ++cc) {
           mbar_wait(emptyA0 + 8 * slot, ph);
+          dbg_stamp(p, 0, (uint32_t)((tile - group0) / ngroups), cc == 0 ? 0 : 1);
           mbar_arrive_expect_tx(fullA0 + 8 * slot, a_bytes);
           tma_load_4d(dst, &tmap_a, p.in_coffset + cc * TC_BK, x0, y0, n_img, fullA0 + 8 * slot);
           dst += (uint32_t)p.a_slot;
@@ -433,12 +436,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       uint64_t bd = bdesc0;
       if (p.resident && group0 < p.num_tiles) mbar_wait(fullB0, 0);
       for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++lt) {
-        const uint32_t buf = lt & 1;
-        mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);
+        const uint32_t buf = lt & (uint32_t)(NBUF - 1);
+        mbar_wait(acce0 + 8 * buf, ((lt / (uint32_t)NBUF) & 1) ^ 1);
         tc_fence_after();
+        dbg_stamp(p, 2, lt, 0);
         const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.acc_stride;
         for (int cc = 0; cc < p.cin_blocks; ++cc) {
           mbar_wait(fullA0 + 8 * slot, pha);
+          if (cc == 0) dbg_stamp(p, 2, lt, 1);
           uint32_t a_tap = a_lo;                                // window of tap (0, 0); +dil rows per kx, +dil patch lines per ky
           int kx = 0;
           if (p.resident) {
@@ -471,11 +476,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           if (++slot == (uint32_t)SA) { slot = 0; pha ^= 1u; a_lo = (sA >> 4) & 0x3FFFu; }
         }
         umma_commit(accf0 + 8 * buf);
+        dbg_stamp(p, 2, lt, 2);
       }
     }
     __syncwarp();
   } else {
-    epilogue_role<1, OCC == 1>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 3) >> 2, 0, group0, ngroups);   // (OCC = 2: 80 registers)
+    epilogue_role<1, OCC == 1, NBUF>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 3) >> 2, 0, group0, ngroups);   // (OCC = 2: 80 registers)
   }
 
   tc_fence_before();
@@ -653,9 +659,9 @@ static int launch_tc(const TcPlan* pl, cudaStream_t st) {
   return CTX_OK;
 }
 
-template <int OCC>
+template <int OCC, int NBUF>
 static int launch_halo(const TcPlan* pl, cudaStream_t st) {
-  CTX_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+  CTX_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<OCC, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)pl->grid);
   cfg.blockDim = dim3(HALO_THREADS);
@@ -667,7 +673,9 @@ static int launch_halo(const TcPlan* pl, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = pdl;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CTX_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_halo_kernel<OCC>, pl->tmap_w, pl->tmap_a, pl->p));
+  TcParams prm = pl->p;
+  prm.dbg = conv_timeline_ptr();
+  CTX_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_halo_kernel<OCC, NBUF>, pl->tmap_w, pl->tmap_a, prm));
   CTX_LAUNCH_CHECK();
   return CTX_OK;
 }
@@ -844,6 +852,7 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
       }
     }
     if (!t.sa) { delete pl; set_error("conv_tc: HALO mode does not fit shared memory (dilation %d, tile width %d)", p->dil, t.bn); return CTX_ERR_UNSUPPORTED; }
+    if (t.occ == 1 && t.cluster == 1 && t.bn <= 128 && t.fast_out) t.acc_stride = 128;        // four accumulators in rotation (conv_halo_kernel<1, 4>)
     pl->stages = t.sb;
   }
   pl->smem = t.a_mode == A_HALO ? (size_t)t.sa * t.a_slot + (size_t)t.sb * t.tps * (t.bn / t.cluster) * TC_BK * 2 + 8 * (2 * t.sa + 2 * t.sb + 4) + 64 + bias_bytes + 1024 :
@@ -897,7 +906,7 @@ extern "C" int ctx_conv2d_tc_plan_run(void* plan, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (pl->p.a_mode == A_STEM2) return launch_stem2(pl, st);
   if (pl->p.a_mode == A_HALO && pl->p.cluster == 2) return launch_halo_pair(pl, st);
-  if (pl->p.a_mode == A_HALO) return pl->p.occ == 2 ? launch_halo<2>(pl, st) : launch_halo<1>(pl, st);
+  if (pl->p.a_mode == A_HALO) return pl->p.occ == 2 ? launch_halo<2, 2>(pl, st) : (pl->p.acc_stride == 128 ? launch_halo<1, 4>(pl, st) : launch_halo<1, 2>(pl, st));
   if (pl->p.cluster == 2) {
     if (pl->stages == 8) return launch_tc<8, 2>(pl, st);
     if (pl->stages == 6) return launch_tc<6, 2>(pl, st);

@@ -63,6 +63,7 @@ struct TcPlan {
   size_t smem;
 };
 int launch_stem2(const TcPlan* pl, cudaStream_t st);      // conv_stem2.cu
+long long* conv_timeline_ptr();                           // conv_stem2.cu: development aid (ctx_debug_set_conv_timeline)
 
 // output pixel (image, linear pixel index, validity) of row r of M-tile mt
 __device__ __forceinline__ bool tile_row_pixel(const TcParams& p, int mt, int r, int& n_img, int& pix) {

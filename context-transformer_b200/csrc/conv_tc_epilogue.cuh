@@ -233,11 +233,11 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
 // Epilogue role (shared by the kernels below): epilogue set `eset` (four warps, one per TMEM lane quarter) drains
 // accumulator `eset` = local tiles eset, eset + 2, ...: tcgen05.ld, + bias (BatchNorm folded) [+ residual] [ReLU]
 // [2x2 max-pool], convert, vectorised NHWC store(s).
-template <int CL, bool BPRE = true>
+template <int CL, bool BPRE = true, int NBUF = 2>       // NBUF = 4 (fast_out only): four accumulators in rotation
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_bias, uint32_t tmem_base, uint32_t accf0, uint32_t acce0,
                                               int warp, int lane, uint32_t eset, int rank, int group0, int ngroups, uint32_t stage_smem = 0u) {
     if (p.fast_out) {
-#define CTX_EPI_FAST(POOL, RES, BULK) epilogue_fast_role<CL, POOL, RES, BULK, -1, 2, 0, BPRE>(p, s_bias, tmem_base, accf0, acce0, warp, lane, eset, rank, group0, ngroups, stage_smem)
+#define CTX_EPI_FAST(POOL, RES, BULK) epilogue_fast_role<CL, POOL, RES, BULK, -1, NBUF, 0, BPRE>(p, s_bias, tmem_base, accf0, acce0, warp, lane, eset, rank, group0, ngroups, stage_smem)
       const bool res = p.residual != nullptr;
       if (p.bulk_out) { if (res) CTX_EPI_FAST(false, true, true); else CTX_EPI_FAST(false, false, true); }
       else if (p.pool2) CTX_EPI_FAST(true, false, false);           // fused pooling never has a residual (tc_supported)
