@@ -508,7 +508,8 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base, sB = smem_base + (uint32_t)(SA * p.a_slot);
   const uint32_t bars = sB + 9u * (uint32_t)p.cin_blocks * B_TAP;
-  const uint32_t fullA0 = bars, emptyA0 = bars + 8 * SA, fullB = bars + 16 * SA, accf0 = fullB + 16, acce0 = accf0 + 16, tmem_slot = acce0 + 16;   // (s_bias stays 16-byte aligned)
+  constexpr int NBUF = 4;                                   // accumulators in rotation (BN <= 128: 4 x 128 TMEM columns)
+  const uint32_t fullA0 = bars, emptyA0 = bars + 8 * SA, fullB = bars + 16 * SA, accf0 = fullB + 16, acce0 = accf0 + 8 * NBUF, tmem_slot = acce0 + 8 * NBUF;   // (s_bias stays 16-byte aligned)
   float* s_bias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -521,7 +522,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) { mbar_init(fullA0 + 8 * s, 1); mbar_init(emptyA0 + 8 * s, 1); }
       mbar_init(fullB, 1);
-      for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 8); }
+      for (int b = 0; b < NBUF; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 8); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -584,8 +585,8 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
       uint32_t slot = 0, pha = 0, lt = 0, a_lo = (sA >> 4) & 0x3FFFu;
       if (group0 < p.num_tiles) mbar_wait(fullB, 0);
       for (int tile = group0; tile < p.num_tiles; tile += ngroups, ++lt) {
-        const uint32_t buf = lt & 1;
-        mbar_wait(acce0 + 8 * buf, ((lt >> 1) & 1) ^ 1);            // both CTAs' epilogues have drained it
+        const uint32_t buf = lt & (uint32_t)(NBUF - 1);
+        mbar_wait(acce0 + 8 * buf, ((lt / (uint32_t)NBUF) & 1) ^ 1);            // both CTAs' epilogues have drained it
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * (uint32_t)p.acc_stride;
         for (int cc = 0; cc < p.cin_blocks; ++cc) {
@@ -609,7 +610,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     }
     __syncwarp();
   } else {
-    epilogue_role<2>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 3) >> 2, rank, group0, ngroups);
+    epilogue_role<2, true, NBUF>(p, s_bias, tmem_base, accf0, acce0, warp, lane, (uint32_t)(warp - 3) >> 2, rank, group0, ngroups);
   }
 
   tc_fence_before();
@@ -817,8 +818,8 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
     t.sa = 0;
     if (tune_amode == 5) {                  // CTA pairs: each CTA keeps half of the weight rows resident (conv_halo_pair_kernel)
       const size_t wbytes = (size_t)9 * t.cin_blocks * (t.bn / 2) * TC_BK * 2, budget = 232448 - 1024 - bias_bytes - 8 * (2 * 6 + 8) - 64;
-      if (t.n_tiles_n == 1 && t.bn % 32 == 0 && t.bn >= 64 && m_tiles >= 2 && wbytes + 3 * (size_t)t.a_slot <= budget) {
-        t.resident = 1; t.occ = 1; t.acc_stride = 256; t.tps = 1; t.clog = 0;
+      if (t.n_tiles_n == 1 && t.bn % 32 == 0 && t.bn >= 64 && t.bn <= 128 && t.fast_out && m_tiles >= 2 && wbytes + 3 * (size_t)t.a_slot <= budget) {
+        t.resident = 1; t.occ = 1; t.acc_stride = 128; t.tps = 1; t.clog = 0;           // four accumulators of 128 TMEM columns
         t.sb = 9 * t.cin_blocks;
         t.sa = (int)std::min<size_t>(6, (budget - wbytes) / t.a_slot);
       } else {
