@@ -329,6 +329,39 @@ softmax_lastdim_kernel(const float* __restrict__ in, float* __restrict__ out, lo
   }
 }
 
+// rows of at most 32 columns (the class dimension: 2, 20, 21): the row lives in registers, every exponential is evaluated once
+// (same operations on the same values as the generic kernel: identical results); 128-bit accesses when COLS % 4 == 0
+template <int COLS>
+__global__ void __launch_bounds__(256)
+softmax_lastdim_small_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    float x[COLS];
+    if (COLS % 4 == 0) {
+      const float4* src = reinterpret_cast<const float4*>(in + r * COLS);
+#pragma unroll
+      for (int c = 0; c < COLS / 4; ++c) { const float4 v = src[c]; x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) x[c] = in[r * COLS + c];
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) m = fmaxf(m, x[c]);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) { x[c] = expf(x[c] - m); s += x[c]; }
+    const float inv = 1.0f / s;
+    if (COLS % 4 == 0) {
+      float4* dst = reinterpret_cast<float4*>(out + r * COLS);
+#pragma unroll
+      for (int c = 0; c < COLS / 4; ++c) dst[c] = make_float4(x[4 * c] * inv, x[4 * c + 1] * inv, x[4 * c + 2] * inv, x[4 * c + 3] * inv);
+    } else {
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) out[r * COLS + c] = x[c] * inv;
+    }
+  }
+}
+
 static int validate_conv(const CtxConvParams* p) {
   CTX_REQUIRE(p, "conv: null params");
   CTX_REQUIRE(!p->pool2, "conv (CUDA-core path): fused pooling is a tensor-core-path feature");
@@ -484,7 +517,11 @@ int softmax_launch(const float* in, float* out, long long rows, int cols, cudaSt
   CTX_REQUIRE(in && out && rows >= 0 && cols > 0, "softmax: bad arguments");
   if (rows == 0) return CTX_OK;
   int blocks = (int)std::min<long long>((rows + 255) / 256, 148LL * 32);
-  softmax_lastdim_kernel<<<blocks, 256, 0, st>>>(in, out, rows, cols);
+  const bool al = ((uintptr_t)in) % 16 == 0 && ((uintptr_t)out) % 16 == 0;
+  if (cols == 20 && al) softmax_lastdim_small_kernel<20><<<blocks, 256, 0, st>>>(in, out, rows);
+  else if (cols == 21) softmax_lastdim_small_kernel<21><<<blocks, 256, 0, st>>>(in, out, rows);
+  else if (cols == 2) softmax_lastdim_small_kernel<2><<<blocks, 256, 0, st>>>(in, out, rows);
+  else softmax_lastdim_kernel<<<blocks, 256, 0, st>>>(in, out, rows, cols);
   CTX_LAUNCH_CHECK();
   return CTX_OK;
 }
