@@ -169,16 +169,14 @@ maxpool_nhwc_kernel(CtxPoolParams p) {
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 maxpool_nhwc_vec8_kernel(CtxPoolParams p) {
+  // grid: x over (output column, 8-channel group), y over (image, output row) — no 64-bit division per element (four of them
+  // per element made this kernel instruction-bound at half of the memory rate)
   const int C8 = p.C >> 3;
-  const long long total = (long long)p.N * p.Ho * p.Wo * C8;
   const uint16_t* in = reinterpret_cast<const uint16_t*>(p.in);
   uint16_t* out = reinterpret_cast<uint16_t*>(p.out);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C8) * 8;
-    long long r = i / C8;
-    const int ox = (int)(r % p.Wo); r /= p.Wo;
-    const int oy = (int)(r % p.Ho);
-    const int n = (int)(r / p.Ho);
+  const int n = (int)blockIdx.y / p.Ho, oy = (int)blockIdx.y - n * p.Ho;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.Wo * C8; i += gridDim.x * blockDim.x) {
+    const int ox = i / C8, c = (i - ox * C8) * 8;
     const int y0 = max(oy * p.stride - p.pad, 0), y1 = min(oy * p.stride - p.pad + p.k, p.H);
     const int x0 = max(ox * p.stride - p.pad, 0), x1 = min(ox * p.stride - p.pad + p.k, p.W);
     float m[8];
@@ -465,9 +463,10 @@ int maxpool_launch(const CtxPoolParams* p, cudaStream_t st) {
   const bool vec = p->dtype != CTX_F32 && p->C % 8 == 0 && p->in_pix_stride % 8 == 0 && p->out_pix_stride % 8 == 0 &&
                    p->in_img_stride % 8 == 0 && p->out_img_stride % 8 == 0 && ((uintptr_t)p->in) % 16 == 0 && ((uintptr_t)p->out) % 16 == 0;
   if (vec) {
-    int blocks = (int)std::min<long long>((total / 8 + 255) / 256, 148LL * 32);
-    if (p->dtype == CTX_BF16) maxpool_nhwc_vec8_kernel<true><<<blocks, 256, 0, st>>>(*p);
-    else maxpool_nhwc_vec8_kernel<false><<<blocks, 256, 0, st>>>(*p);
+    CTX_REQUIRE((long long)p->N * p->Ho <= 65535, "maxpool: too many output rows for the (image, row) grid dimension");
+    const dim3 grid((unsigned)((p->Wo * (p->C / 8) + 255) / 256), (unsigned)(p->N * p->Ho));
+    if (p->dtype == CTX_BF16) maxpool_nhwc_vec8_kernel<true><<<grid, 256, 0, st>>>(*p);
+    else maxpool_nhwc_vec8_kernel<false><<<grid, 256, 0, st>>>(*p);
     CTX_LAUNCH_CHECK();
     return CTX_OK;
   }
