@@ -72,7 +72,7 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
       for (int s = 0; s < S2_SA2; ++s) {
         mbar_init(a2_full0 + 8 * s, S2_MIDS); mbar_init(a2_empty0 + 8 * s, 1);
-        mbar_init(accf0 + 8 * s, 1); mbar_init(acce0 + 8 * s, 4);
+        mbar_init(accf0 + 8 * s, 1); mbar_init(acce0 + 8 * s, 4);          // (the epilogue sets take alternate tiles)
       }
       mbar_init(w_full, 1);
       fence_barrier_init();
@@ -163,8 +163,8 @@ conv_stem2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     __syncwarp();
   } else if (warp >= 12 && warp < 20) {
     // single 16-bit segment, no residual (checked by the plan): the lean epilogue, with or without the fused 2 x 2 pool
-    if (p.pool2) epilogue_fast_role<1, true, false, false, BF16 ? 1 : 0, S2_SA2, 64>(p, bias2.v, tmem_base + S2_D_COLS, accf0, acce0, warp, lane, (uint32_t)(warp - 12) >> 2, 0, group0, ngroups, 0u);
-    else epilogue_fast_role<1, false, false, false, BF16 ? 1 : 0, S2_SA2, 64>(p, bias2.v, tmem_base + S2_D_COLS, accf0, acce0, warp, lane, (uint32_t)(warp - 12) >> 2, 0, group0, ngroups, 0u);
+    if (p.pool2) epilogue_fast_role<1, true, false, false, BF16 ? 1 : 0, S2_SA2, 64, false, false>(p, bias2.v, tmem_base + S2_D_COLS, accf0, acce0, warp, lane, (uint32_t)(warp - 12) >> 2, 0, group0, ngroups, 0u);
+    else epilogue_fast_role<1, false, false, false, BF16 ? 1 : 0, S2_SA2, 64, false, false>(p, bias2.v, tmem_base + S2_D_COLS, accf0, acce0, warp, lane, (uint32_t)(warp - 12) >> 2, 0, group0, ngroups, 0u);
   } else if (warp >= 4 && warp < 10) {
     // ================= mid warps: stem accumulator -> 16-bit activation patch (operand A2) =================
     const int mt = warp >= 8 ? 1 : 0, q = warp & 3;

@@ -77,7 +77,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       const uint32_t full_count = p.a_mode == A_TMA ? 1u : 1u + 4u * (uint32_t)CL;
       for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, full_count); mbar_init(empty0 + 8 * s, 1); }
       // pair mode: the leader's MMA also waits for the peer's four epilogue warps (remote arrivals)
-      for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 4u * (uint32_t)CL); }
+      // (accumulator drained: both epilogue sets work on every tile, except with the bulk-copy output path — conv_tc_epilogue.cuh)
+      for (int b = 0; b < 2; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, (p.bulk_out || !p.epi_split ? 4u : 8u) * (uint32_t)CL); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -357,7 +358,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) { mbar_init(fullA0 + 8 * s, 1); mbar_init(emptyA0 + 8 * s, 1); }
       for (int s = 0; s < SB; ++s) { mbar_init(fullB0 + 8 * s, 1); mbar_init(emptyB0 + 8 * s, 1); }
-      for (int b = 0; b < NBUF; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 4); }
+      for (int b = 0; b < NBUF; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, p.epi_split ? 8 : 4); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -522,7 +523,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_c
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) { mbar_init(fullA0 + 8 * s, 1); mbar_init(emptyA0 + 8 * s, 1); }
       mbar_init(fullB, 1);
-      for (int b = 0; b < NBUF; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, 8); }
+      for (int b = 0; b < NBUF; ++b) { mbar_init(accf0 + 8 * b, 1); mbar_init(acce0 + 8 * b, p.epi_split ? 16 : 8); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -730,6 +731,7 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
   t.Ho = p->Ho; t.Wo = p->Wo; t.relu = p->relu;
   t.relu_cend = p->relu_channels > 0 ? p->relu_channels : p->Cout;
   t.pool2 = p->pool2 != 0;
+  { const char* e = getenv("CTX_EPI_SPLIT"); t.epi_split = (e && e[0] == '0') ? 0 : 1; }
   t.M = p->N * p->Ho * p->Wo;
   t.cin_blocks = (p->Cin + TC_BK - 1) / TC_BK;
   t.nk = p->in_nchw ? 1 : p->KH * p->KW * t.cin_blocks;       // stem: all 27 taps*channels in one 64-wide K-step

@@ -45,6 +45,7 @@ struct TcParams {
   void* out_lo;
   const float* out_scale;
   float trunc_comp;            // expected relative loss of one chain to the tensor core's truncating adder (see conv_x3.cu)
+  int epi_split;               // both epilogue sets drain every tile, half of its chunks each (else: alternate tiles) — conv_tc_epilogue.cuh
   const float* bias1;          // A_STEM2: bias of the fused first conv (conv1_1), 64 floats
   long long* dbg;              // development aid (ctx_debug_set_conv_timeline): clock64 stamps of CTA 0, [8 roles][64 tiles][6]; NULL = off
 };

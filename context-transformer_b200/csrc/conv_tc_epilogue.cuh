@@ -26,7 +26,7 @@ __device__ __forceinline__ uint32_t max2_packed(uint32_t a, uint32_t b, bool bf1
 // BPRE: the bias of a 32-column chunk is fetched while the chunk's TMEM load is in flight (the first one before the accumulator
 // is complete): a shared-memory load issued right before its FADDs waits behind the tensor cores' operand fetch, which keeps the
 // shared-memory pipe busy in exactly the layers whose epilogue sets the pace
-template <int CL, bool POOL, bool RES, bool BULK, int DT = -1, int NBUF = 2, int CBN = 0, bool BPRE = false>
+template <int CL, bool POOL, bool RES, bool BULK, int DT = -1, int NBUF = 2, int CBN = 0, bool BPRE = false, bool SPLIT_ = true>
 __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const float* s_bias, uint32_t tmem_base, uint32_t accf0, uint32_t acce0,
                                                    int warp, int lane, uint32_t eset, int rank, int group0, int ngroups, uint32_t stage_smem) {
   const int q = warp & 3;
@@ -37,8 +37,13 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
   const long long img_stride = p.segs.seg[0].img_stride;
   const int pix_stride = p.segs.seg[0].pix_stride;
   const uint32_t stage_row = stage_smem + (uint32_t)(lane * Cout) * 2u;
-  uint32_t lt = eset;
-  for (int tile = group0 + (int)eset * ngroups; tile < p.num_tiles; tile += 2 * ngroups, lt += 2) {
+  // Both epilogue sets drain EVERY tile, half of its 32-column chunks each (SPLIT): the epilogue of a tile then takes half as long,
+  // which is what a kernel with one or two tiles per CTA — most of the pyramid — pays in full at its end (with the sets on
+  // alternate tiles one of them idled through the last tile).  The bulk-copy output path needs whole rows per warp and keeps
+  // the alternate-tile scheme.
+  const bool SPLIT = SPLIT_ && !BULK && p.epi_split;      // (SPLIT_ = false: kernels with many tiles per CTA and four accumulators measured better with the sets on alternate tiles)
+  uint32_t lt = SPLIT ? 0u : eset;
+  for (int tile = group0 + (SPLIT ? 0 : (int)eset * ngroups); tile < p.num_tiles; tile += (SPLIT ? 1 : 2) * ngroups, lt += (SPLIT ? 1u : 2u)) {
     const uint32_t buf = lt & (uint32_t)(NBUF - 1);
     const int mg = CBN ? tile : tile / p.n_tiles_n, n0 = CBN ? 0 : (tile - mg * p.n_tiles_n) * BN, mt = mg * CL + rank;
     int n_img, pix;
@@ -58,6 +63,9 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
     const uint16_t* res = nullptr;
     if (RES) res = reinterpret_cast<const uint16_t*>(p.residual) + ((long long)n_img * p.Ho * p.Wo + pix) * p.res_cstride + p.res_coffset;
     const int c_end = CBN ? CBN : min(Cout, n0 + BN);
+    // this set's chunks: [c_lo, c_hi)
+    const int nchunk = (c_end - n0 + 31) >> 5, first = (nchunk + 1) >> 1;
+    const int c_lo = SPLIT && eset ? n0 + first * 32 : n0, c_hi = SPLIT && !eset ? min(c_end, n0 + first * 32) : c_end;
     // Transposed stores (plain case): a thread owns one output row, so its 16-byte pieces of a 32-column chunk would go out
     // as four requests touching 32 half-written sectors each.  The four lanes of a quad exchange pieces (4 x 4 transpose, 16
     // shuffles per chunk) so that a request writes, per row, the 64 contiguous bytes of the chunk from four adjacent lanes:
@@ -81,13 +89,13 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
         rnext[gq] = (row_ok && c < c_end) ? __ldg(reinterpret_cast<const uint4*>(res + c)) : make_uint4(0u, 0u, 0u, 0u);
       }
     };
-    if (RES) load_res(n0);
+    if (RES) load_res(c_lo);
     float4 bnext[8];
     auto load_bias = [&](int c0) {                                // s_bias is zero-padded to a whole chunk past Cout
 #pragma unroll
       for (int k = 0; k < 8; ++k) bnext[k] = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * k);
     };
-    if (BPRE && !CBN) load_bias(n0);
+    if (BPRE && !CBN) load_bias(c_lo);
     mbar_wait(accf0 + 8 * buf, (lt / (uint32_t)NBUF) & 1);
     tc_fence_after();
     if (q == 0 && lane == 0) dbg_stamp(p, 5 + (int)eset, lt, 0);
@@ -103,9 +111,9 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
       if (RES) {
 #pragma unroll
         for (int gq = 0; gq < 4; ++gq) rcur[gq] = rnext[gq];
-        if (c0 + 32 < c_end) load_res(c0 + 32);
+        if (c0 + 32 < c_hi) load_res(c0 + 32);
       }
-      if (BPRE && !CBN && c0 != n0) load_bias(c0);                 // (the first chunk's was issued before the accumulator wait)
+      if (BPRE && !CBN && c0 != c_lo) load_bias(c0);                 // (the first chunk's was issued before the accumulator wait)
       tmem_ld_wait();
       if (q == 0 && lane == 0) dbg_stamp(p, 5 + (int)eset, lt, c0 == n0 ? 2 : 4);
       if (BULK && !row_ok) return;
@@ -203,10 +211,11 @@ __device__ __forceinline__ void epilogue_fast_role(const TcParams& p, const floa
     };
     if constexpr (CBN > 0) {                                      // tile width known at compile time: chunks unrolled, bias indices constant
 #pragma unroll
-      for (int c0 = 0; c0 < CBN; c0 += 32) chunk(c0);
+      for (int c0 = 0; c0 < CBN; c0 += 32)
+        if (c0 >= c_lo && c0 < c_hi) chunk(c0);
     } else {
 #pragma unroll 1
-      for (int c0 = n0; c0 < c_end; c0 += 32) chunk(c0);
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) chunk(c0);
     }
     if (BULK) {
       // rows of this warp are 32 consecutive pixels of a dense NHWC map: one contiguous block (valid rows are a prefix)
@@ -250,8 +259,9 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_
     const int BN = p.bn;
     const int r = q * 32 + lane;
     const bool bf16 = p.is_bf16 != 0;
-    uint32_t lt = eset;
-    for (int tile = group0 + (int)eset * ngroups; tile < p.num_tiles; tile += 2 * ngroups, lt += 2) {
+    const bool split = !p.bulk_out && p.epi_split;                    // both sets on every tile, half of the chunks each (see above)
+    uint32_t lt = split ? 0u : eset;
+    for (int tile = group0 + (split ? 0 : (int)eset * ngroups); tile < p.num_tiles; tile += (split ? 1 : 2) * ngroups, lt += (split ? 1u : 2u)) {
       const uint32_t buf = lt & 1;
       const int mg = tile / p.n_tiles_n, n0 = (tile - mg * p.n_tiles_n) * BN, mt = mg * CL + rank;
       int n_img, pix;
@@ -264,8 +274,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const float* s_
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
       }
+      const int nch = (min(p.Cout - n0, BN) + 31) >> 5, first = (nch + 1) >> 1;
+      const int cb_lo = split && eset ? first : 0, cb_hi = split && !eset ? first : nch;
 #pragma unroll 1
-      for (int cb = 0; cb * 32 < BN; ++cb) {
+      for (int cb = cb_lo; cb < cb_hi; ++cb) {
         const int c0 = n0 + cb * 32;
         if (c0 >= p.Cout) break;                                   // warp-uniform
         const int lim = BN - cb * 32;                              // columns of this chunk that belong to the tile
