@@ -26,6 +26,8 @@
 //     warp 9     TMEM allocator + MMA issuer (one elected lane); tcgen05.commit drives every hand-off mbarrier.
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace ctx {
 
 constexpr int AT_BQ = 128;        // queries per q-tile
@@ -117,6 +119,7 @@ struct AttnTcParams {
 #define AT_DBG(slot) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[(slot)] = clock64(); } while (0)
 
 // one row (64 fp32 values) -> fp16 hi and lo rows of two 128B-swizzled K-major operand tiles
+template <bool WITH_LO = true>
 __device__ __forceinline__ void store_split_row(uint32_t tile_hi, uint32_t tile_lo, int r, const float (&x)[64]) {
 #pragma unroll
   for (int ch = 0; ch < 8; ++ch) {
@@ -132,7 +135,7 @@ __device__ __forceinline__ void store_split_row(uint32_t tile_hi, uint32_t tile_
     }
     const uint32_t off = r * 128 + ((ch ^ (r & 7)) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+    if (WITH_LO) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
   }
 }
 
@@ -142,20 +145,30 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
   tmem_ld_wait();
 }
 
-template <int D, int NN>       // feature dim, novel classes (rows of OBJ_Target)
-__global__ void __launch_bounds__(AT_THREADS, 1)
+// QT = 2: CTA = two q-tiles sharing the key stream, one CTA per SM (all modes).  QT = 1 (fp16-logit mode only): CTA = one q-tile with
+// half of TMEM and < half of the shared memory, TWO CTAs per SM — the prologue (projection) and the per-row epilogue of one CTA, 27 %
+// of its life with the tensor cores and the SFU idle, then run beside the key loop of the other.
+template <int D, int NN, int QT>       // feature dim, novel classes (rows of OBJ_Target), q-tiles per CTA
+__global__ void __launch_bounds__((4 * QT + 2) * 32, QT == 2 ? 1 : 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_vl, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // (QT = 1 has no room for alignment slack: the dynamic shared-memory window of a kernel without static shared memory starts 1 KB
+  // into the CTA's allocation, which is 1024-aligned; checked below)
+  const uint32_t base = QT == 2 ? (smem_u32(smem_raw) + 1023u) & ~1023u : smem_u32(smem_raw);
+  if (QT == 1 && (base & 1023u)) __trap();
+  constexpr int NQ = QT == 2 ? 4 : 1;                  // Q tiles: hi / lo per q-tile, or hi only
+  constexpr int RING = QT == 2 ? AT_RING : 64 * 1024;
+  constexpr int NSB = QT == 2 ? 3 : 1;                 // S buffers (128 TMEM columns each)
+  constexpr int W_TMA = 4 * QT, W_MMA = 4 * QT + 1;
   // [QhA QlA QhB QlB] 64 KB (epilogue: classifier weights per q-tile)
   // [P_A P_B] 2 x 32 KB, each two 128x64 K-blocks (prologue: conf hi / lo tiles of the projection)
   // ring 96 KB: 2 x {Kh 16, Vt 2 x 8, Kl 16} or 3 x {Kh, Vt} (prologue: the last stage holds theta' hi/lo)
-  const uint32_t sQ = base, sP = sQ + 4 * AT_TILE_Q, sKV = sP + 4 * AT_TILE_Q;
-  const uint32_t bars = sKV + AT_RING;
+  const uint32_t sQ = base, sP = sQ + NQ * AT_TILE_Q, sKV = sP + 2 * QT * AT_TILE_Q;
+  const uint32_t bars = sKV + RING;
   // precise mode: 64-key tiles, stage = {Kh 8, Kl 8, Vh^T 8, Vl^T 8} KB, three stages
   const int KT = p.precise ? 64 : AT_BK;                 // keys per tile
-  const int NST = p.precise ? 3 : (p.split ? 2 : 3);     // ring depth
+  const int NST = QT == 1 ? 2 : (p.precise ? 3 : (p.split ? 2 : 3));     // ring depth
   const uint32_t STAGE = p.precise ? 4u * AT_TILE_W : (p.split ? AT_STAGE_SPLIT : AT_STAGE_FAST);
   const uint32_t w_full = bars, x_full = bars + 8, xq_done = bars + 24, q_ready = bars + 40, kv_full = bars + 56,
                  kv_empty = kv_full + 8 * 3, s_full = kv_empty + 8 * 3, s_empty = s_full + 32,
@@ -163,14 +176,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bars + 256 - smem_u32(smem_raw)));   // [64] theta bias
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y, q0 = blockIdx.x * (AT_QT * AT_BQ);
+  const int b = blockIdx.y, q0 = blockIdx.x * (QT * AT_BQ);
+  // staging area of a q-tile's fp32 conf rows (30 KB): its Q hi / lo tiles, or (QT = 1: Q is one tile) the first ring stage
+  auto xstage = [&](int t) { return QT == 2 ? sQ + 2 * t * AT_TILE_Q : sKV; };
   const int T = p.ntiles;
 
-  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); if (p.precise) tma_prefetch_desc(&tm_vl); }
-  if (warp == 9) {
+  if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); if (p.precise) tma_prefetch_desc(&tm_vl); }
+  if (warp == W_MMA) {
     if (lane == 0) {
       mbar_init(w_full, 1);
-      for (int t = 0; t < AT_QT; ++t) {
+      for (int t = 0; t < QT; ++t) {
         mbar_init(x_full + 8 * t, 4); mbar_init(xq_done + 8 * t, 1); mbar_init(q_ready + 8 * t, 4);
         mbar_init(p_full + 8 * t, 4); mbar_init(pv_done + 8 * t, 1);
         for (int sb = 0; sb < 2; ++sb) { mbar_init(s_full + 8 * (2 * t + sb), 1); mbar_init(s_empty + 8 * (2 * t + sb), 4); }   // (three of the four are used)
@@ -180,7 +195,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, QT == 2 ? 512 : 256);
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < 64; i += blockDim.x) s_bias[i] = i < D ? p.theta_b[i] : 0.f;
@@ -191,17 +206,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
   // TMEM columns: three rotating S buffers (128 keys each) at 0 / 128 / 256 (the projection of q-tile t lands in buffer t);
   // O of q-tile t at 384 + 64 t
-  const uint32_t tO = tmem + 384;
+  const uint32_t tO = tmem + NSB * AT_BK;
 
-  if (warp == 8) {
+  if (warp == W_TMA) {
     // ================= TMA producer =================
     const uint32_t wstage = sKV + (NST - 1) * STAGE;        // theta' lives in the last ring stage during the projection
     if (elect_one()) {
-      for (int t = 0; t < AT_QT; ++t) {                     // conf rows of q-tile t: one contiguous block -> the Q_t region
+      for (int t = 0; t < QT; ++t) {                        // conf rows of q-tile t: one contiguous block -> its staging area
         const int rows = min(AT_BQ, p.P - (q0 + t * AT_BQ));
         const uint32_t bytes = rows > 0 ? (uint32_t)rows * D * 4u : 0u;
         mbar_arrive_expect_tx(xin_full + 8 * t, p.bulk_x ? bytes : 0u);
-        if (p.bulk_x && bytes) bulk_load(sQ + 2 * t * AT_TILE_Q, p.conf + ((size_t)b * p.P + q0 + t * AT_BQ) * D, bytes, xin_full + 8 * t);
+        if (p.bulk_x && bytes) bulk_load(xstage(t), p.conf + ((size_t)b * p.P + q0 + t * AT_BQ) * D, bytes, xin_full + 8 * t);
       }
       mbar_arrive_expect_tx(w_full, 2 * AT_TILE_W);
       tma_load_2d(wstage, &tm_w, 0, 0, w_full);                   // theta' hi
@@ -209,7 +224,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     }
     __syncwarp();
     for (int j = 0, s = 0, ph = 1; j < T; ++j) {                // ring slot / EMPTY parity tracked incrementally (no division)
-      if (j == NST - 1) { mbar_wait(xq_done, 0); mbar_wait(xq_done + 8, 0); }     // theta' (last ring stage) has been consumed
+      if (j == NST - 1) { for (int t = 0; t < QT; ++t) mbar_wait(xq_done + 8 * t, 0); }     // theta' (last ring stage) has been consumed
+      if (QT == 1 && j == 0) mbar_wait(x_full, 0);               // the conf rows staged in ring stage 0 have been read
       mbar_wait(kv_empty + 8 * s, ph);
       if (elect_one()) {
         const uint32_t dst = sKV + s * STAGE;
@@ -229,14 +245,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       __syncwarp();
       if (++s == NST) { s = 0; ph ^= 1; }
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // ================= MMA issuer ================= (whole warp converged, one elected lane issues)
     const uint32_t idesc_s = make_idesc_f16(false, AT_BQ, KT);       // logits: M128 x N = keys per tile
     const uint32_t idesc_d = make_idesc_f16(false, AT_BQ, AT_DP);    // projection / PV: M128 x N64 features
     const uint64_t dQ = make_sw128_desc(sQ), dP = make_sw128_desc(sP), dKV = make_sw128_desc(sKV);
     // ---- projection: Q_t = conf_t (theta + I)^T, hi/lo split, into the first 64 columns of S_t
     mbar_wait(w_full, 0);
-    for (int t = 0; t < AT_QT; ++t) {
+    for (int t = 0; t < QT; ++t) {
       mbar_wait(x_full + 8 * t, 0);
       tc_fence_after();
       if (elect_one()) {
@@ -259,9 +275,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     // (with one buffer per q-tile they idled for an MMA round trip per tile).
     int sq = 0, phq = 0, sp = 0;                                 // ring slot / FULL parity on the QK side; ring slot on the PV side
     int buf = 0, bpar = 0;                                       // S buffer u % 3 and parity of its (u / 3)-th use
-    for (int u = 0; u < 2 * T + 2; ++u) {
-      if (u < 2 * T) {
-        const int t = u & 1, j = u >> 1;
+    for (int u = 0; u < QT * T + QT; ++u) {
+      if (u < QT * T) {
+        const int t = u % QT, j = u / QT;
         if (t == 0) { mbar_wait(kv_full + 8 * sq, phq); if (lane == 0) AT_DBG(j * 16 + 0); }
         if (j == 0) mbar_wait(q_ready + 8 * t, 0);
         mbar_wait(s_empty + 8 * buf, bpar ^ 1);
@@ -269,7 +285,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         if (lane == 0) AT_DBG(j * 16 + 1 + t);
         if (elect_one()) {
           const uint64_t kh = dKV + (uint64_t)((sq * STAGE) >> 4), kl = kh + (uint64_t)((p.precise ? AT_TILE_W : 2 * AT_TILE_K) >> 4);
-          const uint64_t qh = dQ + (uint64_t)((2 * t * AT_TILE_Q) >> 4), ql = qh + (uint64_t)(AT_TILE_Q >> 4);
+          const uint64_t qh = dQ + (uint64_t)(((QT == 2 ? 2 * t : 0) * AT_TILE_Q) >> 4), ql = qh + (uint64_t)(AT_TILE_Q >> 4);
           const uint32_t d = tmem + buf * AT_BK;
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(d, qh + 2 * k, kh + 2 * k, idesc_s, k ? 1u : 0u);
@@ -282,11 +298,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
           umma_commit(s_full + 8 * buf);
         }
         __syncwarp();
-        if (t == AT_QT - 1 && ++sq == NST) { sq = 0; phq ^= 1; }
-        if (++buf == 3) { buf = 0; bpar ^= 1; }
+        if (t == QT - 1 && ++sq == NST) { sq = 0; phq ^= 1; }
+        if (++buf == NSB) { buf = 0; bpar ^= 1; }
       }
-      if (u >= 2) {
-        const int uu = u - 2, t = uu & 1, jj = uu >> 1;
+      if (u >= QT) {
+        const int uu = u - QT, t = uu % QT, jj = uu / QT;
         if (lane == 0 && t == 0) AT_DBG(jj * 16 + 3);
         mbar_wait(p_full + 8 * t, jj & 1);
         tc_fence_after();
@@ -307,11 +323,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
             umma_f16(tO + t * AT_DP, pp + (uint64_t)((k >> 2) * (AT_TILE_Q >> 4)) + 2 * (k & 3),
                      vt + (uint64_t)((k >> 2) * (AT_TILE_W >> 4)) + 2 * (k & 3), idesc_d, (jj | k) ? 1u : 0u);
           umma_commit(pv_done + 8 * t);
-          if (t == AT_QT - 1) umma_commit(kv_empty + 8 * sp);
+          if (t == QT - 1) umma_commit(kv_empty + 8 * sp);
         }
         __syncwarp();
         if (lane == 0 && t == 1) AT_DBG(jj * 16 + 6);
-        if (t == AT_QT - 1 && ++sp == NST) sp = 0;
+        if (t == QT - 1 && ++sp == NST) sp = 0;
       }
     }
   } else {
@@ -331,7 +347,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     {
       float x[64];
       mbar_wait(xin_full + 8 * t, 0);
-      const float* xs = p.bulk_x ? reinterpret_cast<const float*>(smem_raw + (sQ + 2 * t * AT_TILE_Q - smem_u32(smem_raw))) + r * D : xrow;
+      const float* xs = p.bulk_x ? reinterpret_cast<const float*>(smem_raw + (xstage(t) - smem_u32(smem_raw))) + r * D : xrow;
 #pragma unroll
       for (int d = 0; d < 64; ++d) x[d] = (d < D && q_ok) ? xs[d] : 0.f;
       if (warp == 0 && lane == 0) AT_DBG(501);
@@ -346,7 +362,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       tmem_ld64(tS, v);
 #pragma unroll
       for (int d = 0; d < 64; ++d) x[d] = __uint_as_float(v[d]) + s_bias[d];
-      store_split_row(sQ + (2 * t) * AT_TILE_Q, sQ + (2 * t + 1) * AT_TILE_Q, r, x);
+      if (QT == 2) store_split_row(sQ + (2 * t) * AT_TILE_Q, sQ + (2 * t + 1) * AT_TILE_Q, r, x);
+      else store_split_row<false>(sQ, 0u, r, x);                 // fp16-logit mode: the lo half of Q is never read
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -359,9 +376,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     const uint32_t tOrow = tO + lane_sel + t * AT_DP;
     for (int j = 0; j < T; ++j) {
       if (warp == 0 && lane == 0) AT_DBG(j * 16 + 7);
-      const int u = 2 * j + t, ub = u % 3;                     // this q-tile's use of S buffer u % 3 (see the MMA issuer)
+      const int u = QT * j + t, ub = u % NSB;                  // this q-tile's use of S buffer u % NSB (see the MMA issuer)
       const uint32_t tSu = tmem + lane_sel + ub * AT_BK;
-      mbar_wait(s_full + 8 * ub, (u / 3) & 1);
+      mbar_wait(s_full + 8 * ub, (u / NSB) & 1);
       tc_fence_after();
       if (warp == 0 && lane == 0) AT_DBG(j * 16 + 8);
       const int NH = p.precise ? 1 : 2;                          // 64-key halves per tile
@@ -470,7 +487,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       const int rows = min(AT_BQ, p.P - (q0 + t * AT_BQ));
       const uint32_t bytes = rows > 0 ? (uint32_t)rows * D * 4u : 0u;
       mbar_arrive_expect_tx(xin_full + 8 * t, bytes);
-      if (bytes) bulk_load(sQ + 2 * t * AT_TILE_Q, p.conf + ((size_t)b * p.P + q0 + t * AT_BQ) * D, bytes, xin_full + 8 * t);
+      if (bytes) bulk_load(xstage(t), p.conf + ((size_t)b * p.P + q0 + t * AT_BQ) * D, bytes, xin_full + 8 * t);
     }
     float* s_obj = reinterpret_cast<float*>(smem_raw + (sPt - smem_u32(smem_raw)));      // [num_novel][D]
     float* s_wz = s_obj + NN * D;                                                // [D]
@@ -492,7 +509,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
     if (p.bulk_x) mbar_wait(xin_full + 8 * t, 1);
     if (warp == 0 && lane == 0) AT_DBG(508);
     if (q_ok) {
-      const float* xs = p.bulk_x ? reinterpret_cast<const float*>(smem_raw + (sQ + 2 * t * AT_TILE_Q - smem_u32(smem_raw))) + r * D : xrow;
+      const float* xs = p.bulk_x ? reinterpret_cast<const float*>(smem_raw + (xstage(t) - smem_u32(smem_raw))) + r * D : xrow;
       static_assert(D < AT_DP, "the row sum lives in the padding feature column D");
       const float inv_l = 1.0f / __uint_as_float(v[D]);        // sum_j p_j, accumulated by the PV MMA (ones feature of V)
       float x[D], z[D];
@@ -574,9 +591,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == W_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, QT == 2 ? 512 : 256);
   }
 }
 
@@ -635,9 +652,19 @@ static int attention_tc_launch_t(const CtxAttnParams* a, cudaStream_t st) {
   p.conf = a->conf; p.theta_b = a->theta_b; p.Wz = a->Wz; p.obj_w = a->obj_target_w; p.fc_w = a->fc_base_w; p.fc_b = a->fc_base_b;
   p.scale = a->scale; p.out = a->out;
   p.dbg = g_attn_dbg;
+  static const int qt1_env = [] { const char* e = getenv("CTX_ATTN_QT1"); return (e && e[0] == '0') ? 0 : 1; }();
+  if (!p.split && qt1_env) {
+    // fp16-logit mode: one q-tile per CTA, two CTAs per SM
+    const size_t smem1 = (size_t)AT_TILE_Q + 2 * AT_TILE_Q + 64 * 1024 + 256 + 256 + 64;
+    CTX_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<D, NN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    CTX_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<D, NN, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    attention_tc_kernel<D, NN, 1><<<dim3(cdiv(P, AT_BQ), B), 6 * 32, smem1, st>>>(tw, tk, tv, tvl, p);
+    CTX_LAUNCH_CHECK();
+    return CTX_OK;
+  }
   const size_t smem = attn_tc_smem(D, a->num_novel, a->incre);
-  CTX_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<D, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_tc_kernel<D, NN><<<dim3(cdiv(P, AT_QT * AT_BQ), B), AT_THREADS, smem, st>>>(tw, tk, tv, tvl, p);
+  CTX_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<D, NN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_tc_kernel<D, NN, 2><<<dim3(cdiv(P, AT_QT * AT_BQ), B), AT_THREADS, smem, st>>>(tw, tk, tv, tvl, p);
   CTX_LAUNCH_CHECK();
   return CTX_OK;
 }
