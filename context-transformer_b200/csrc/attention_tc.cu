@@ -16,8 +16,8 @@
 //                MMA (Q = conf (theta+I)^T, 12 UMMAs) read Q from TMEM, add the bias, split hi/lo and stage
 //                it as the A operand of the logits MMAs.
 //                key loop: logits (4 UMMAs / tile, 12 in split mode), p = ex2(s*log2e - ref) against a reference that
-//                only moves when a tile's maximum exceeds it by more than 2^AT_TAU (online softmax with LAZY rescale:
-//                the first half tile sets it; a later jump rescales the row's O / l accumulator in TMEM and the half
+//                only moves when a tile's maximum exceeds it by more than 2^tau (online softmax with LAZY rescale:
+//                the first half tile sets it, ref_up above its maximum; a later jump rescales the row's O / l accumulator in TMEM and the half
 //                tile of P already staged — a handful of times per row, so PV of tile j still overlaps the
 //                exponentials of tile j+1 and no separate maximum pass over the keys exists); P is written as the
 //                fp16 A operand of the PV MMA.
@@ -41,7 +41,7 @@ constexpr int AT_TILE_K = AT_BK * AT_DP * 2;      // 16 KB: 128 keys x 64 featur
 constexpr int AT_TILE_W = AT_DP * AT_DP * 2;      // 8 KB: 64 x 64 (theta' half, V^T key block)
 constexpr int AT_STAGE_SPLIT = 3 * AT_TILE_K, AT_STAGE_FAST = 2 * AT_TILE_K;   // stage layout: Kh | Vt[2] | Kl
 constexpr float AT_LOG2E = 1.4426950408889634f;
-constexpr float AT_TAU = 12.0f;   // a row's softmax reference follows the running maximum only in jumps of > 2^12 (fp16 P stays < 65504)
+constexpr float AT_TAU = 12.0f;   // precise mode: a row's softmax reference follows the running maximum only in jumps of > 2^12 (the other modes: AttnTcParams::tau)
 
 // ---- K / V projection (fp32 CUDA cores) -> fp16 operands --------------------------------------------
 // rows: B*Pk_pad keys (rows >= Pk of an image are zero).  Khl: [2][B*Pk_pad][64]; Vt: [B][64][Pk_pad].
@@ -112,6 +112,7 @@ struct AttnTcParams {
   const float* conf;                // [B,P,D] fp32: projection input and residual x
   const float *theta_b, *Wz, *obj_w, *fc_w, *fc_b;
   float scale;
+  float tau, ref_up;                // softmax reference window (log2 units), see the key loop
   float* out;
   long long* dbg;                   // optional timeline buffer (ctx_debug_set_buffer), CTA (0,0) only
 };
@@ -405,17 +406,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
           m4[3] = fmaxf(m4[3], fmaxf(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7])));
         }
         const float m2 = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * AT_LOG2E;
-        if (hb == 0 && j > 0) mbar_wait(pv_done + 8 * t, (j - 1) & 1);   // PV_{j-1} has finished reading P_t (and writing O_t)
+        // PV_{j-1} must have finished reading P_t before this tile's P is stored, and writing O_t before O_t is rescaled: the wait
+        // sits in front of those two places, not here — the 64 exponentials of the first half run while PV_{j-1} completes
+        bool pv_ok = j == 0 || hb > 0;
+        auto need_pv = [&] { if (!pv_ok) { mbar_wait(pv_done + 8 * t, (j - 1) & 1); tc_fence_after(); pv_ok = true; } };
         if (j == 0 && hb == 0) {
-          ref2 = m2;                                           // first half tile: the reference starts at its maximum
+          ref2 = m2 + p.ref_up;                                // first half tile: the reference starts ref_up above its maximum
         } else {
-          const bool jump = m2 > ref2 + AT_TAU;
+          const bool jump = m2 > ref2 + p.tau;
           if (__any_sync(0xffffffffu, jump)) {
             // rare: move the reference of the rows that jumped and rescale what they have accumulated under the old one
-            const float nref = jump ? m2 : ref2;
+            const float nref = jump ? m2 + p.ref_up : ref2;
             const float f = fast_exp2(ref2 - nref);            // 1 for rows that stay
             ref2 = nref;
-            if (j > 0) {                                       // O_t / l (TMEM): all MMAs that wrote it are complete (pv_done above)
+            need_pv();
+            if (j > 0) {                                       // O_t / l (TMEM): all MMAs that wrote it are complete
               uint32_t o[32];
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
@@ -428,17 +433,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
               tmem_st_wait();
             }
             if (hb == 1) {                                     // the first half of this tile's P is already staged: scale it in place
-              const __half2 f2 = __float2half2_rn(f);
+              // (in fp32: f < 2^-tau is a subnormal with a few significant bits — or zero — as an fp16 factor, and the staged
+              // values it scales can weigh as much as the new maximum)
               const uint32_t prow0 = sPt + r * 128;
 #pragma unroll
               for (int ch = 0; ch < 8; ++ch) {
-                uint32_t w0, w1, w2, w3;
+                uint32_t w[4];
                 const uint32_t a = prow0 + ((ch ^ (r & 7)) << 4);
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a) : "memory");
-                __half2 h0 = __hmul2(*reinterpret_cast<__half2*>(&w0), f2), h1 = __hmul2(*reinterpret_cast<__half2*>(&w1), f2);
-                __half2 h2 = __hmul2(*reinterpret_cast<__half2*>(&w2), f2), h3 = __hmul2(*reinterpret_cast<__half2*>(&w3), f2);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(*reinterpret_cast<uint32_t*>(&h0)), "r"(*reinterpret_cast<uint32_t*>(&h1)),
-                             "r"(*reinterpret_cast<uint32_t*>(&h2)), "r"(*reinterpret_cast<uint32_t*>(&h3)) : "memory");
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(a) : "memory");
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 x2 = __half22float2(*reinterpret_cast<__half2*>(&w[k]));
+                  __half2 h = __floats2half2_rn(x2.x * f, x2.y * f);
+                  w[k] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
               }
             }
           }
@@ -446,6 +455,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         if (p.precise) {                     // P as fp16 hi / lo pairs: the two K-blocks of P_t hold Ph and Pl of the same 64 keys
 #pragma unroll
           for (int c = 0; c < 64; ++c) v[c] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(v[c]), AT_LOG2E, -ref2)));
+          need_pv();
           store_split_row(sPt, sPt + AT_TILE_Q, r, *reinterpret_cast<const float(*)[64]>(&v[0]));
           continue;
         }
@@ -458,6 +468,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         }
         if (warp == 0 && lane == 0) AT_DBG(j * 16 + 10 + 3 * hb);
         if (warp == 0 && lane == 0) AT_DBG(j * 16 + 11 + 3 * hb);
+        need_pv();
         const uint32_t prow = sPt + hb * AT_TILE_Q + r * 128;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch)
@@ -647,6 +658,16 @@ static int attention_tc_launch_t(const CtxAttnParams* a, cudaStream_t st) {
   p.num_novel = a->num_novel; p.incre = a->incre; p.apply_softmax = a->apply_softmax;
   p.k_rows = k_rows;
   p.split = a->use_tensor_cores >= 2;
+  // P is fp16: normal from 2^-14, subnormal (absolute precision 2^-24) below, finite below 2^16.  A row's reference starts
+  // ref_up ABOVE the first maximum it sees and moves (rescaling O, 64 TMEM columns per row) only when a later maximum exceeds it
+  // by more than tau: the row maximum may grow by ref_up + tau before the first rescale, and the largest P of a row lies in
+  // [2^-ref_up, 2^tau].  With ref_up = 0, tau = 12 (round 1) 46 % of the 64-key half tiles of the benchmark input had a row
+  // of their warp jump, and every jump rescales all 32 rows of the warp.  The precise mode splits P into fp16 hi + lo and needs
+  // lo = 2^-11 P to stay normal: it keeps ref_up = 0.
+  static const float tau_env = [] { const char* e = getenv("CTX_ATTN_TAU"); return e ? (float)atof(e) : -1.f; }();
+  static const float up_env = [] { const char* e = getenv("CTX_ATTN_REFUP"); return e ? (float)atof(e) : -1.f; }();
+  p.tau = tau_env >= 0.f ? tau_env : (precise ? AT_TAU : 15.0f);
+  p.ref_up = up_env >= 0.f ? up_env : (precise ? 0.0f : 6.0f);
   p.bulk_x = ((uintptr_t)a->conf % 16 == 0) && ((size_t)P * D * 4 % 16 == 0) && ((size_t)AT_BQ * D * 4 % 16 == 0) &&
              ((size_t)(P % AT_BQ) * D * 4 % 16 == 0);
   p.conf = a->conf; p.theta_b = a->theta_b; p.Wz = a->Wz; p.obj_w = a->obj_target_w; p.fc_w = a->fc_base_w; p.fc_b = a->fc_base_b;
