@@ -15,6 +15,8 @@
 // IoU bit-matrix of the reference (nms_kernel.cu:110-122) — candidates are streamed in chunks of
 // 64 against the list of already-kept boxes, which lives in shared memory.
 #include "common.cuh"
+
+#include <stdlib.h>
 #include "sort.cuh"
 #include <algorithm>
 
@@ -352,9 +354,9 @@ __device__ int block_soft_nms(float4* box, float* sc, int* tag, int* tmp, int n,
 // the latency of an iteration ~6x.  Longer lists keep the generic kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSoftSmall = 2048;
-constexpr int kSoftThreads = 128;     // lists <= kSoftSplit; longer ones (<= kSoftSmall) get kSoftThreadsBig: the decay pass is (N / threads) deep
-constexpr int kSoftThreadsBig = 256;
-constexpr int kSoftSplit = 384;
+constexpr int kSoftThreads = 128;     // lists <= split1; longer ones get 256, lists > split2 kSoftThreadsBig: the decay pass is (N / threads) deep
+constexpr int kSoftThreadsBig = 512;
+constexpr int kSoftSplit = 384, kSoftSplit2 = 1024;
 struct SoftSmem {
   uint64_t keys[kSoftSmall];
   float4 box[kSoftSmall];
@@ -374,6 +376,21 @@ __device__ __forceinline__ void first_max(float& best, int& bpos, float ov, int 
   if (op != 0x7fffffff && (bpos == 0x7fffffff || ov > best || (ov == best && op < bpos))) { best = ov; bpos = op; }
 }
 
+// the same over a warp in two REDUX instructions instead of five shuffle rounds: scores map to unsigned keys that order like the
+// floats (0 = no candidate), the maximum key is reduced, then the minimum position among the lanes that hold it.  All lanes
+// receive the result.
+__device__ __forceinline__ unsigned ordered_key(float v) {
+  const unsigned b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ void warp_first_max(float& best, int& bpos) {
+  const unsigned key = bpos == 0x7fffffff ? 0u : ordered_key(best);
+  const unsigned m = __reduce_max_sync(0xffffffffu, key);
+  const unsigned c = (m != 0u && key == m) ? (unsigned)bpos : 0x7fffffffu;
+  bpos = (int)__reduce_min_sync(0xffffffffu, c);
+  best = m == 0u ? -INFINITY : __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);
+}
+
 __device__ int block_soft_nms_small(SoftSmem& sm, int n, float sigma, float Nt, float threshold, unsigned method, int T) {
   // T = participating threads (the first T of the CTA; the others have exited)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
@@ -386,30 +403,36 @@ __device__ int block_soft_nms_small(SoftSmem& sm, int n, float sigma, float Nt, 
       const float v = sc[pos];
       if (bpos == 0x7fffffff || best < v) { best = v; bpos = pos; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) first_max(best, bpos, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bpos, o));
+    warp_first_max(best, bpos);
     if (lane == 0) { sm.best[warp] = best; sm.bpos[warp] = bpos; }
   };
-  // thread 0: combine the warps' partial maxima over [i, N) and bring the winner to position i (the reference starts
-  // from maxscore = boxes[i,4] and only moves on a strictly larger score)
+  // warp 0: combine the warps' partial maxima (all its lanes get them) ...
+  auto combine = [&](float& best, int& bpos) {
+    best = lane < nw ? sm.best[lane] : -INFINITY;
+    bpos = lane < nw ? sm.bpos[lane] : 0x7fffffff;
+    warp_first_max(best, bpos);
+  };
+  // ... and bring the winner over [i, N) to position i (the reference starts from maxscore = boxes[i,4] and only moves on a
+  // strictly larger score)
+  auto swap_in = [&](int i, float best, int bpos) {
+    if (lane == 0) {
+      if (i < N) {
+        const int mp = (bpos != 0x7fffffff && sc[i] < best) ? bpos : i;
+        if (mp != i) {
+          const float4 tb = box[i]; box[i] = box[mp]; box[mp] = tb;
+          const float ts = sc[i]; sc[i] = sc[mp]; sc[mp] = ts;
+          const int tt = tag[i]; tag[i] = tag[mp]; tag[mp] = tt;
+          const float ta = ar[i]; ar[i] = ar[mp]; ar[mp] = ta;
+        }
+      }
+      sm.nrem = 0;
+    }
+  };
   auto select = [&](int i) {
     if (warp == 0) {
-      float best = lane < nw ? sm.best[lane] : -INFINITY;
-      int bpos = lane < nw ? sm.bpos[lane] : 0x7fffffff;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) first_max(best, bpos, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bpos, o));
-      if (lane == 0) {
-        if (i < N) {
-          const int mp = (bpos != 0x7fffffff && sc[i] < best) ? bpos : i;
-          if (mp != i) {
-            const float4 tb = box[i]; box[i] = box[mp]; box[mp] = tb;
-            const float ts = sc[i]; sc[i] = sc[mp]; sc[mp] = ts;
-            const int tt = tag[i]; tag[i] = tag[mp]; tag[mp] = tt;
-            const float ta = ar[i]; ar[i] = ar[mp]; ar[mp] = ta;
-          }
-        }
-        sm.nrem = 0;
-      }
+      float best; int bpos;
+      combine(best, bpos);
+      swap_in(i, best, bpos);
     }
   };
   scan_max(0);
@@ -441,7 +464,7 @@ __device__ int block_soft_nms_small(SoftSmem& sm, int n, float sigma, float Nt, 
           else weight = ov > Nt ? 0.0f : 1.0f;
           v = __fmul_rn(weight, v);
           sc[pos] = v;
-          if (v < threshold) sm.removed[atomicAdd(&sm.nrem, 1)] = pos;
+          if (v < threshold) { sm.removed[atomicAdd(&sm.nrem, 1)] = pos; return; }   // leaves the list: not a candidate for the next maximum
         }
       }
       if (bpos == 0x7fffffff || best < v) { best = v; bpos = pos; }
@@ -453,37 +476,57 @@ __device__ int block_soft_nms_small(SoftSmem& sm, int n, float sigma, float Nt, 
       decay_one(pos, b0, v0); decay_one(pos + T, b1, v1); decay_one(pos + 2 * T, b2, v2); decay_one(pos + 3 * T, b3, v3);
     }
     for (; pos < N; pos += T) decay_one(pos, box[pos], sc[pos]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) first_max(best, bpos, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bpos, o));
+    warp_first_max(best, bpos);
     if (lane == 0) { sm.best[warp] = best; sm.bpos[warp] = bpos; }
     __syncthreads();
     const int nrem = sm.nrem;
-    if (nrem > 0) {
-      // swap-with-last compaction: holes (removed positions < Nf, ascending) are filled by the survivors at positions
-      // >= Nf taken in descending position order.  Positions move, so the maxima gathered above are recomputed afterwards.
+    if (nrem > 0 && nrem <= 32) {
+      // The usual case, entirely in warp 0 between the same two barriers as an iteration without removals: swap-with-last
+      // compaction (holes = removed positions < Nf, ascending, filled by the survivors at positions >= Nf in descending
+      // position order), then the selection for the next iteration WITHOUT a second pass over the scores: removed boxes are
+      // below the threshold and every survivor is not, so the maximum gathered above is still the maximum; only its position
+      // can change — to the hole a filler with that score moved into.  The first position of the maximum afterwards is the
+      // smaller of the old one (if it stayed, i.e. lies below Nf) and the destinations of the fillers that carry it.
       const int Nf = N - nrem;
-      if (nrem <= 32) {
-        if (warp == 0) {
-          const int pr = lane < nrem ? sm.removed[lane] : 0x7fffffff;
-          int rank = 0;                                 // rank of this lane's removed position among the holes
-          bool taken = false;                           // is position N - 1 - lane (a filler candidate) itself removed?
-          const int q = N - 1 - lane;
-          for (int k = 0; k < nrem; ++k) {
-            const int pk = __shfl_sync(0xffffffffu, pr, k);
-            rank += (pk < pr && pk < Nf) ? 1 : 0;
-            taken = taken || pk == q;
-          }
-          if (pr < Nf) sm.holes[rank] = pr;
-          __syncwarp();
-          const bool filler = lane < nrem && !taken;    // q >= Nf by construction
-          const unsigned fm = __ballot_sync(0xffffffffu, filler);
-          if (filler) {
-            const int dst = sm.holes[__popc(fm & ((1u << lane) - 1u))];
-            box[dst] = box[q]; sc[dst] = sc[q]; tag[dst] = tag[q]; ar[dst] = ar[q];
-          }
+      if (warp == 0) {
+        float vbest; int vpos;
+        combine(vbest, vpos);
+        const int pr = lane < nrem ? sm.removed[lane] : 0x7fffffff;
+        int rank = 0;                                 // rank of this lane's removed position among the holes
+        bool taken = false;                           // is position N - 1 - lane (a filler candidate) itself removed?
+        const int q = N - 1 - lane;
+        for (int k = 0; k < nrem; ++k) {
+          const int pk = __shfl_sync(0xffffffffu, pr, k);
+          rank += (pk < pr && pk < Nf) ? 1 : 0;
+          taken = taken || pk == q;
         }
-      } else {
-        // many removals at once (rare): flags + two block-wide scans, as in the generic kernel
+        if (pr < Nf) sm.holes[rank] = pr;
+        __syncwarp();
+        const bool filler = lane < nrem && !taken;    // q >= Nf by construction
+        const unsigned fm = __ballot_sync(0xffffffffu, filler);
+        unsigned moved_to = 0x7fffffffu;
+        if (filler) {
+          const int dst = sm.holes[__popc(fm & ((1u << lane) - 1u))];
+          const float qs = sc[q];
+          box[dst] = box[q]; sc[dst] = qs; tag[dst] = tag[q]; ar[dst] = ar[q];
+          if (qs == vbest) moved_to = (unsigned)dst;
+        }
+        const unsigned first_moved = __reduce_min_sync(0xffffffffu, moved_to);
+        const unsigned stay = vpos < Nf ? (unsigned)vpos : 0x7fffffffu;
+        vpos = (int)min(stay, first_moved);
+        N = Nf;
+        __syncwarp();
+        swap_in(i + 1, vbest, vpos);
+      }
+      N = Nf;
+      __syncthreads();
+      continue;
+    }
+    if (nrem > 0) {
+      // more than 32 removals at once (rare): the same compaction with flags + two block-wide scans, as in the generic kernel;
+      // positions move, so the maxima are gathered again afterwards
+      const int Nf = N - nrem;
+      {
         int* flag = reinterpret_cast<int*>(sm.keys);            // the sort buffer is free by now: [0, N) flags, [N, 2N) holes
         for (int pos = i + 1 + tid; pos < N; pos += T) flag[pos] = 0;
         __syncthreads();
@@ -527,7 +570,7 @@ __global__ void __launch_bounds__(kSoftThreadsBig)
 class_soft_nms_small_kernel(const float* __restrict__ conf, const float* __restrict__ obj, const float4* boxes_px,
                             const int* __restrict__ cand_count, const uint64_t* cand_keys, int key_stride, int P, int C,
                             float thresh, int method, float sigma, float soft_threshold,
-                            float4* spill, int* kept_prior, float* kept_score, int* kept_count) {
+                            float4* spill, int* kept_prior, float* kept_score, int* kept_count, int split1, int split2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SoftSmem& sm = *reinterpret_cast<SoftSmem*>(smem_raw);
   const int j = blockIdx.x, b = blockIdx.y;
@@ -536,7 +579,7 @@ class_soft_nms_small_kernel(const float* __restrict__ conf, const float* __restr
   if (n > kSoftSmall) return;                                   // the generic kernel takes long lists
   if (n == 0) { if (threadIdx.x == 0) kept_count[row] = 0; return; }
   // short lists run on the first kSoftThreads threads only (cheaper barriers and reductions); the rest of the CTA leaves
-  const int T = n > kSoftSplit ? kSoftThreadsBig : kSoftThreads;
+  const int T = n > split2 ? kSoftThreadsBig : (n > split1 ? 256 : kSoftThreads);
   if ((int)threadIdx.x >= T) return;
   const float4* bpx = boxes_px + (size_t)b * P;
   // candidate order = ascending prior index (np.where order, test.py:143): sort keys (0xFFFFFFFF - prior) descending
@@ -811,9 +854,11 @@ extern "C" int ctx_detect_postprocess(const float* loc, const float* conf, const
   CTX_CUDA_TRY(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem)));
   if (p->nms_method != 0) {
     CTX_CUDA_TRY(cudaFuncSetAttribute(class_soft_nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SoftSmem)));
+    static const int split1 = [] { const char* e = getenv("CTX_SOFT_SPLIT1"); return e ? atoi(e) : kSoftSplit; }();
+    static const int split2 = [] { const char* e = getenv("CTX_SOFT_SPLIT2"); return e ? atoi(e) : kSoftSplit2; }();
     class_soft_nms_small_kernel<<<dim3(C, B), kSoftThreadsBig, sizeof(SoftSmem), st>>>(
         conf, obj, w.boxes_px, w.cand_count, w.cand_keys, w.key_stride, P, C, p->nms_thresh, p->nms_method, p->soft_sigma,
-        p->soft_threshold, w.spill, w.kept_prior, w.kept_score, w.kept_count);
+        p->soft_threshold, w.spill, w.kept_prior, w.kept_score, w.kept_count, split1, split2);
     CTX_LAUNCH_CHECK();
   }
   class_nms_kernel<<<dim3(C, B), kNmsThreads, sizeof(NmsSmem), st>>>(

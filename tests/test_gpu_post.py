@@ -209,6 +209,47 @@ def test_postprocess_soft_nms(method):
     assert np.allclose(got[:, 4], want[:, 4], rtol=3e-7 if method == 2 else 0, atol=0)
 
 
+@pytest.mark.parametrize('method,soft_threshold', [(1, 0.001), (1, 0.2), (2, 0.2), (3, 0.001)])
+def test_postprocess_soft_nms_tied_scores(method, soft_threshold):
+    """Scores quantised to sixteenths (the first maximum among equal scores is decided by POSITION, which the swap-with-last
+    compaction keeps changing) and a soft threshold above some of the initial scores (boxes that never overlap a selected one
+    stay in the list below the threshold, cpu_nms.pyx:139-147 only tests a score it has just decayed): the cases in which the
+    selection that follows a compaction without a second pass over the scores could go wrong."""
+    priors = ctx.PriorBox(ctx.VOC_300).forward()
+    P = priors.size(0)
+    g = synth._gen(11, 'ties%d' % method)
+    loc = torch.randn(1, P, 4, generator=g) * 0.3
+    level = torch.randint(1, 9, (1, P, 20), generator=g).float() / 16.0
+    conf = torch.where(torch.rand(1, P, 20, generator=g) < 0.08, level, torch.zeros(()))
+    conf[..., 3] = torch.where(torch.rand(1, P, generator=g) < 0.4, level[..., 3], torch.zeros(()))     # one long list (generic kernel)
+    obj = torch.zeros(1, P, 2)
+    obj[..., 1] = 1.0
+    scale = np.array([500, 375, 500, 375], np.float32)
+    post = ctx.DetectPost(21, 0, ctx.VOC_300, nms_thresh=0.3, nms_method=method, soft_threshold=soft_threshold, max_per_image=0,
+                          max_out=65536)
+    rec, cnt, pidx = post.forward((loc.to(DEV), conf.to(DEV), obj.to(DEV)), priors.to(DEV), scale)
+    gb, gs = ctx.Detect(21, 0, ctx.VOC_300).forward((loc.to(DEV), conf.to(DEV), obj.to(DEV)), priors.to(DEV))
+    boxes, scores = gb.cpu().numpy(), gs.cpu().numpy()
+    bx = (boxes[0] * scale).astype(np.float32)
+    rows, lens = [], []
+    for j in range(1, 21):
+        inds = np.where(scores[0][:, j] > np.float32(0.01))[0]
+        lens.append(len(inds))
+        if len(inds) == 0:
+            continue
+        c_dets = np.hstack((bx[inds], scores[0][inds, j][:, None])).astype(np.float32)
+        out, n = c_oracle.cpu_soft_nms(c_dets, 0.5, 0.3, soft_threshold, 0 if method == 3 else method)
+        rows.append(np.hstack([out, np.full((n, 1), j, np.float32)]))
+    assert min(lens) > 300 and max(lens) > 2048                       # both the shared-memory kernel and the generic one ran
+    want = np.vstack(rows)
+    n = int(cnt[0])
+    got = rec[0, :n].cpu().numpy()
+    assert n == len(want)
+    assert np.array_equal(got[:, 5], want[:, 5])
+    assert np.array_equal(got[:, :4], want[:, :4])
+    assert np.allclose(got[:, 4], want[:, 4], rtol=3e-7 if method == 2 else 0, atol=0)
+
+
 def test_postprocess_full_size_properties():
     """BASELINE config 3 size (512x512 priors, B = 16): properties the oracle need not be run for."""
     priors = ctx.PriorBox(ctx.VOC_512).forward()
