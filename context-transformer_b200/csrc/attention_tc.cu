@@ -552,7 +552,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
 #pragma unroll
       for (int c = 0; c < NN; ++c) nov[c] = 0.f;
       static_assert(D % 4 == 0 || D == 15, "classifier loop assumes 16-byte rows (D % 4 == 0) or the scalar path");
-      if (D % 4 == 0) {
+      if (D % 4 == 0 && NN % 4 == 0) {
+        // four classes per trip of a ROLLED loop (the raw sums pass through the row's output staging): 0.3 k instructions of
+        // code instead of 1.5 k of straight line that every warp fetches once per CTA — the unrolled form spent a quarter of
+        // the epilogue's samples in stall_no_inst (0.535 -> 0.523 ms for the kernel, same box).  Per class the sum still runs
+        // over d in ascending order: same bits.
+        float* stage = orow_s + (p.incre ? D : 0);
+#pragma unroll 1
+        for (int g = 0; g < NN; g += 4) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          const float* wg = s_obj + g * D;
+#pragma unroll
+          for (int d = 0; d < D; d += 4) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wg + d), w1 = *reinterpret_cast<const float4*>(wg + D + d);
+            const float4 w2 = *reinterpret_cast<const float4*>(wg + 2 * D + d), w3 = *reinterpret_cast<const float4*>(wg + 3 * D + d);
+            a0 = fmaf(w0.x, z[d], a0); a0 = fmaf(w0.y, z[d + 1], a0); a0 = fmaf(w0.z, z[d + 2], a0); a0 = fmaf(w0.w, z[d + 3], a0);
+            a1 = fmaf(w1.x, z[d], a1); a1 = fmaf(w1.y, z[d + 1], a1); a1 = fmaf(w1.z, z[d + 2], a1); a1 = fmaf(w1.w, z[d + 3], a1);
+            a2 = fmaf(w2.x, z[d], a2); a2 = fmaf(w2.y, z[d + 1], a2); a2 = fmaf(w2.z, z[d + 2], a2); a2 = fmaf(w2.w, z[d + 3], a2);
+            a3 = fmaf(w3.x, z[d], a3); a3 = fmaf(w3.y, z[d + 1], a3); a3 = fmaf(w3.z, z[d + 2], a3); a3 = fmaf(w3.w, z[d + 3], a3);
+          }
+          stage[g] = a0; stage[g + 1] = a1; stage[g + 2] = a2; stage[g + 3] = a3;
+        }
+#pragma unroll
+        for (int c = 0; c < NN; ++c) nov[c] = stage[c];
+      } else if (D % 4 == 0) {
 #pragma unroll
         for (int d = 0; d < D; d += 4) {
 #pragma unroll
