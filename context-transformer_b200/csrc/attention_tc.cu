@@ -168,9 +168,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   const uint32_t sQ = base, sP = sQ + NQ * AT_TILE_Q, sKV = sP + 2 * QT * AT_TILE_Q;
   const uint32_t bars = sKV + RING;
   // precise mode: 64-key tiles, stage = {Kh 8, Kl 8, Vh^T 8, Vl^T 8} KB, three stages
-  const int KT = p.precise ? 64 : AT_BK;                 // keys per tile
-  const int NST = QT == 1 ? 2 : (p.precise ? 3 : (p.split ? 2 : 3));     // ring depth
-  const uint32_t STAGE = p.precise ? 4u * AT_TILE_W : (p.split ? AT_STAGE_SPLIT : AT_STAGE_FAST);
+  // (the one-q-tile kernel only exists for the fp16-logit mode: the other modes' code is compiled out of it)
+  const bool precise = QT == 2 && p.precise != 0, split = QT == 2 && p.split != 0;
+  const int KT = precise ? 64 : AT_BK;                 // keys per tile
+  const int NST = QT == 1 ? 2 : (precise ? 3 : (split ? 2 : 3));     // ring depth
+  const uint32_t STAGE = precise ? 4u * AT_TILE_W : (split ? AT_STAGE_SPLIT : AT_STAGE_FAST);
   const uint32_t w_full = bars, x_full = bars + 8, xq_done = bars + 24, q_ready = bars + 40, kv_full = bars + 56,
                  kv_empty = kv_full + 8 * 3, s_full = kv_empty + 8 * 3, s_empty = s_full + 32,
                  p_full = s_empty + 32, pv_done = p_full + 16, tmem_slot = pv_done + 16, xin_full = tmem_slot + 8;
@@ -182,7 +184,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   auto xstage = [&](int t) { return QT == 2 ? sQ + 2 * t * AT_TILE_Q : sKV; };
   const int T = p.ntiles;
 
-  if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); if (p.precise) tma_prefetch_desc(&tm_vl); }
+  if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); if (precise) tma_prefetch_desc(&tm_vl); }
   if (warp == W_MMA) {
     if (lane == 0) {
       mbar_init(w_full, 1);
@@ -231,7 +233,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       if (elect_one()) {
         const uint32_t dst = sKV + s * STAGE;
         mbar_arrive_expect_tx(kv_full + 8 * s, STAGE);
-        if (p.precise) {                                        // (tm_k is encoded with 64-row boxes in this mode)
+        if (precise) {                                        // (tm_k is encoded with 64-row boxes in this mode)
           tma_load_2d(dst, &tm_k, 0, b * p.Pk_pad + j * 64, kv_full + 8 * s);
           tma_load_2d(dst + AT_TILE_W, &tm_k, 0, (int)p.k_rows + b * p.Pk_pad + j * 64, kv_full + 8 * s);
           tma_load_2d(dst + 2 * AT_TILE_W, &tm_v, j * 64, b * AT_DP, kv_full + 8 * s);
@@ -240,7 +242,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
           tma_load_2d(dst, &tm_k, 0, b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
           tma_load_2d(dst + AT_TILE_K, &tm_v, j * AT_BK, b * AT_DP, kv_full + 8 * s);
           tma_load_2d(dst + AT_TILE_K + AT_TILE_W, &tm_v, j * AT_BK + 64, b * AT_DP, kv_full + 8 * s);
-          if (p.split) tma_load_2d(dst + 2 * AT_TILE_K, &tm_k, 0, (int)p.k_rows + b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
+          if (split) tma_load_2d(dst + 2 * AT_TILE_K, &tm_k, 0, (int)p.k_rows + b * p.Pk_pad + j * AT_BK, kv_full + 8 * s);
         }
       }
       __syncwarp();
@@ -285,12 +287,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         tc_fence_after();
         if (lane == 0) AT_DBG(j * 16 + 1 + t);
         if (elect_one()) {
-          const uint64_t kh = dKV + (uint64_t)((sq * STAGE) >> 4), kl = kh + (uint64_t)((p.precise ? AT_TILE_W : 2 * AT_TILE_K) >> 4);
+          const uint64_t kh = dKV + (uint64_t)((sq * STAGE) >> 4), kl = kh + (uint64_t)((precise ? AT_TILE_W : 2 * AT_TILE_K) >> 4);
           const uint64_t qh = dQ + (uint64_t)(((QT == 2 ? 2 * t : 0) * AT_TILE_Q) >> 4), ql = qh + (uint64_t)(AT_TILE_Q >> 4);
           const uint32_t d = tmem + buf * AT_BK;
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(d, qh + 2 * k, kh + 2 * k, idesc_s, k ? 1u : 0u);
-          if (p.split) {
+          if (split) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(d, ql + 2 * k, kh + 2 * k, idesc_s, 1u);
 #pragma unroll
@@ -309,8 +311,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
         tc_fence_after();
         if (lane == 0) AT_DBG(jj * 16 + 4 + t);
         if (elect_one()) {
-          const uint64_t vt = dKV + (uint64_t)((sp * STAGE + (p.precise ? 2 * AT_TILE_W : AT_TILE_K)) >> 4), pp = dP + (uint64_t)((t * 2 * AT_TILE_Q) >> 4);
-          if (p.precise) {                 // 64 keys: O += Pl Vh + Ph Vl + Ph Vh (small terms first)
+          const uint64_t vt = dKV + (uint64_t)((sp * STAGE + (precise ? 2 * AT_TILE_W : AT_TILE_K)) >> 4), pp = dP + (uint64_t)((t * 2 * AT_TILE_Q) >> 4);
+          if (precise) {                 // 64 keys: O += Pl Vh + Ph Vl + Ph Vh (small terms first)
             const uint64_t pl = pp + (uint64_t)(AT_TILE_Q >> 4), vl = vt + (uint64_t)(AT_TILE_W >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(tO + t * AT_DP, pl + 2 * k, vt + 2 * k, idesc_d, (jj | k) ? 1u : 0u);
@@ -382,7 +384,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
       mbar_wait(s_full + 8 * ub, (u / NSB) & 1);
       tc_fence_after();
       if (warp == 0 && lane == 0) AT_DBG(j * 16 + 8);
-      const int NH = p.precise ? 1 : 2;                          // 64-key halves per tile
+      const int NH = precise ? 1 : 2;                          // 64-key halves per tile
       for (int hb = 0; hb < NH; ++hb) {
         tmem_ld64(tSu + hb * 64, v);
         if (warp == 0 && lane == 0) AT_DBG(j * 16 + 9 + 3 * hb);
@@ -452,7 +454,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
             }
           }
         }
-        if (p.precise) {                     // P as fp16 hi / lo pairs: the two K-blocks of P_t hold Ph and Pl of the same 64 keys
+        if (precise) {                     // P as fp16 hi / lo pairs: the two K-blocks of P_t hold Ph and Pl of the same 64 keys
 #pragma unroll
           for (int c = 0; c < 64; ++c) v[c] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(v[c]), AT_LOG2E, -ref2)));
           need_pv();
