@@ -633,6 +633,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_const
   }
 }
 
+// The one-q-tile kernel has no room for alignment slack in its 112.6 KB (two CTAs must fit an SM): it relies on the dynamic
+// shared-memory window of a kernel without static shared memory starting on a 1 KB boundary (it does: the first KB of a CTA's
+// allocation is reserved on sm_90+).  Checked once per process with a probe kernel instead of trusted; if it ever did not hold,
+// or the probe cannot run (no device, or the first call arrives inside a stream capture), the two-q-tile kernel is used.
+__global__ void smem_base_probe_kernel(unsigned* out) {
+  extern __shared__ uint8_t probe_smem[];
+  *out = smem_u32(probe_smem);
+}
+static int qt1_smem_base_ok(cudaStream_t st) {
+  static int ok = -1;
+  if (ok >= 0) return ok;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return 0; }   // undecided: ask again later
+  unsigned* d = nullptr;
+  unsigned h = 1u;
+  if (cudaMalloc(&d, sizeof(unsigned)) == cudaSuccess) {
+    smem_base_probe_kernel<<<1, 32, 4096, st>>>(d);
+    if (cudaMemcpyAsync(&h, d, sizeof(unsigned), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) h = 1u;
+    cudaFree(d);
+  }
+  cudaGetLastError();
+  ok = (h & 1023u) == 0u ? 1 : 0;
+  return ok;
+}
+
 static size_t attn_tc_smem(int D, int num_novel, int incre) {
   (void)D; (void)num_novel; (void)incre;      // classifier weights alias the Q region in the epilogue (<= 32 KB per q-tile)
   return 1024 + 4 * AT_TILE_Q + 4 * AT_TILE_Q + AT_RING + 256 + 256 + 64;
@@ -699,7 +724,7 @@ static int attention_tc_launch_t(const CtxAttnParams* a, cudaStream_t st) {
   p.scale = a->scale; p.out = a->out;
   p.dbg = g_attn_dbg;
   static const int qt1_env = [] { const char* e = getenv("CTX_ATTN_QT1"); return (e && e[0] == '0') ? 0 : 1; }();
-  if (!p.split && qt1_env) {
+  if (!p.split && qt1_env && qt1_smem_base_ok(st)) {
     // fp16-logit mode: one q-tile per CTA, two CTAs per SM
     const size_t smem1 = (size_t)AT_TILE_Q + 2 * AT_TILE_Q + 64 * 1024 + 256 + 256 + 64;
     CTX_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<D, NN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
