@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128)
 proj_kv_kernel(const float* __restrict__ pooled, const float* __restrict__ phi_w, const float* __restrict__ phi_b,
                const float* __restrict__ g_w, const float* __restrict__ g_b, int B, int Pk, int Pk_pad,
                __half* __restrict__ khl, __half* __restrict__ vt, __half* __restrict__ vt_lo) {
-  __shared__ float s_phi[D * D], s_g[D * D], s_pb[D], s_gb[D];
+  __shared__ __align__(16) float s_phi[D * D], s_g[D * D], s_pb[D], s_gb[D];
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) { s_phi[i] = phi_w[i]; s_g[i] = g_w[i]; }
   for (int i = threadIdx.x; i < D; i += blockDim.x) { s_pb[i] = phi_b[i]; s_gb[i] = g_b[i]; }
   __syncthreads();
@@ -89,16 +89,20 @@ proj_kv_kernel(const float* __restrict__ pooled, const float* __restrict__ phi_w
   }
 }
 
-// theta' = theta + I (the "+conf" residual of Q = theta(conf) + conf), padded to 64 x 64, as fp16 hi/lo: wq[2][64][64]
-__global__ void prep_wq_kernel(const float* __restrict__ theta_w, int D, __half* __restrict__ wq) {
+// W' = W + I (the "+x" residual of theta(x) + x, phi(x) + x, g(x) + x), padded to 64 x 64, as fp16 hi/lo: wq[3][2][64][64] for
+// theta, phi, g
+__global__ void prep_wq_kernel(const float* __restrict__ theta_w, const float* __restrict__ phi_w, const float* __restrict__ g_w, int D,
+                               __half* __restrict__ wq) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= AT_DP * AT_DP) return;
-  const int o = i / AT_DP, d = i - o * AT_DP;
+  if (i >= 3 * AT_DP * AT_DP) return;
+  const int m = i / (AT_DP * AT_DP), e = i - m * (AT_DP * AT_DP);
+  const int o = e / AT_DP, d = e - o * AT_DP;
+  const float* src = m == 0 ? theta_w : (m == 1 ? phi_w : g_w);
   float w = 0.f;
-  if (o < D && d < D) w = theta_w[o * D + d] + (o == d ? 1.f : 0.f);
+  if (o < D && d < D) w = src[o * D + d] + (o == d ? 1.f : 0.f);
   const __half h = __float2half_rn(w);
-  wq[i] = h;
-  wq[AT_DP * AT_DP + i] = __float2half_rn(w - __half2float(h));
+  wq[(2 * m) * AT_DP * AT_DP + e] = h;
+  wq[(2 * m + 1) * AT_DP * AT_DP + e] = __float2half_rn(w - __half2float(h));
 }
 
 // ---- fused attention --------------------------------------------------------------------------------
@@ -144,6 +148,119 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
   tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
   tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
   tmem_ld_wait();
+}
+
+// ---- K / V projection on the tensor cores -----------------------------------------------------------
+// The same arithmetic as the Q projection inside the fused kernel: a 128-row tile of pooled conf rows, split into fp16 hi / lo
+// A tiles, times phi' = phi + I and g' = g + I (hi / lo, prepared by prep_wq_kernel): x_hi W_hi + x_lo W_hi + x_hi W_lo in fp32
+// (12 UMMAs per projection), bias added on the way out of TMEM.  K goes out as fp16 hi / lo rows, V transposed (+ its lo plane
+// in the precise mode), rows past an image's Pk as zeros, feature D of V as the "ones" column.  One CTA per tile, 128 threads,
+// thread = row = TMEM lane.  The CUDA-core kernel above needs 7 200 FMAs per row at 0.4 IPC: 61 us for 61 k rows, 11 % of the
+// whole Context-Transformer op.
+template <int D>
+__global__ void __launch_bounds__(128)
+proj_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const float* __restrict__ pooled, const float* __restrict__ phi_b,
+                  const float* __restrict__ g_b, int B, int Pk, int Pk_pad, __half* __restrict__ khl, __half* __restrict__ vt,
+                  __half* __restrict__ vt_lo) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sW = sA + 2 * AT_TILE_Q, bars = sW + 4 * AT_TILE_W;     // A hi | A lo | phi' hi | phi' lo | g' hi | g' lo
+  const uint32_t w_full = bars, mma_done = bars + 8, tmem_slot = bars + 16;
+  float* s_b = reinterpret_cast<float*>(smem_raw + (bars + 32 - smem_u32(smem_raw)));   // [2][64] biases, zero padded
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = threadIdx.x;
+  const long long rows = (long long)B * Pk_pad;
+  const long long row = (long long)blockIdx.x * 128 + r;
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_w);
+      mbar_init(w_full, 1); mbar_init(mma_done, 1);
+      fence_barrier_init();
+      mbar_arrive_expect_tx(w_full, 4 * AT_TILE_W);
+      for (int k = 0; k < 4; ++k) tma_load_2d(sW + k * AT_TILE_W, &tm_w, 0, (2 + k) * AT_DP, w_full);   // rows 128 .. 383 of wq
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  if (r < 64) { s_b[r] = r < D ? phi_b[r] : 0.f; s_b[64 + r] = r < D ? g_b[r] : 0.f; }
+  const int b = row < rows ? (int)(row / Pk_pad) : 0, j = row < rows ? (int)(row - (long long)b * Pk_pad) : Pk;
+  const bool valid = j < Pk;
+  {
+    float x[64];
+    const float* src = pooled + ((long long)b * Pk + (valid ? j : 0)) * D;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) x[d] = (d < D && valid) ? src[d] : 0.f;
+    store_split_row(sA, sA + AT_TILE_Q, r, x);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+  if (warp == 0) {
+    mbar_wait(w_full, 0);
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(false, AT_BQ, AT_DP);
+      const uint64_t xh = make_sw128_desc(sA), xl = xh + (uint64_t)(AT_TILE_Q >> 4), w0 = make_sw128_desc(sW);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {                              // K = x phi'^T -> columns 0..63, V = x g'^T -> columns 64..127
+        const uint64_t wh = w0 + (uint64_t)((2 * m * AT_TILE_W) >> 4), wl = wh + (uint64_t)(AT_TILE_W >> 4);
+        const uint32_t d = tmem + m * AT_DP;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(d, xh + 2 * k, wh + 2 * k, idesc, k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(d, xl + 2 * k, wh + 2 * k, idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(d, xh + 2 * k, wl + 2 * k, idesc, 1u);
+      }
+      umma_commit(mma_done);
+    }
+    __syncwarp();
+  }
+  mbar_wait(mma_done, 0);
+  tc_fence_after();
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t v[64];
+  tmem_ld64(trow, v);
+  if (row < rows) {
+    __half* hi = khl + row * AT_DP;
+    __half* lo = khl + (rows + row) * AT_DP;
+#pragma unroll
+    for (int o0 = 0; o0 < AT_DP; o0 += 8) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float k0 = valid ? __uint_as_float(v[o0 + 2 * e]) + s_b[o0 + 2 * e] : 0.f;
+        const float k1 = valid ? __uint_as_float(v[o0 + 2 * e + 1]) + s_b[o0 + 2 * e + 1] : 0.f;
+        const __half2 hh = __floats2half2_rn(k0, k1);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(k0 - hf.x, k1 - hf.y);
+        h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+      *reinterpret_cast<uint4*>(hi + o0) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(lo + o0) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+  tmem_ld64(trow + AT_DP, v);
+  if (row < rows) {
+#pragma unroll
+    for (int o = 0; o < AT_DP; ++o) {
+      float val = valid ? __uint_as_float(v[o]) + s_b[64 + o] : 0.f;
+      if (o == D) val = valid ? 1.f : 0.f;                       // "ones" feature: the PV MMA then accumulates sum_j p_j in O[:, D]
+      if (o > D) val = 0.f;
+      const __half vh = __float2half_rn(val);
+      vt[((long long)b * AT_DP + o) * Pk_pad + j] = vh;
+      if (vt_lo) vt_lo[((long long)b * AT_DP + o) * Pk_pad + j] = __float2half_rn(val - __half2float(vh));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
 }
 
 // QT = 2: CTA = two q-tiles sharing the key stream, one CTA per SM (all modes).  QT = 1 (fp16-logit mode only): CTA = one q-tile with
@@ -665,9 +782,9 @@ static size_t attn_tc_smem(int D, int num_novel, int incre) {
 
 size_t attention_tc_workspace_bytes(int B, int P, int Pk) {
   const size_t Pk_pad = (size_t)(Pk + AT_BK - 1) / AT_BK * AT_BK;
-  (void)P;                                  // K hi/lo, V^T hi, V^T lo (precise mode), theta' hi/lo
+  (void)P;                                  // K hi/lo, V^T hi, V^T lo (precise mode), theta' / phi' / g' hi/lo
   return align_up((size_t)2 * B * Pk_pad * AT_DP * 2, 1024) + 2 * align_up((size_t)B * AT_DP * Pk_pad * 2, 1024) +
-         align_up((size_t)2 * AT_DP * AT_DP * 2, 1024);
+         align_up((size_t)6 * AT_DP * AT_DP * 2, 1024);
 }
 
 static long long* g_attn_dbg = nullptr;
@@ -692,12 +809,20 @@ static int attention_tc_launch_t(const CtxAttnParams* a, cudaStream_t st) {
   const bool precise = a->use_tensor_cores == 3;
   const int KT = precise ? 64 : AT_BK;
   const long long k_rows = (long long)B * Pk_pad;
-  prep_wq_kernel<<<cdiv(AT_DP * AT_DP, 256), 256, 0, st>>>(a->theta_w, D, wq);
-  CTX_LAUNCH_CHECK();
-  proj_kv_kernel<D><<<cdiv(k_rows, 128), 128, 0, st>>>(a->pooled, a->phi_w, a->phi_b, a->g_w, a->g_b, B, Pk, Pk_pad, khl, vt, precise ? vt_lo : nullptr);
+  prep_wq_kernel<<<cdiv(3 * AT_DP * AT_DP, 256), 256, 0, st>>>(a->theta_w, a->phi_w, a->g_w, D, wq);
   CTX_LAUNCH_CHECK();
   CUtensorMap tw, tk, tv, tvl;
-  int rc = encode_2d_sw128(&tw, wq, false, 2ull * AT_DP, AT_DP, AT_DP);
+  int rc = encode_2d_sw128(&tw, wq, false, 6ull * AT_DP, AT_DP, AT_DP);
+  if (rc) return rc;
+  static const int proj_tc = [] { const char* e = getenv("CTX_ATTN_PROJ_TC"); return (e && e[0] == '0') ? 0 : 1; }();
+  if (proj_tc) {
+    const size_t psmem = 1024 + 2 * AT_TILE_Q + 4 * AT_TILE_W + 32 + 2 * 64 * sizeof(float);
+    CTX_CUDA_TRY(cudaFuncSetAttribute(proj_kv_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    proj_kv_tc_kernel<D><<<cdiv(k_rows, 128), 128, psmem, st>>>(tw, a->pooled, a->phi_b, a->g_b, B, Pk, Pk_pad, khl, vt, precise ? vt_lo : nullptr);
+  } else {
+    proj_kv_kernel<D><<<cdiv(k_rows, 128), 128, 0, st>>>(a->pooled, a->phi_w, a->phi_b, a->g_w, a->g_b, B, Pk, Pk_pad, khl, vt, precise ? vt_lo : nullptr);
+  }
+  CTX_LAUNCH_CHECK();
   if (!rc) rc = encode_2d_sw128(&tk, khl, false, 2ull * k_rows, AT_DP, (unsigned)KT);
   if (!rc) rc = encode_2d_sw128(&tv, vt, false, (unsigned long long)B * AT_DP, (unsigned long long)Pk_pad, AT_DP);   // box: 64 keys x 64 features
   if (!rc) rc = encode_2d_sw128(&tvl, precise ? vt_lo : vt, false, (unsigned long long)B * AT_DP, (unsigned long long)Pk_pad, AT_DP);
