@@ -157,19 +157,22 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
 // in the precise mode), rows past an image's Pk as zeros, feature D of V as the "ones" column.  One CTA per tile, 128 threads,
 // thread = row = TMEM lane.  The CUDA-core kernel above needs 7 200 FMAs per row at 0.4 IPC: 61 us for 61 k rows, 11 % of the
 // whole Context-Transformer op.
+constexpr int PJ_TILES = 2;       // 128-row tiles per CTA (they share the four weight tiles): 240 CTAs of 256 threads, two per SM = one wave
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128 * PJ_TILES)
 proj_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const float* __restrict__ pooled, const float* __restrict__ phi_b,
                   const float* __restrict__ g_b, int B, int Pk, int Pk_pad, __half* __restrict__ khl, __half* __restrict__ vt,
-                  __half* __restrict__ vt_lo) {
+                  __half* __restrict__ vt_lo, int vec_x) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base, sW = sA + 2 * AT_TILE_Q, bars = sW + 4 * AT_TILE_W;     // A hi | A lo | phi' hi | phi' lo | g' hi | g' lo
+  // A hi | A lo per tile, then phi' hi | phi' lo | g' hi | g' lo
+  const uint32_t sA = base, sW = sA + PJ_TILES * 2 * AT_TILE_Q, bars = sW + 4 * AT_TILE_W;
   const uint32_t w_full = bars, mma_done = bars + 8, tmem_slot = bars + 16;
   float* s_b = reinterpret_cast<float*>(smem_raw + (bars + 32 - smem_u32(smem_raw)));   // [2][64] biases, zero padded
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = warp >> 2, r = threadIdx.x & 127;                 // tile of the CTA, row of the tile = TMEM lane
   const long long rows = (long long)B * Pk_pad;
-  const long long row = (long long)blockIdx.x * 128 + r;
+  const long long row = ((long long)blockIdx.x * PJ_TILES + t) * 128 + r;
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_w);
@@ -179,18 +182,26 @@ proj_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const float* __restr
       for (int k = 0; k < 4; ++k) tma_load_2d(sW + k * AT_TILE_W, &tm_w, 0, (2 + k) * AT_DP, w_full);   // rows 128 .. 383 of wq
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 128);
+    tmem_alloc(tmem_slot, 128 * PJ_TILES);
     tmem_relinquish();
   }
-  if (r < 64) { s_b[r] = r < D ? phi_b[r] : 0.f; s_b[64 + r] = r < D ? g_b[r] : 0.f; }
+  if (threadIdx.x < 64) { s_b[threadIdx.x] = threadIdx.x < D ? phi_b[threadIdx.x] : 0.f; s_b[64 + threadIdx.x] = threadIdx.x < D ? g_b[threadIdx.x] : 0.f; }
   const int b = row < rows ? (int)(row / Pk_pad) : 0, j = row < rows ? (int)(row - (long long)b * Pk_pad) : Pk;
   const bool valid = j < Pk;
   {
     float x[64];
     const float* src = pooled + ((long long)b * Pk + (valid ? j : 0)) * D;
+    if (D % 4 == 0 && vec_x) {                                    // 16-byte row pieces: a quarter of the requests
 #pragma unroll
-    for (int d = 0; d < 64; ++d) x[d] = (d < D && valid) ? src[d] : 0.f;
-    store_split_row(sA, sA + AT_TILE_Q, r, x);
+      for (int d = 0; d < 64; d += 4) {
+        const float4 q = (d < D && valid) ? __ldg(reinterpret_cast<const float4*>(src + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[d] = q.x; x[d + 1] = q.y; x[d + 2] = q.z; x[d + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < 64; ++d) x[d] = (d < D && valid) ? src[d] : 0.f;
+    }
+    store_split_row(sA + t * 2 * AT_TILE_Q, sA + (t * 2 + 1) * AT_TILE_Q, r, x);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -202,17 +213,21 @@ proj_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const float* __restr
     mbar_wait(w_full, 0);
     if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(false, AT_BQ, AT_DP);
-      const uint64_t xh = make_sw128_desc(sA), xl = xh + (uint64_t)(AT_TILE_Q >> 4), w0 = make_sw128_desc(sW);
+      const uint64_t w0 = make_sw128_desc(sW);
 #pragma unroll
-      for (int m = 0; m < 2; ++m) {                              // K = x phi'^T -> columns 0..63, V = x g'^T -> columns 64..127
-        const uint64_t wh = w0 + (uint64_t)((2 * m * AT_TILE_W) >> 4), wl = wh + (uint64_t)(AT_TILE_W >> 4);
-        const uint32_t d = tmem + m * AT_DP;
+      for (int tt = 0; tt < PJ_TILES; ++tt) {
+        const uint64_t xh = make_sw128_desc(sA + tt * 2 * AT_TILE_Q), xl = xh + (uint64_t)(AT_TILE_Q >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(d, xh + 2 * k, wh + 2 * k, idesc, k ? 1u : 0u);
+        for (int m = 0; m < 2; ++m) {                            // K = x phi'^T -> columns 0..63 of the tile's 128, V = x g'^T -> 64..127
+          const uint64_t wh = w0 + (uint64_t)((2 * m * AT_TILE_W) >> 4), wl = wh + (uint64_t)(AT_TILE_W >> 4);
+          const uint32_t d = tmem + tt * 128 + m * AT_DP;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(d, xl + 2 * k, wh + 2 * k, idesc, 1u);
+          for (int k = 0; k < 4; ++k) umma_f16(d, xh + 2 * k, wh + 2 * k, idesc, k ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(d, xh + 2 * k, wl + 2 * k, idesc, 1u);
+          for (int k = 0; k < 4; ++k) umma_f16(d, xl + 2 * k, wh + 2 * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(d, xh + 2 * k, wl + 2 * k, idesc, 1u);
+        }
       }
       umma_commit(mma_done);
     }
@@ -220,7 +235,7 @@ proj_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const float* __restr
   }
   mbar_wait(mma_done, 0);
   tc_fence_after();
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t trow = tmem + t * 128 + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t v[64];
   tmem_ld64(trow, v);
   if (row < rows) {
@@ -259,7 +274,7 @@ proj_kv_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const float* __restr
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 128);
+    tmem_dealloc(tmem, 128 * PJ_TILES);
   }
 }
 
@@ -816,9 +831,12 @@ static int attention_tc_launch_t(const CtxAttnParams* a, cudaStream_t st) {
   if (rc) return rc;
   static const int proj_tc = [] { const char* e = getenv("CTX_ATTN_PROJ_TC"); return (e && e[0] == '0') ? 0 : 1; }();
   if (proj_tc) {
-    const size_t psmem = 1024 + 2 * AT_TILE_Q + 4 * AT_TILE_W + 32 + 2 * 64 * sizeof(float);
+    const size_t psmem = 1024 + PJ_TILES * 2 * AT_TILE_Q + 4 * AT_TILE_W + 32 + 2 * 64 * sizeof(float);
+    static const int vec_env = [] { const char* e = getenv("CTX_ATTN_PROJ_VECX"); return (e && e[0] == '0') ? 0 : 1; }();
+    const int vec_x = vec_env && ((uintptr_t)a->pooled % 16 == 0) && ((size_t)D * 4 % 16 == 0);
     CTX_CUDA_TRY(cudaFuncSetAttribute(proj_kv_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-    proj_kv_tc_kernel<D><<<cdiv(k_rows, 128), 128, psmem, st>>>(tw, a->pooled, a->phi_b, a->g_b, B, Pk, Pk_pad, khl, vt, precise ? vt_lo : nullptr);
+    proj_kv_tc_kernel<D><<<cdiv(k_rows, 128 * PJ_TILES), 128 * PJ_TILES, psmem, st>>>(tw, a->pooled, a->phi_b, a->g_b, B, Pk, Pk_pad, khl, vt,
+                                                                                   precise ? vt_lo : nullptr, vec_x);
   } else {
     proj_kv_kernel<D><<<cdiv(k_rows, 128), 128, 0, st>>>(a->pooled, a->phi_w, a->phi_b, a->g_w, a->g_b, B, Pk, Pk_pad, khl, vt, precise ? vt_lo : nullptr);
   }
