@@ -166,7 +166,7 @@ maxpool_nhwc_kernel(CtxPoolParams p) {
 }
 
 // 16-bit fast path: 8 channels (16 bytes) per thread, fully coalesced 128-bit loads/stores.
-template <bool BF16>
+template <bool BF16, int K = 0>      // K = 2, 3: window unrolled (all its loads in flight at once); 0: any window
 __global__ void __launch_bounds__(256)
 maxpool_nhwc_vec8_kernel(CtxPoolParams p) {
   // grid: x over (output column, 8-channel group), y over (image, output row) — no 64-bit division per element (four of them
@@ -182,18 +182,35 @@ maxpool_nhwc_vec8_kernel(CtxPoolParams p) {
     float m[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
-    for (int y = y0; y < y1; ++y)
-      for (int x = x0; x < x1; ++x) {
-        const uint4 v = *reinterpret_cast<const uint4*>(in + (long long)n * p.in_img_stride + (long long)(y * p.W + x) * p.in_pix_stride + c);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    auto take = [&](const uint4 v) {
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float2 f;
-          if (BF16) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-          else f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-          m[2 * e] = fmaxf(m[2 * e], f.x); m[2 * e + 1] = fmaxf(m[2 * e + 1], f.y);
-        }
+      for (int e = 0; e < 4; ++e) {
+        float2 f;
+        if (BF16) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+        else f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+        m[2 * e] = fmaxf(m[2 * e], f.x); m[2 * e + 1] = fmaxf(m[2 * e + 1], f.y);
       }
+    };
+    if (K > 0) {
+      uint4 v[K > 0 ? K * K : 1];
+      const int yb = oy * p.stride - p.pad, xb = ox * p.stride - p.pad;
+#pragma unroll
+      for (int dy = 0; dy < K; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx) {
+          const int y = yb + dy, x = xb + dx;
+          // a clipped tap repeats a tap that is inside the window (the window always holds one): the maximum does not change
+          const int yc = min(max(y, y0), y1 - 1), xc = min(max(x, x0), x1 - 1);
+          v[dy * K + dx] = *reinterpret_cast<const uint4*>(in + (long long)n * p.in_img_stride + (long long)(yc * p.W + xc) * p.in_pix_stride + c);
+        }
+#pragma unroll
+      for (int q = 0; q < K * K; ++q) take(v[q]);
+    } else {
+      for (int y = y0; y < y1; ++y)
+        for (int x = x0; x < x1; ++x)
+          take(*reinterpret_cast<const uint4*>(in + (long long)n * p.in_img_stride + (long long)(y * p.W + x) * p.in_pix_stride + c));
+    }
     uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -487,7 +504,10 @@ int maxpool_launch(const CtxPoolParams* p, cudaStream_t st) {
   if (vec) {
     CTX_REQUIRE((long long)p->N * p->Ho <= 65535, "maxpool: too many output rows for the (image, row) grid dimension");
     const dim3 grid((unsigned)((p->Wo * (p->C / 8) + 255) / 256), (unsigned)(p->N * p->Ho));
-    if (p->dtype == CTX_BF16) maxpool_nhwc_vec8_kernel<true><<<grid, 256, 0, st>>>(*p);
+    const bool bf = p->dtype == CTX_BF16;
+    if (p->k == 2) { if (bf) maxpool_nhwc_vec8_kernel<true, 2><<<grid, 256, 0, st>>>(*p); else maxpool_nhwc_vec8_kernel<false, 2><<<grid, 256, 0, st>>>(*p); }
+    else if (p->k == 3) { if (bf) maxpool_nhwc_vec8_kernel<true, 3><<<grid, 256, 0, st>>>(*p); else maxpool_nhwc_vec8_kernel<false, 3><<<grid, 256, 0, st>>>(*p); }
+    else if (bf) maxpool_nhwc_vec8_kernel<true><<<grid, 256, 0, st>>>(*p);
     else maxpool_nhwc_vec8_kernel<false><<<grid, 256, 0, st>>>(*p);
     CTX_LAUNCH_CHECK();
     return CTX_OK;
