@@ -237,8 +237,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const int per_img = p.tiles_x * p.tiles_y;
         n_img = mt / per_img;
         const int t = mt - n_img * per_img;
-        y0 = (t / p.tiles_x) * p.TH - p.pad_h;
-        x0 = (t % p.tiles_x) * p.TW - p.pad_w;
+        y0 = (t / p.tiles_x) * p.TH * p.stride - p.pad_h;       // input coordinates of the patch's first output pixel
+        x0 = (t % p.tiles_x) * p.TW * p.stride - p.pad_w;
       }
       int cc = 0, ky = 0, kx = 0;
       for (int it = 0; it < nk; ++it, ++g) {
@@ -778,7 +778,7 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
   else if (p->in_nchw) t.a_mode = A_STEM;
   else if (tune_amode == 0 && !p->pool2) t.a_mode = A_GATHER;
   else if (flat_eligible(p)) { t.a_mode = A_TMA; tw = 128; th = 1; }
-  else t.a_mode = choose_patch(p, &tw, &th, tune_amode == 1 ? 100000 : 150) ? A_TMA : A_GATHER;
+  else t.a_mode = choose_patch(p, &tw, &th, tune_amode == 1 ? 100000 : 150, 2) ? A_TMA : A_GATHER;
   t.flat = t.a_mode == A_TMA && flat_eligible(p);
   t.TW = tw; t.TH = th;
   const bool patches = t.a_mode == A_TMA || t.a_mode == A_HALO;
@@ -877,7 +877,8 @@ static int plan_create(const CtxConvParams* p, int tune_n, int tune_cluster, int
     rc = encode_nhwc_sw128(&pl->tmap_a, p->in, t.is_bf16 != 0, p->N, p->H, p->W, p->in_cstride, p->in_coffset + p->Cin, (unsigned)t.PW, (unsigned)t.PH);
   if (!rc && t.a_mode == A_TMA)
     rc = t.flat ? encode_nhwc_sw128(&pl->tmap_a, p->in, t.is_bf16 != 0, 1, 1, t.M, p->in_cstride, p->in_coffset + p->Cin, 128u, 1u)
-                : encode_nhwc_sw128(&pl->tmap_a, p->in, t.is_bf16 != 0, p->N, p->H, p->W, p->in_cstride, p->in_coffset + p->Cin, (unsigned)tw, (unsigned)th);
+                : encode_nhwc_sw128(&pl->tmap_a, p->in, t.is_bf16 != 0, p->N, p->H, p->W, p->in_cstride, p->in_coffset + p->Cin, (unsigned)tw, (unsigned)th,
+                                    (unsigned)p->stride);
   if (rc) { delete pl; return rc; }
   if (t.pool2 && !(((t.a_mode == A_TMA && t.TW == 16) || t.a_mode == A_HALO) && t.fast_out)) {
     delete pl;

@@ -100,14 +100,16 @@ static inline int num_sms() {
 // TMA activation mode: stride-1 conv whose output map is tiled by TW x TH pixel patches, TW * TH <= 128 (the rows of the
 // M = 128 tile beyond TW * TH are never loaded nor stored).  The patch that needs the fewest tiles wins; `max_ratio_pct`
 // bounds the tile count against the gather mode's ceil(M / 128) (gather packs pixels across rows and images).
-static inline bool tma_eligible(const CtxConvParams* p) {
-  return p->stride == 1 && p->Cin % 8 == 0 && p->in_coffset % 8 == 0 && p->in_cstride % 8 == 0 && !p->in_nchw;
+static inline bool tma_eligible(const CtxConvParams* p, int max_stride = 1) {
+  return p->stride >= 1 && p->stride <= max_stride && p->Cin % 8 == 0 && p->in_coffset % 8 == 0 && p->in_cstride % 8 == 0 && !p->in_nchw;
 }
 static inline bool flat_eligible(const CtxConvParams* p) {
   return tma_eligible(p) && p->KH == 1 && p->KW == 1 && p->pad_h == 0 && p->pad_w == 0 && !p->pool2;
 }
-static inline bool choose_patch(const CtxConvParams* p, int* tw, int* th, int max_ratio_pct = 150) {
-  if (!tma_eligible(p)) return false;
+// max_stride = 2 (conv_tc.cu only): the TMA unit walks the input with a traversal stride, so the TW x TH patch of OUTPUT pixels of a
+// stride-2 conv is still one box per tap (the RFB blocks that halve the map: extras.1 / extras.2)
+static inline bool choose_patch(const CtxConvParams* p, int* tw, int* th, int max_ratio_pct = 150, int max_stride = 1) {
+  if (!tma_eligible(p, max_stride) || (p->stride > 1 && p->pool2)) return false;
   if (p->pool2) {                       // 2 x 2 windows must sit inside one warp of the epilogue: 16 x 8 patches
     if ((p->Ho | p->Wo) & 1) return false;
     *tw = 16; *th = 8;

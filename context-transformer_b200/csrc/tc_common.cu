@@ -37,13 +37,16 @@ int encode_2d_sw128(CUtensorMap* out, const void* base, bool bf16, unsigned long
 // NHWC activation [N][H][W][C] 16-bit as a 4-D tensor (C innermost, pixels C elements apart, only channels < c_limit
 // addressable); box = 64 channels x bw x bh pixels of one image, SWIZZLE_128B.  Out-of-range pixels (conv padding) and
 // channels >= c_limit (the tail of a channel slice that is not a multiple of 64) read as zero.
-int encode_nhwc_sw128(CUtensorMap* out, const void* base, bool bf16, int N, int H, int W, int C, int c_limit, unsigned bw, unsigned bh) {
+int encode_nhwc_sw128(CUtensorMap* out, const void* base, bool bf16, int N, int H, int W, int C, int c_limit, unsigned bw, unsigned bh,
+                      unsigned step) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return CTX_ERR_CUDA; }
   cuuint64_t gdim[4] = {(cuuint64_t)c_limit, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64u, bw, bh, 1u};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // step > 1: every step-th pixel in x and y (a box dimension counts the elements walked over, ceil(box / step) of them are loaded)
+  cuuint32_t box[4] = {64u, bw * step, bh * step, 1u};
+  cuuint32_t estr[4] = {1, step, step, 1};
+  if (box[1] > 256u || box[2] > 256u) { set_error("encode_nhwc_sw128: strided box %u x %u exceeds 256", box[1], box[2]); return CTX_ERR_UNSUPPORTED; }
   CUresult r = enc(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base),
                    gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -208,6 +208,7 @@ EncodeTiledFn get_encode_fn();
 int encode_2d_sw128(CUtensorMap* out, const void* base, bool bf16, unsigned long long rows, unsigned long long cols,
                     unsigned box_rows);
 // NHWC 16-bit activation as a 4-D tensor, box = 64 channels x bw x bh pixels; returns 0 on success
-int encode_nhwc_sw128(CUtensorMap* out, const void* base, bool bf16, int N, int H, int W, int C, int c_limit, unsigned bw, unsigned bh);
+int encode_nhwc_sw128(CUtensorMap* out, const void* base, bool bf16, int N, int H, int W, int C, int c_limit, unsigned bw, unsigned bh,
+                      unsigned step = 1u);
 
 }  // namespace ctx

@@ -203,7 +203,10 @@ def test_conv_cta_pair_mode(case, monkeypatch):
 @pytest.mark.parametrize('case', [(128, 128, 3, 1, 1, 1, 38, 38), (256, 256, 3, 1, 2, 2, 19, 19), (96, 128, (3, 1), 1, (1, 0), 1, 38, 38),
                                   (512, 320, 1, 1, 0, 1, 19, 19), (192, 256, 3, 1, 1, 1, 10, 10), (64, 64, 3, 1, 1, 1, 75, 75),
                                   (128, 256, 3, 1, 1, 1, 5, 5), (1024, 264, 1, 1, 0, 1, 7, 9), (128, 128, 3, 1, 3, 3, 38, 38),
-                                  (64, 128, 3, 1, 1, 1, 40, 24)], ids=str)
+                                  (64, 128, 3, 1, 1, 1, 40, 24),
+                                  # stride 2 (the RFB blocks that halve the map): TMA patches walk the input with a traversal stride
+                                  (128, 256, 3, 2, 1, 1, 19, 19), (192, 256, 3, 2, 1, 1, 10, 10), (1024, 384, 1, 2, 0, 1, 19, 19),
+                                  (64, 128, 3, 2, 1, 1, 10, 14)], ids=str)
 def test_conv_every_tiling_is_bit_identical(case):
     """ctx_conv2d_tc_plan_create_tuned: N-tile count, CTA pairs and the A-operand mode (TMA pixel patches of any
     TW x TH <= 128 shape, flat 128-pixel runs for 1x1 convs, im2col gather) only change the tiling, never a bit of the result."""
@@ -245,10 +248,11 @@ def test_conv_every_tiling_is_bit_identical(case):
                 L.ctx_conv2d_tc_plan_destroy(plan)
     assert len(seen) >= 4
     assert {k[3] for k in seen} >= {0, 1}                         # gather and TMA-patch A-operand modes were exercised
-    assert (3 in {k[3] for k in seen}) == (kh == 3 and kw == 3)   # ... and the halo mode for every 3x3 case
-    assert (4 in {k[3] for k in seen}) == (kh == 3 and kw == 3)   # ... also with two CTAs per SM (tiles <= 128 wide: n >= 2 splits any Cout here)
+    halo = kh == 3 and kw == 3 and stride == 1
+    assert (3 in {k[3] for k in seen}) == halo                    # ... and the halo mode for every stride-1 3x3 case
+    assert (4 in {k[3] for k in seen}) == halo                    # ... also with two CTAs per SM (tiles <= 128 wide: n >= 2 splits any Cout here)
     assert len({k[4] for k in seen}) >= 2                         # ... and more than one commit-group size
-    if kh == 3 and kw == 3 and cin == 64 and cout <= 128 and dil == 1:
+    if halo and cin == 64 and cout <= 128 and dil == 1:
         assert 5 in {k[3] for k in seen}                           # resident weights (they fit: 9 x Cout x 128 B beside three patches)
 
 
