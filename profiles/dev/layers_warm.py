@@ -1,4 +1,4 @@
-"""Development aid: per-op warm times (20 launches back to back) of the 512x512 fp16 B=16 engine (BASELINE config 3), sorted."""
+"""Development aid: per-op warm times (20 launches back to back) of an engine, sorted (default: 512x512 fp16 B=16, BASELINE config 3; LAYERS_SIZE / LAYERS_PRECISION / LAYERS_BATCH select another)."""
 import sys
 
 import torch
@@ -10,7 +10,9 @@ import bench  # noqa
 def main():
     dev = torch.device('cuda:0')
     torch.cuda.set_device(dev)
-    w = bench.Workload(512, 'fp16', 16, dev, 'linear', 0)
+    import os
+    size, prec, batch = (int(os.environ.get("LAYERS_SIZE", "512")), os.environ.get("LAYERS_PRECISION", "fp16"), int(os.environ.get("LAYERS_BATCH", "16")))
+    w = bench.Workload(size, prec, batch, dev, "linear" if size == 512 else "hard", 0)
     eng = w.eng
     for _ in range(3):
         eng.load_input(w.x_dev); eng.launch()
