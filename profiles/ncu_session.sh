@@ -9,7 +9,7 @@ ncu --profile-from-start off --metrics $M --clock-control none -c 400 --csv --lo
 ncu --profile-from-start off --metrics $M --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches_512.csv python bench.py --quick --no-graph --size 512 --batch 16 --precision fp16 --steps 2 --warmup 3 > gpurun_out/${T}_ncu_launch_512.log 2>&1
 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'conv_tc_kernel|conv_halo|conv_stem2' -c 16 -f -o /tmp/rep/conv python bench.py --quick --no-graph --steps 1 --warmup 3 > gpurun_out/${T}_ncu_conv.log 2>&1
 ncu -i /tmp/rep/conv.ncu-rep --page raw --csv > gpurun_out/${T}_conv_raw.csv 2>/dev/null
-ncu --profile-from-start off --set full --clock-control none -k regex:attention -c 1 -f -o /tmp/rep/attn python bench.py --quick --no-graph --steps 1 --warmup 3 > gpurun_out/${T}_ncu_attn.log 2>&1
+ncu --profile-from-start off --set full --clock-control none -k regex:"attention_tc|proj_kv_tc" -c 2 -f -o /tmp/rep/attn python bench.py --quick --no-graph --steps 1 --warmup 3 > gpurun_out/${T}_ncu_attn.log 2>&1
 ncu -i /tmp/rep/attn.ncu-rep --page raw --csv > gpurun_out/${T}_attn_raw.csv 2>/dev/null
 tail -n 3 gpurun_out/${T}_ncu_launch.log gpurun_out/${T}_ncu_conv.log gpurun_out/${T}_ncu_attn.log
 wc -l gpurun_out/${T}_*.csv
