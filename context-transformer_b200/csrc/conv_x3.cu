@@ -221,8 +221,8 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const int per_img = p.tiles_x * p.tiles_y;
         n_img = mt / per_img;
         const int t = mt - n_img * per_img;
-        y0 = (t / p.tiles_x) * p.TH - p.pad_h;
-        x0 = (t % p.tiles_x) * p.TW - p.pad_w;
+        y0 = (t / p.tiles_x) * p.TH * p.stride - p.pad_h;       // input coordinates of the patch's first output pixel
+        x0 = (t % p.tiles_x) * p.TW * p.stride - p.pad_w;
       }
       int cc = 0, ky = 0, kx = 0;
       for (int it = 0; it < nk; ++it, ++g) {
@@ -529,7 +529,7 @@ extern "C" int ctx_conv2d_x3_plan_create(const CtxConvParams* p, int n_tiles_n, 
   int tw = 0, th = 0;
   if (p->in_nchw) t.a_mode = A_STEM;
   else if (flat_eligible(p)) { t.a_mode = A_TMA; tw = 128; th = 1; }
-  else t.a_mode = choose_patch(p, &tw, &th, 150) ? A_TMA : A_GATHER;
+  else t.a_mode = choose_patch(p, &tw, &th, 150, 2) ? A_TMA : A_GATHER;      // (stride 2: the tensor maps walk the input with a traversal stride)
   t.flat = t.a_mode == A_TMA && flat_eligible(p);
   t.TW = tw; t.TH = th;
   const bool patches = t.a_mode == A_TMA;
@@ -555,8 +555,9 @@ extern "C" int ctx_conv2d_x3_plan_create(const CtxConvParams* p, int n_tiles_n, 
       rc = encode_nhwc_sw128(&pl->tmap_a, p->in, false, 1, 1, t.M, p->in_cstride, p->in_coffset + p->Cin, 128u, 1u);
       if (!rc) rc = encode_nhwc_sw128(&pl->tmap_a_lo, p->in_lo, false, 1, 1, t.M, p->in_cstride, p->in_coffset + p->Cin, 128u, 1u);
     } else {
-      rc = encode_nhwc_sw128(&pl->tmap_a, p->in, false, p->N, p->H, p->W, p->in_cstride, p->in_coffset + p->Cin, (unsigned)tw, (unsigned)th);
-      if (!rc) rc = encode_nhwc_sw128(&pl->tmap_a_lo, p->in_lo, false, p->N, p->H, p->W, p->in_cstride, p->in_coffset + p->Cin, (unsigned)tw, (unsigned)th);
+      rc = encode_nhwc_sw128(&pl->tmap_a, p->in, false, p->N, p->H, p->W, p->in_cstride, p->in_coffset + p->Cin, (unsigned)tw, (unsigned)th, (unsigned)p->stride);
+      if (!rc) rc = encode_nhwc_sw128(&pl->tmap_a_lo, p->in_lo, false, p->N, p->H, p->W, p->in_cstride, p->in_coffset + p->Cin, (unsigned)tw, (unsigned)th,
+                                      (unsigned)p->stride);
     }
   }
   if (rc) { delete pl; return rc; }

@@ -98,7 +98,8 @@ def test_conv_kernel_vs_torch(case, precision):
         assert torch.allclose(got, want, rtol=1e-2, atol=1e-2)            # bf16 output rounding (8 bits)
 
 
-X3_CASES = CONV_CASES + [(512, 512, 3, 1, 1, 1, 19), (1024, 264, 1, 1, 0, 1, 9), (48, 64, 3, 2, 1, 1, 9), (32, 48, 3, 1, 1, 1, 8)]
+X3_CASES = CONV_CASES + [(512, 512, 3, 1, 1, 1, 19), (1024, 264, 1, 1, 0, 1, 9), (48, 64, 3, 2, 1, 1, 9), (32, 48, 3, 1, 1, 1, 8),
+                         (128, 256, 3, 2, 1, 1, 19), (256, 192, 1, 2, 0, 1, 19)]      # stride 2 through strided TMA patches
 
 
 @pytest.mark.parametrize('case', X3_CASES, ids=[str(c) for c in X3_CASES])
