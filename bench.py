@@ -338,7 +338,11 @@ def measure(w, steps, warmup, world, rank, full=True, layers_path=None, quick=Fa
     # through the 126 MB L2, so nothing survives from one step to the next.
     copy_stream = torch.cuda.Stream(device=dev)
     post_stream = torch.cuda.Stream(device=dev)
-    post_on_own_stream = os.environ.get('CTX_BENCH_POST_STREAM', 'own') == 'own'      # measured: 10.10 k img/s on its own stream, 9.86 k behind the forward on the main one
+    # hard NMS (short kernels): DetectPost on its own stream beside the next forward (10.10 k img/s against 9.86 k behind it on the main one).
+    # Soft-NMS: the per-class kernel keeps 80 KB of shared memory and up to 512 threads per CTA for as long as its list takes (up to
+    # 0.9 ms), which no ~200 KB conv CTA can share an SM with — beside the next forward it gave 4.0 .. 4.7 k img/s from run to run
+    # (one sample of 0.9 k) against a steady 4.2 k behind it, so that configuration keeps it on the main stream.
+    post_on_own_stream = os.environ.get('CTX_BENCH_POST_STREAM', 'own' if w.nms_kind == 'hard' else 'main') == 'own'
     x_bufs = [torch.empty_like(w.x_host, device=dev) for _ in range(2)]
     out_bufs = [torch.empty_like(out_host).pin_memory() for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
@@ -421,9 +425,10 @@ def measure(w, steps, warmup, world, rank, full=True, layers_path=None, quick=Fa
                   'ms_per_step': ms_e2e / steps, 'serial_ms_per_step': ms_e2e_serial / steps,
                   'workers': workers,
                   'includes': 'every step: H2D of the pinned input (side stream, overlapping the previous batch), forward '
-                              '%s, DetectPost (decode+score+NMS+top-200; on its own stream beside the next forward), %sD2H of the '
+                              '%s, DetectPost (decode+score+NMS+top-200; %s), %sD2H of the '
                               'records; serial_ms_per_step is the same chain with one batch in flight'
                               % ('(two replicas of the compiled network on two streams take alternate batches)' if workers == 2 else '(one stream)',
+                                 'on its own stream beside the next forward' if post_on_own_stream else 'behind the forward on the same stream',
                                  'all-gather, ' if world > 1 else '')}
     out['detections_per_batch_e2e'] = n_det[0]
 
